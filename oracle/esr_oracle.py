@@ -1,0 +1,368 @@
+"""CPU oracle for the x4 efficient-SR hot path (IMDN / RFDN / RLFN / BSRN forward).
+
+TEST INFRASTRUCTURE ONLY.  Nothing in the product package (`ntire2022_esr_b200/`) may import this
+module; only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference`
+legs do, and only as the checker or the timed CPU arm.
+
+This is a numpy restatement of the reference's PyTorch graphs.  The reference itself contains no
+arithmetic: every op is delegated to PyTorch ATen (third-party, un-pinned by the reference; the
+container has torch 2.11.0+cu128).  The ATen ops used on the path are restated here from their
+published definitions (cross-correlation conv2d with zero padding, max_pool2d floor mode,
+upsample_bilinear2d align_corners=False, pixel_shuffle, leaky_relu, exact-erf GELU, sigmoid).
+
+Parity pin: `tests/golden/*.npz` hold outputs of the UNMODIFIED reference modules
+(`/root/reference/models/...` + `model_zoo/*.pth`, run through `test_demo.select_model/forward`)
+produced by `tests/golden/make_golden.py`; `tests/test_oracle.py` checks this file against them.
+
+All functions take NCHW arrays; `dtype` selects float32 (default, like the reference) or float64
+(tie-breaker).  Reference citations are relative to /root/reference.
+"""
+from __future__ import annotations
+
+import math
+import numpy as np
+
+try:  # exact erf for nn.GELU(approximate='none')
+    from scipy.special import erf as _erf
+except Exception:  # pragma: no cover
+    _erf = np.vectorize(math.erf)
+
+
+# ------------------------------------------------------------------------------------------------
+# primitive ops (ATen semantics)
+# ------------------------------------------------------------------------------------------------
+def conv2d(x, w, b=None, stride=1, padding=0, groups=1):
+    """torch.nn.functional.conv2d (cross-correlation, zero padding).  x (N,C,H,W), w (O,C/g,kh,kw)."""
+    n, c, h, wd = x.shape
+    o, cg, kh, kw = w.shape
+    if padding:
+        x = np.pad(x, ((0, 0), (0, 0), (padding, padding), (padding, padding)))
+    ho = (h + 2 * padding - kh) // stride + 1
+    wo = (wd + 2 * padding - kw) // stride + 1
+    if groups == 1:
+        assert cg == c
+        # accumulate tap by tap: y[n,o,:,:] += w[o,:,i,j] . x[n,:,i::s,j::s]
+        y = np.zeros((n, o, ho, wo), dtype=x.dtype)
+        for i in range(kh):
+            for j in range(kw):
+                xs = x[:, :, i:i + (ho - 1) * stride + 1:stride, j:j + (wo - 1) * stride + 1:stride]
+                y += np.einsum("oc,nchw->nohw", w[:, :, i, j], xs, optimize=True)
+    else:
+        assert groups == c == o and cg == 1, "only depthwise grouping is on the path"
+        y = np.zeros((n, o, ho, wo), dtype=x.dtype)
+        for i in range(kh):
+            for j in range(kw):
+                xs = x[:, :, i:i + (ho - 1) * stride + 1:stride, j:j + (wo - 1) * stride + 1:stride]
+                y += w[None, :, 0, i, j, None, None] * xs
+    if b is not None:
+        y += b[None, :, None, None]
+    return y
+
+
+def linear_nchw(x, w, b):
+    """nn.Linear applied on the channel axis of an NCHW tensor (the reference permutes to NHWC,
+    models/team18_bsrn.py:82-88,110,150) == 1x1 conv with w (O,I)."""
+    return np.einsum("oc,nchw->nohw", w, x, optimize=True) + b[None, :, None, None]
+
+
+def leaky_relu(x, slope):
+    return np.where(x >= 0, x, x * x.dtype.type(slope))
+
+
+def relu(x):
+    return np.maximum(x, 0)
+
+
+def gelu(x):
+    """nn.GELU() default approximate='none': 0.5*x*(1+erf(x/sqrt(2)))."""
+    return (0.5 * x * (1.0 + _erf(x.astype(np.float64) / math.sqrt(2.0)))).astype(x.dtype)
+
+
+def sigmoid(x):
+    return (1.0 / (1.0 + np.exp(-x.astype(np.float64)))).astype(x.dtype)
+
+
+def max_pool2d(x, k, s):
+    """F.max_pool2d(kernel_size=k, stride=s), padding 0, floor mode."""
+    n, c, h, w = x.shape
+    ho = (h - k) // s + 1
+    wo = (w - k) // s + 1
+    if ho < 1 or wo < 1:
+        raise ValueError(f"max_pool2d: input {h}x{w} smaller than window {k}")
+    y = np.full((n, c, ho, wo), -np.inf, dtype=x.dtype)
+    for i in range(k):
+        for j in range(k):
+            y = np.maximum(y, x[:, :, i:i + (ho - 1) * s + 1:s, j:j + (wo - 1) * s + 1:s])
+    return y
+
+
+def _bilinear_axis(n_in, n_out, dtype):
+    d = np.arange(n_out, dtype=np.float64)
+    src = np.maximum((d + 0.5) * (n_in / n_out) - 0.5, 0.0)
+    i0 = np.minimum(np.floor(src).astype(np.int64), n_in - 1)
+    i1 = np.minimum(i0 + 1, n_in - 1)
+    lam = (src - i0).astype(dtype)
+    return i0, i1, lam
+
+
+def interpolate_bilinear(x, size):
+    """F.interpolate(mode='bilinear', align_corners=False)."""
+    h_out, w_out = size
+    n, c, h, w = x.shape
+    y0, y1, ly = _bilinear_axis(h, h_out, x.dtype)
+    x0, x1, lx = _bilinear_axis(w, w_out, x.dtype)
+    top = x[:, :, y0, :]
+    bot = x[:, :, y1, :]
+    rows = top * (1 - ly)[None, None, :, None] + bot * ly[None, None, :, None]
+    left = rows[:, :, :, x0]
+    right = rows[:, :, :, x1]
+    return left * (1 - lx)[None, None, None, :] + right * lx[None, None, None, :]
+
+
+def pixel_shuffle(x, r):
+    """nn.PixelShuffle(r): out[b,c,r*h+i,r*w+j] = in[b, c*r*r + i*r + j, h, w]."""
+    n, c, h, w = x.shape
+    co = c // (r * r)
+    return x.reshape(n, co, r, r, h, w).transpose(0, 1, 4, 2, 5, 3).reshape(n, co, h * r, w * r)
+
+
+def _cast(weights, dtype):
+    return {k: np.asarray(v, dtype=dtype) for k, v in weights.items()}
+
+
+def _conv(wt, name, x, stride=1, padding=0, groups=1):
+    return conv2d(x, wt[name + ".weight"], wt[name + ".bias"], stride, padding, groups)
+
+
+# ------------------------------------------------------------------------------------------------
+# RFDN  (models/rfdn_baseline/RFDN.py:29-41, block.py:117-129,148-166)
+# ------------------------------------------------------------------------------------------------
+def _esa_rfdn(wt, p, x):
+    """ESA.forward, models/rfdn_baseline/block.py:117-129."""
+    c1_ = _conv(wt, p + "conv1", x)
+    c1 = _conv(wt, p + "conv2", c1_, stride=2, padding=0)
+    v_max = max_pool2d(c1, 7, 3)
+    v_range = relu(_conv(wt, p + "conv_max", v_max, padding=1))
+    c3 = relu(_conv(wt, p + "conv3", v_range, padding=1))
+    c3 = _conv(wt, p + "conv3_", c3, padding=1)
+    c3 = interpolate_bilinear(c3, x.shape[2:])
+    cf = _conv(wt, p + "conv_f", c1_)
+    c4 = _conv(wt, p + "conv4", c3 + cf)
+    return x * sigmoid(c4)
+
+
+def _rfdb(wt, p, x, slope=0.05):
+    """RFDB.forward, models/rfdn_baseline/block.py:148-166 (residual add BEFORE the activation)."""
+    d1 = leaky_relu(_conv(wt, p + "c1_d", x), slope)
+    r1 = leaky_relu(_conv(wt, p + "c1_r", x, padding=1) + x, slope)
+    d2 = leaky_relu(_conv(wt, p + "c2_d", r1), slope)
+    r2 = leaky_relu(_conv(wt, p + "c2_r", r1, padding=1) + r1, slope)
+    d3 = leaky_relu(_conv(wt, p + "c3_d", r2), slope)
+    r3 = leaky_relu(_conv(wt, p + "c3_r", r2, padding=1) + r2, slope)
+    r4 = leaky_relu(_conv(wt, p + "c4", r3, padding=1), slope)
+    out = np.concatenate([d1, d2, d3, r4], axis=1)
+    return _esa_rfdn(wt, p + "esa.", _conv(wt, p + "c5", out))
+
+
+def rfdn_forward(weights, x, dtype=np.float32, return_intermediates=False):
+    """RFDN.forward, models/rfdn_baseline/RFDN.py:29-41."""
+    wt = _cast(weights, dtype)
+    x = np.asarray(x, dtype=dtype)
+    fea = _conv(wt, "fea_conv", x, padding=1)
+    b1 = _rfdb(wt, "B1.", fea)
+    b2 = _rfdb(wt, "B2.", b1)
+    b3 = _rfdb(wt, "B3.", b2)
+    b4 = _rfdb(wt, "B4.", b3)
+    out_b = leaky_relu(_conv(wt, "c.0", np.concatenate([b1, b2, b3, b4], axis=1)), 0.05)
+    out_lr = _conv(wt, "LR_conv", out_b, padding=1) + fea
+    y = pixel_shuffle(_conv(wt, "upsampler.0", out_lr, padding=1), 4)
+    if return_intermediates:
+        return y, dict(fea=fea, b1=b1, b2=b2, b3=b3, b4=b4, out_b=out_b, out_lr=out_lr)
+    return y
+
+
+# ------------------------------------------------------------------------------------------------
+# IMDN  (models/imdn_baseline.py:32-65, models/basicblock.py:191-205,230-265,446-449)
+# ------------------------------------------------------------------------------------------------
+def _imdb(wt, p, x, slope=0.05, d_nc=16):
+    """IMDBlock.forward, models/basicblock.py:259-265: the split is taken AFTER the LeakyReLU."""
+    t = leaky_relu(_conv(wt, p + "conv1.0", x, padding=1), slope)
+    d1, r1 = t[:, :d_nc], t[:, d_nc:]
+    t = leaky_relu(_conv(wt, p + "conv2.0", r1, padding=1), slope)
+    d2, r2 = t[:, :d_nc], t[:, d_nc:]
+    t = leaky_relu(_conv(wt, p + "conv3.0", r2, padding=1), slope)
+    d3, r3 = t[:, :d_nc], t[:, d_nc:]
+    d4 = _conv(wt, p + "conv4", r3, padding=1)
+    res = _conv(wt, p + "conv1x1", np.concatenate([d1, d2, d3, d4], axis=1))
+    return x + res
+
+
+def imdn_forward(weights, x, dtype=np.float32, nb=None):
+    """IMDN.forward, models/imdn_baseline.py:63-65 with the Sequential built at :46-61."""
+    wt = _cast(weights, dtype)
+    x = np.asarray(x, dtype=dtype)
+    if nb is None:
+        nb = sum(1 for k in wt if k.startswith("model.1.sub.") and k.endswith(".conv1x1.weight"))
+    head = _conv(wt, "model.0", x, padding=1)
+    t = head
+    for i in range(nb):
+        t = _imdb(wt, f"model.1.sub.{i}.", t)
+    t = _conv(wt, f"model.1.sub.{nb}", t, padding=1)
+    t = head + t                                    # ShortcutBlock, basicblock.py:197-199
+    return pixel_shuffle(_conv(wt, "model.2", t, padding=1), 4)
+
+
+# ------------------------------------------------------------------------------------------------
+# RLFN  (models/team04_rlfn.py:76-89,109-122,141-152)
+# ------------------------------------------------------------------------------------------------
+def _esa_rlfn(wt, p, x):
+    """slim ESA, models/team04_rlfn.py:76-89: only conv3 after the pool, no ReLU."""
+    c1_ = _conv(wt, p + "conv1", x)
+    c1 = _conv(wt, p + "conv2", c1_, stride=2, padding=0)
+    v_max = max_pool2d(c1, 7, 3)
+    c3 = _conv(wt, p + "conv3", v_max, padding=1)
+    c3 = interpolate_bilinear(c3, x.shape[2:])
+    cf = _conv(wt, p + "conv_f", c1_)
+    c4 = _conv(wt, p + "conv4", c3 + cf)
+    return x * sigmoid(c4)
+
+
+def _rlfb(wt, p, x, slope=0.05):
+    """RLFB.forward, models/team04_rlfn.py:109-122."""
+    t = leaky_relu(_conv(wt, p + "c1_r", x, padding=1), slope)
+    t = leaky_relu(_conv(wt, p + "c2_r", t, padding=1), slope)
+    t = leaky_relu(_conv(wt, p + "c3_r", t, padding=1), slope)
+    t = t + x
+    return _esa_rlfn(wt, p + "esa.", _conv(wt, p + "c5", t))
+
+
+def rlfn_forward(weights, x, dtype=np.float32):
+    """RLFN_cut.forward, models/team04_rlfn.py:141-152."""
+    wt = _cast(weights, dtype)
+    x = np.asarray(x, dtype=dtype)
+    fea = _conv(wt, "fea_conv", x, padding=1)
+    t = fea
+    for b in ("B1.", "B2.", "B3.", "B4."):
+        t = _rlfb(wt, b, t)
+    out_lr = _conv(wt, "LR_conv", t, padding=1) + fea
+    return pixel_shuffle(_conv(wt, "upsampler.0", out_lr, padding=1), 4)
+
+
+# ------------------------------------------------------------------------------------------------
+# BSRN  (models/team18_bsrn.py:82-88,109-122,150-172,217-236)
+# ------------------------------------------------------------------------------------------------
+def _bsconvu(wt, p, x):
+    """BSConvU.forward, team18_bsrn.py:82-88: pointwise Linear THEN depthwise 3x3 (zero pad 1)."""
+    t = linear_nchw(x, wt[p + "pw.weight"], wt[p + "pw.bias"])
+    return conv2d(t, wt[p + "dw.weight"], wt[p + "dw.bias"], 1, 1, groups=t.shape[1])
+
+
+def _lin(wt, name, x):
+    return linear_nchw(x, wt[name + ".weight"], wt[name + ".bias"])
+
+
+def _esa_bsrn(wt, p, x):
+    """ESA.forward, team18_bsrn.py:109-122."""
+    c1_ = _lin(wt, p + "conv1", x)
+    c1 = _conv(wt, p + "conv2", c1_, stride=2, padding=0)
+    v_max = max_pool2d(c1, 7, 3)
+    v_range = gelu(_bsconvu(wt, p + "conv_max.", v_max))
+    c3 = gelu(_bsconvu(wt, p + "conv3.", v_range))
+    c3 = _bsconvu(wt, p + "conv3_.", c3)
+    c3 = interpolate_bilinear(c3, x.shape[2:])
+    cf = _lin(wt, p + "conv_f", c1_)
+    c4 = _lin(wt, p + "conv4", c3 + cf)
+    return x * sigmoid(c4)
+
+
+def _rfdb_bsrn(wt, p, x):
+    """RFDB.forward, team18_bsrn.py:150-172."""
+    d1 = gelu(_lin(wt, p + "c1_d", x))
+    r1 = gelu(_bsconvu(wt, p + "c1_r.", x) + x)
+    d2 = gelu(_lin(wt, p + "c2_d", r1))
+    r2 = gelu(_bsconvu(wt, p + "c2_r.", r1) + r1)
+    d3 = gelu(_lin(wt, p + "c3_d", r2))
+    r3 = gelu(_bsconvu(wt, p + "c3_r.", r2) + r2)
+    r4 = gelu(_bsconvu(wt, p + "c4.", r3))
+    out = _lin(wt, p + "c5", np.concatenate([d1, d2, d3, r4], axis=1))
+    fused = _esa_bsrn(wt, p + "esa.", out) * wt[p + "cw"].reshape(1, -1, 1, 1)
+    return _lin(wt, p + "conv_out", fused) + x
+
+
+def bsrn_forward(weights, x, dtype=np.float32):
+    """BSRN.forward, team18_bsrn.py:217-236 (num_feat=48, num_block=5, test_demo.py:155-156)."""
+    wt = _cast(weights, dtype)
+    x = np.asarray(x, dtype=dtype)
+    x4 = np.concatenate([x, x, x, x], axis=1)
+    fea = _bsconvu(wt, "fea_conv.", x4)
+    outs = []
+    t = fea
+    nblk = sum(1 for k in wt if k.endswith(".cw"))
+    for i in range(1, nblk + 1):
+        t = _rfdb_bsrn(wt, f"B{i}.", t)
+        outs.append(t)
+    out_b = gelu(_lin(wt, "c1", np.concatenate(outs, axis=1)))
+    out_lr = _bsconvu(wt, "c2.", out_b) + fea
+    return pixel_shuffle(_conv(wt, "upsampler.upsampleOneStep.0", out_lr, padding=1), 4)
+
+
+# ------------------------------------------------------------------------------------------------
+# registry mirroring test_demo.select_model (test_demo.py:13-30,52-58,150-157)
+# ------------------------------------------------------------------------------------------------
+MODELS = {
+    -1: dict(arch="imdn", name="-1_IMDN_baseline", data_range=1.0, weights="imdn_baseline", fn=imdn_forward),
+    0: dict(arch="rfdn", name="00_RFDN_baseline", data_range=255.0, weights="rfdn_baseline", fn=rfdn_forward),
+    4: dict(arch="rlfn", name="04_RLFN", data_range=255.0, weights="team04_rlfn", fn=rlfn_forward),
+    18: dict(arch="bsrn", name="18_RFDNFINALB5", data_range=1.0, weights="team18_bsrn", fn=bsrn_forward),
+}
+FORWARD = {"imdn": imdn_forward, "rfdn": rfdn_forward, "rlfn": rlfn_forward, "bsrn": bsrn_forward}
+
+
+def forward(arch, weights, x, dtype=np.float32):
+    return FORWARD[arch](weights, x, dtype=dtype)
+
+
+def forward_tiled(arch, weights, x, tile, tile_overlap=32, scale=4, dtype=np.float32):
+    """test_demo.forward tiled branch, test_demo.py:368-389 (E/W accumulate and divide)."""
+    x = np.asarray(x, dtype=dtype)
+    b, c, h, w = x.shape
+    tile = min(tile, h, w)
+    stride = tile - tile_overlap
+    hs = list(range(0, h - tile, stride)) + [h - tile]
+    ws = list(range(0, w - tile, stride)) + [w - tile]
+    e = np.zeros((b, c, h * scale, w * scale), dtype=dtype)
+    wsum = np.zeros_like(e)
+    for hi in hs:
+        for wi in ws:
+            o = forward(arch, weights, x[..., hi:hi + tile, wi:wi + tile], dtype=dtype)
+            e[..., hi * scale:(hi + tile) * scale, wi * scale:(wi + tile) * scale] += o
+            wsum[..., hi * scale:(hi + tile) * scale, wi * scale:(wi + tile) * scale] += 1
+    return e / wsum
+
+
+def tensor2uint(y, data_range):
+    """utils/utils_image.py:204-208 for a (1,3,H,W) array -> HWC uint8."""
+    img = np.clip(np.asarray(y, dtype=np.float32)[0], 0, data_range).transpose(1, 2, 0)
+    return np.uint8(np.round(img * np.float32(255.0) / np.float32(data_range)))
+
+
+def uint2tensor4(img, data_range):
+    """utils/utils_image.py:190-193: HWC uint8 -> (1,3,H,W) float32 scaled to [0,data_range]."""
+    return (img.astype(np.float32).transpose(2, 0, 1) / np.float32(255.0 / data_range))[None]
+
+
+def psnr(a, b, border=0, peak=255.0):
+    """utils/utils_image.py:490-503."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    if border:
+        a = a[..., border:-border, border:-border] if a.ndim == 4 else a[border:-border, border:-border]
+        b = b[..., border:-border, border:-border] if b.ndim == 4 else b[border:-border, border:-border]
+    mse = np.mean((a - b) ** 2)
+    return float("inf") if mse == 0 else 20 * math.log10(peak / math.sqrt(mse))
+
+
+def load_weights(path):
+    """Load an .npz written by tests/golden/make_golden.py (state-dict names -> fp32 arrays)."""
+    with np.load(path) as z:
+        return {k: z[k] for k in z.files}

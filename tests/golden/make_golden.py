@@ -1,0 +1,92 @@
+"""Generate golden fixtures from the UNMODIFIED reference (run in the build container only).
+
+    python tests/golden/make_golden.py            # needs /root/reference (read-only)
+
+Imports the reference's own `test_demo.select_model` / `forward` (SURVEY Appendix A recipe: stub
+matplotlib, force map_location, chdir to the reference root) and writes, next to this file:
+
+  weights/<name>.npz      state-dicts of the four in-scope checkpoints as fp32 numpy arrays
+  test_bmp.npz            utils/test.bmp as uint8 HWC RGB (via the reference's imread_uint)
+  ref_<arch>_small.npz    seeded small inputs + FULL reference outputs (several odd sizes)
+  ref_<arch>_256.npz      reference output on test.bmp (256x256): crops, strided subsample, stats
+  ref_rfdn_tiled.npz      reference tiled forward (tile=32, overlap=8) on a 48x40 input
+
+Nothing at test/bench time reads /root/reference; these files are the pin.
+"""
+import copy
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = os.environ.get("ESR_REFERENCE_DIR", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+for m in ("matplotlib", "matplotlib.pyplot"):
+    sys.modules.setdefault(m, types.ModuleType(m))
+sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+sys.dont_write_bytecode = True
+sys.path.insert(0, REF)
+os.chdir(REF)
+_load = torch.load
+torch.load = lambda p, **k: _load(p, **{"map_location": "cpu", **k})
+import test_demo  # noqa: E402
+from utils import utils_image as util  # noqa: E402
+
+torch.set_num_threads(os.cpu_count())
+
+MODELS = {-1: ("imdn", "imdn_baseline.pth"), 0: ("rfdn", "rfdn_baseline.pth"),
+          4: ("rlfn", "team04_rlfn.pth"), 18: ("bsrn", "team18_bsrn.pth")}
+SMALL_SIZES = [(15, 15), (24, 20), (33, 47), (64, 64)]
+CROPS = [(0, 0), (0, 992), (992, 0), (992, 992), (500, 500), (0, 480), (700, 0), (301, 777)]
+
+
+def main():
+    os.makedirs(os.path.join(HERE, "weights"), exist_ok=True)
+    img = util.imread_uint(os.path.join(REF, "utils", "test.bmp"), n_channels=3)
+    np.savez_compressed(os.path.join(HERE, "test_bmp.npz"), img=img)
+    for mid, (arch, fname) in MODELS.items():
+        args = types.SimpleNamespace(model_id=mid)
+        model, name, data_range, tile = test_demo.select_model(args, torch.device("cpu"))
+        sd = {k: v.detach().cpu().numpy().astype(np.float32) for k, v in model.state_dict().items()}
+        np.savez(os.path.join(HERE, "weights", fname.replace(".pth", ".npz")), **sd)
+        small = {"data_range": np.float32(data_range), "name": np.array(name)}
+        for i, (h, w) in enumerate(SMALL_SIZES):
+            g = torch.Generator().manual_seed(100 + i)
+            nb = 2 if i == 1 else 1
+            x = torch.rand(nb, 3, h, w, generator=g) * data_range
+            with torch.no_grad():
+                y = test_demo.forward(x, model, tile)
+            small[f"x{i}"] = x.numpy()
+            small[f"y{i}"] = y.numpy()
+        np.savez_compressed(os.path.join(HERE, f"ref_{arch}_small.npz"), **small)
+
+        x = util.uint2tensor4(img, data_range)
+        with torch.no_grad():
+            y = test_demo.forward(x, model, tile).numpy().copy()
+            y64 = copy.deepcopy(model).double()(x.double()).numpy().copy()
+        big = {"data_range": np.float32(data_range),
+               "crops_yx": np.array(CROPS, dtype=np.int32),
+               "crops": np.stack([y[0, :, a:a + 32, b:b + 32] for a, b in CROPS]),
+               "sub16": y[0, :, ::16, ::16].copy(),
+               "sum_c": y.astype(np.float64).sum(axis=(0, 2, 3)),
+               "abs_sum_c": np.abs(y.astype(np.float64)).sum(axis=(0, 2, 3)),
+               "minmax": np.array([y.min(), y.max()], dtype=np.float32),
+               "uint8_sub": util.tensor2uint(torch.from_numpy(y.copy()), data_range)[::8, ::8].copy()}
+        if y64 is not None:
+            big["fp32_vs_fp64_maxabs"] = np.float64(np.abs(y - y64).max())
+        np.savez_compressed(os.path.join(HERE, f"ref_{arch}_256.npz"), **big)
+        print(name, "ok; fp32-vs-fp64 max abs", big.get("fp32_vs_fp64_maxabs"))
+
+        if arch == "rfdn":
+            g = torch.Generator().manual_seed(7)
+            xt = torch.rand(1, 3, 48, 40, generator=g) * data_range
+            with torch.no_grad():
+                yt = test_demo.forward(xt, model, tile=32, tile_overlap=8)
+            np.savez_compressed(os.path.join(HERE, "ref_rfdn_tiled.npz"), x=xt.numpy(), y=yt.numpy())
+
+
+if __name__ == "__main__":
+    main()
