@@ -1,0 +1,88 @@
+/* esr_b200 — C ABI of the B200-native x4 efficient-SR inference engine.
+ *
+ * This is the drop-in boundary for the hot path of ofsoundof/NTIRE2022_ESR: the call
+ * `model(img_lq)` made by `forward()` (reference test_demo.py:364-367) on the module returned by
+ * `select_model()` (test_demo.py:13-341).  The reference has no FFI of its own (it is pure PyTorch);
+ * the entry points below are what a Python/ctypes binding of that path needs, one per step of
+ * `select_model` (construct -> load_state_dict(strict=True) -> eval/to(device)) and of `forward`.
+ * The Python mirror lives in ntire2022_esr_b200/engine.py; INTEGRATION.md shows the stub a
+ * maintainer of the reference would add to test_demo.py.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a negative
+ * ESR_E_* code and never throws/aborts; esr_last_error() gives the message.  A handle is bound to
+ * one CUDA device, calls on it are stream-ordered and not re-entrant.  Device buffers (input,
+ * output, workspace) are owned by the caller; packed weights and TMA descriptors by the engine.
+ */
+#ifndef ESR_B200_H_
+#define ESR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct esr_engine esr_handle;
+
+/* architectures: the four networks SURVEY.md section 8(a) puts on the hot path */
+enum { ESR_ARCH_IMDN = 0, ESR_ARCH_RFDN = 1, ESR_ARCH_RLFN = 2, ESR_ARCH_BSRN = 3 };
+/* I/O + storage dtype of a forward call (math is fp32-accumulate in both) */
+enum { ESR_DTYPE_F32 = 0, ESR_DTYPE_F16 = 1 };
+enum {
+  ESR_OK = 0,
+  ESR_E_INVALID = -1,   /* bad argument / unsupported shape */
+  ESR_E_STATE = -2,     /* call order (e.g. forward before finalize) */
+  ESR_E_WEIGHTS = -3,   /* missing / unexpected / mis-shaped state-dict entry (strict=True) */
+  ESR_E_CUDA = -4,      /* CUDA runtime or driver error */
+  ESR_E_NOGPU = -5      /* no sm_100 device: the engine has no CPU fallback */
+};
+
+/* Replaces the module constructors at test_demo.py:22 (IMDN(nc=64, nb=8)), :29 (RFDN()),
+ * :57 (RLFN_cut()) and :155 (BSRN(num_feat=48, num_block=5)).  nf / nblocks <= 0 pick those
+ * defaults.  `device` is the CUDA ordinal the handle is bound to. */
+int esr_create(esr_handle** out, int arch, int nf, int nblocks, int device);
+
+/* Replaces `model.load_state_dict(torch.load(path), strict=True)` (test_demo.py:23,30,58,157):
+ * called once per state-dict entry with its exact reference name, a HOST fp32
+ * pointer and its shape.  Unknown names / wrong shapes are reported by esr_finalize. */
+int esr_load_weights(esr_handle* h, const char* name, const float* host_ptr, const int64_t* shape, int ndim);
+
+/* Replaces `.eval()` + `.to(device)` (test_demo.py:336-340): checks the entry set strictly, packs
+ * the weights into the engine's layouts (fp32 tables for the CUDA-core kernels, pre-swizzled fp16
+ * K-major blocks for the tcgen05 kernels) and uploads them. */
+int esr_finalize(esr_handle* h);
+
+/* Scratch bytes esr_forward needs for a (B,3,H,W) input of `dtype`; 0 on error. */
+size_t esr_workspace_bytes(esr_handle* h, int B, int H, int W, int dtype);
+
+/* Replaces `model(img_lq)` (test_demo.py:367, and :380 for each tile): in = (B,3,H,W) NCHW, values
+ * in [0,data_range]; out = (B,3,4H,4W) NCHW; both DEVICE pointers of `dtype`.  Asynchronous on
+ * `stream` (a cudaStream_t passed as void*; NULL = default stream). */
+int esr_forward(esr_handle* h, const void* in_nchw, void* out_nchw, int B, int H, int W, int dtype,
+                void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same computation with HOST buffers (pageable or pinned): the engine stages them through its own
+ * device buffers on `stream` and synchronises before returning.  This is the path a non-PyTorch
+ * caller binds; bench.py times it as the end-to-end number. */
+int esr_forward_host(esr_handle* h, const void* in_host, void* out_host, int B, int H, int W, int dtype);
+
+/* Number of kernels one esr_forward of this shape launches (0 on error); used by bench.py. */
+int esr_launch_count(esr_handle* h, int B, int H, int W, int dtype);
+/* Name of the i-th launch of that plan ("conv_tc", "conv_generic", ...), or NULL. */
+const char* esr_launch_name(esr_handle* h, int B, int H, int W, int dtype, int i);
+
+/* Runtime knobs (tuning / A-B measurements): "tc_shift_mode", "use_graph", "tc_rows_per_item". */
+int esr_set_option(esr_handle* h, const char* key, int value);
+
+const char* esr_last_error(esr_handle* h);
+void esr_destroy(esr_handle* h);
+
+/* Library-level queries (no handle): version string, and whether a usable sm_100 GPU is present. */
+const char* esr_version(void);
+int esr_device_ok(int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ESR_B200_H_ */

@@ -1,0 +1,430 @@
+// CUDA-core kernels of the SR engine (NHWC activations, fp32 math, fp32 or fp16 storage).
+// They carry the whole fp32 mode and, in fp16 mode, the small / irregular layers around the
+// tcgen05 convolutions (3-channel head, ESA attention branch, depthwise convs of BSRN).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace esr {
+
+enum Act : int { ACT_NONE = 0, ACT_LRELU = 1, ACT_RELU = 2, ACT_GELU = 3 };
+
+__device__ __forceinline__ float apply_act(float v, int act, float slope) {
+  switch (act) {
+    case ACT_LRELU: return v >= 0.f ? v : v * slope;
+    case ACT_RELU: return fmaxf(v, 0.f);
+    case ACT_GELU: return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+    default: return v;
+  }
+}
+
+// ---- 8-channel vector load/store helpers ------------------------------------------------------
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load8(const __half* p, float (&v)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __half22float2(h[i]);
+    v[2 * i] = f.x; v[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store8(__half* p, const float (&v)[8]) {
+  uint4 u;
+  __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ float ldf(const float* p) { return *p; }
+__device__ __forceinline__ float ldf(const __half* p) { return __half2float(*p); }
+__device__ __forceinline__ void stf(float* p, float v) { *p = v; }
+__device__ __forceinline__ void stf(__half* p, float v) { *p = __float2half_rn(v); }
+
+// ---------------------------------------------------------------------------------------------
+// Head: 3x3 conv (pad 1) on the NCHW 3-channel input, NHWC output with `cstore` channels
+// (channels >= cout are written as zero so padded lanes stay finite).
+// w: [27][64] fp32, index (ky*3+kx)*3+ci; bias [64].
+// ---------------------------------------------------------------------------------------------
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(128) k_head_conv(const TIn* __restrict__ in, TOut* __restrict__ out,
+                                                   const float* __restrict__ w, const float* __restrict__ bias,
+                                                   int B, int H, int W, int out_stride, int cstore) {
+  __shared__ float ws[27 * 64];
+  __shared__ float bs[64];
+  for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) ws[i] = w[i];
+  if (threadIdx.x < 64) bs[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const long long npix = (long long)B * H * W;
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= npix) return;
+  const int x = (int)(pix % W);
+  const int y = (int)((pix / W) % H);
+  const int b = (int)(pix / ((long long)W * H));
+  float xin[27];
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int yy = y + ky - 1, xx = x + kx - 1;
+      const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci)
+        xin[(ky * 3 + kx) * 3 + ci] = ok ? ldf(in + (((long long)b * 3 + ci) * H + yy) * W + xx) : 0.f;
+    }
+  TOut* o = out + pix * out_stride;
+  for (int c0 = 0; c0 < cstore; c0 += 8) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = bs[c0 + j];
+#pragma unroll
+    for (int t = 0; t < 27; ++t) {
+      const float xv = xin[t];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv, ws[t * 64 + c0 + j], acc[j]);
+    }
+    store8(o + c0, acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// BSRN head: cat(x,x,x,x) -> Linear(12->48) -> depthwise 3x3 (zero pad applied AFTER the Linear,
+// models/team18_bsrn.py:82-88,218).  wpw: [3][64] (the four replicas pre-summed), bpw[64],
+// wdw: [9][64], bdw[64].
+// ---------------------------------------------------------------------------------------------
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(128) k_bsrn_head(const TIn* __restrict__ in, TOut* __restrict__ out,
+                                                   const float* __restrict__ wpw, const float* __restrict__ bpw,
+                                                   const float* __restrict__ wdw, const float* __restrict__ bdw,
+                                                   int B, int H, int W, int out_stride, int cstore) {
+  __shared__ float s_wpw[3 * 64], s_bpw[64], s_wdw[9 * 64], s_bdw[64];
+  for (int i = threadIdx.x; i < 3 * 64; i += blockDim.x) s_wpw[i] = wpw[i];
+  for (int i = threadIdx.x; i < 9 * 64; i += blockDim.x) s_wdw[i] = wdw[i];
+  if (threadIdx.x < 64) { s_bpw[threadIdx.x] = bpw[threadIdx.x]; s_bdw[threadIdx.x] = bdw[threadIdx.x]; }
+  __syncthreads();
+  const long long npix = (long long)B * H * W;
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= npix) return;
+  const int x = (int)(pix % W);
+  const int y = (int)((pix / W) % H);
+  const int b = (int)(pix / ((long long)W * H));
+  float xin[27];
+  bool okt[9];
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int yy = y + ky - 1, xx = x + kx - 1;
+      const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+      okt[ky * 3 + kx] = ok;
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci)
+        xin[(ky * 3 + kx) * 3 + ci] = ok ? ldf(in + (((long long)b * 3 + ci) * H + yy) * W + xx) : 0.f;
+    }
+  TOut* o = out + pix * out_stride;
+  for (int c0 = 0; c0 < cstore; c0 += 8) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = s_bdw[c0 + j];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      if (!okt[t]) continue;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = c0 + j;
+        float pw = s_bpw[c];
+        pw = fmaf(xin[t * 3 + 0], s_wpw[0 * 64 + c], pw);
+        pw = fmaf(xin[t * 3 + 1], s_wpw[1 * 64 + c], pw);
+        pw = fmaf(xin[t * 3 + 2], s_wpw[2 * 64 + c], pw);
+        acc[j] = fmaf(pw, s_wdw[t * 64 + c], acc[j]);
+      }
+    }
+    store8(o + c0, acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Generic dense conv (k = 1 or 3, stride 1 or 2, zero pad) on NHWC buffers.
+//   thread = one output pixel x 16 output columns (blockIdx.y selects the 16-column group)
+//   w:    [taps][cin8][cout16] fp32 (cin8 = Cin rounded up to 8, cout16 = columns rounded to 16;
+//         rows/columns beyond the logical extent are zero)
+//   out:  NHWC (columns [0,cout16) of the group are stored) or pixel-shuffle x4 NCHW
+// residual is added before (res_after=0) or after (res_after=1) the activation.
+// ---------------------------------------------------------------------------------------------
+struct ConvGenericParams {
+  const void* in; int in_stride, in_coff, cin8;
+  void* out; int out_stride, out_coff, cout16;
+  const float* w; const float* bias;
+  const void* res; int res_stride, res_coff, res_after;
+  int act; float slope;
+  int B, Hin, Win, Hout, Wout, ksize, stride, pad;
+  int ps_mode;      // 1: out is (B,3,4H,4W) NCHW, columns are 16*c+4*i+j
+  int ps_fp32;      // dtype of the pixel-shuffled output
+};
+
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(128) k_conv_generic(const ConvGenericParams p) {
+  extern __shared__ float wsm[];  // [taps][cin8][16]
+  const int taps = p.ksize * p.ksize;
+  const int g = blockIdx.y;
+  const int nw = taps * p.cin8 * 16;
+  for (int i = threadIdx.x; i < nw; i += blockDim.x) {
+    const int r = i >> 4, c = i & 15;
+    wsm[i] = p.w[(long long)r * p.cout16 + g * 16 + c];
+  }
+  __syncthreads();
+  const long long npix = (long long)p.B * p.Hout * p.Wout;
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= npix) return;
+  const int x = (int)(pix % p.Wout);
+  const int y = (int)((pix / p.Wout) % p.Hout);
+  const int b = (int)(pix / ((long long)p.Wout * p.Hout));
+  float acc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = p.bias[g * 16 + j];
+  const TIn* in = reinterpret_cast<const TIn*>(p.in);
+  for (int ky = 0; ky < p.ksize; ++ky) {
+    const int yy = y * p.stride + ky - p.pad;
+    if (yy < 0 || yy >= p.Hin) continue;
+    for (int kx = 0; kx < p.ksize; ++kx) {
+      const int xx = x * p.stride + kx - p.pad;
+      if (xx < 0 || xx >= p.Win) continue;
+      const TIn* ip = in + (((long long)b * p.Hin + yy) * p.Win + xx) * p.in_stride + p.in_coff;
+      const float* wt = wsm + (ky * p.ksize + kx) * p.cin8 * 16;
+      for (int c0 = 0; c0 < p.cin8; c0 += 8) {
+        float xv[8];
+        load8(ip + c0, xv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4* w4 = reinterpret_cast<const float4*>(wt + (c0 + i) * 16);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 ww = w4[q];
+            acc[4 * q + 0] = fmaf(xv[i], ww.x, acc[4 * q + 0]);
+            acc[4 * q + 1] = fmaf(xv[i], ww.y, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(xv[i], ww.z, acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(xv[i], ww.w, acc[4 * q + 3]);
+          }
+        }
+      }
+    }
+  }
+  float rv[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) rv[j] = 0.f;
+  if (p.res != nullptr) {
+    const TOut* rp = reinterpret_cast<const TOut*>(p.res) + pix * p.res_stride + p.res_coff + g * 16;
+    float a[8], c[8];
+    load8(rp, a);
+    load8(rp + 8, c);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { rv[j] = a[j]; rv[8 + j] = c[j]; }
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    float v = acc[j];
+    if (!p.res_after) v += rv[j];
+    v = apply_act(v, p.act, p.slope);
+    if (p.res_after) v += rv[j];
+    acc[j] = v;
+  }
+  if (!p.ps_mode) {
+    TOut* o = reinterpret_cast<TOut*>(p.out) + pix * p.out_stride + p.out_coff + g * 16;
+    float a[8], c[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { a[j] = acc[j]; c[j] = acc[8 + j]; }
+    store8(o, a);
+    store8(o + 8, c);
+  } else {
+    // column 16*c + 4*i + j of pixel (y,x) -> out[b, c, 4y+i, 4x+j]; this thread owns channel c = g
+    const int Ho = 4 * p.Hout, Wo = 4 * p.Wout;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const long long o = (((long long)b * 3 + g) * Ho + 4 * y + i) * Wo + 4 * x;
+      if (p.ps_fp32) {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o) =
+            make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+      } else {
+        uint2 u;
+        __half2* h = reinterpret_cast<__half2*>(&u);
+        h[0] = __floats2half2_rn(acc[4 * i], acc[4 * i + 1]);
+        h[1] = __floats2half2_rn(acc[4 * i + 2], acc[4 * i + 3]);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out) + o) = u;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Depthwise 3x3 (pad 1) + bias (+ residual) + activation; thread = pixel x 8 channels.
+// w: [9][c8] fp32, bias [c8]
+// ---------------------------------------------------------------------------------------------
+struct DwParams {
+  const void* in; int in_stride, in_coff;
+  void* out; int out_stride, out_coff;
+  const void* res; int res_stride, res_coff;
+  const float* w; const float* bias;
+  int c8; int act; float slope; int B, H, W;
+};
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(128) k_dwconv3x3(const DwParams p) {
+  const int groups = p.c8 >> 3;
+  const long long total = (long long)p.B * p.H * p.W * groups;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int g = (int)(idx % groups);
+  const long long pix = idx / groups;
+  const int x = (int)(pix % p.W);
+  const int y = (int)((pix / p.W) % p.H);
+  const int b = (int)(pix / ((long long)p.W * p.H));
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = p.bias[g * 8 + j];
+  const TIn* in = reinterpret_cast<const TIn*>(p.in);
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int yy = y + ky - 1;
+    if (yy < 0 || yy >= p.H) continue;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int xx = x + kx - 1;
+      if (xx < 0 || xx >= p.W) continue;
+      float xv[8];
+      load8(in + (((long long)b * p.H + yy) * p.W + xx) * p.in_stride + p.in_coff + g * 8, xv);
+      const float* wt = p.w + (ky * 3 + kx) * p.c8 + g * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv[j], wt[j], acc[j]);
+    }
+  }
+  if (p.res != nullptr) {
+    float rv[8];
+    load8(reinterpret_cast<const TOut*>(p.res) + pix * p.res_stride + p.res_coff + g * 8, rv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += rv[j];
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = apply_act(acc[j], p.act, p.slope);
+  store8(reinterpret_cast<TOut*>(p.out) + pix * p.out_stride + p.out_coff + g * 8, acc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// max_pool2d(kernel 7, stride 3, no pad, floor) on fp32 NHWC with 16-channel pixels.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_maxpool7s3(const float* __restrict__ in, float* __restrict__ out, int B,
+                                                    int Hin, int Win, int Hout, int Wout) {
+  const long long total = (long long)B * Hout * Wout * 4;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int q = (int)(idx & 3);
+  const long long pix = idx >> 2;
+  const int x = (int)(pix % Wout);
+  const int y = (int)((pix / Wout) % Hout);
+  const int b = (int)(pix / ((long long)Wout * Hout));
+  float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  for (int i = 0; i < 7; ++i)
+    for (int j = 0; j < 7; ++j) {
+      const float4 v = *reinterpret_cast<const float4*>(
+          in + (((long long)b * Hin + 3 * y + i) * Win + 3 * x + j) * 16 + q * 4);
+      m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+    }
+  *reinterpret_cast<float4*>(out + pix * 16 + q * 4) = m;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ESA tail: y = x * sigmoid(conv4(bilinear(c3) + conv_f(c1_)))          (block.py:123-129)
+//   x   : NHWC T, `xs` channels per pixel; c1_: NHWC T, 16 ch; c3: NHWC fp32 16 ch at (H3,W3)
+//   wf  : [16][16] (in,out) fp32, bf[16];  w4: [16][64] (in,out), b4[64]
+//   thread = pixel x 16 output channels (4 threads per pixel)
+// ---------------------------------------------------------------------------------------------
+struct EsaApplyParams {
+  const void* x; int x_stride, x_coff;
+  const void* c1; int c1_stride, c1_coff;
+  const float* c3; int H3, W3;
+  void* out; int out_stride, out_coff;
+  const float* wf; const float* bf; const float* w4; const float* b4;
+  int B, H, W, f, cgroups;  // f: ESA channels (<=16); cgroups: number of 16-channel output groups
+};
+template <typename T>
+__global__ void __launch_bounds__(128) k_esa_apply(const EsaApplyParams p) {
+  __shared__ float s_wf[16 * 16], s_bf[16], s_w4[16 * 64], s_b4[64];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_wf[i] = p.wf[i];
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_w4[i] = p.w4[i];
+  if (threadIdx.x < 16) s_bf[threadIdx.x] = p.bf[threadIdx.x];
+  if (threadIdx.x < 64) s_b4[threadIdx.x] = p.b4[threadIdx.x];
+  __syncthreads();
+  const long long total = (long long)p.B * p.H * p.W * p.cgroups;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int g = (int)(idx % p.cgroups);
+  const long long pix = idx / p.cgroups;
+  const int x = (int)(pix % p.W);
+  const int y = (int)((pix / p.W) % p.H);
+  const int b = (int)(pix / ((long long)p.W * p.H));
+  // bilinear source coordinates, align_corners=False (ATen area_pixel_compute_source_index)
+  const float sy = fmaxf(((float)y + 0.5f) * ((float)p.H3 / (float)p.H) - 0.5f, 0.f);
+  const float sx = fmaxf(((float)x + 0.5f) * ((float)p.W3 / (float)p.W) - 0.5f, 0.f);
+  const int y0 = min((int)sy, p.H3 - 1), x0 = min((int)sx, p.W3 - 1);
+  const int y1 = min(y0 + 1, p.H3 - 1), x1 = min(x0 + 1, p.W3 - 1);
+  const float ly = sy - (float)y0, lx = sx - (float)x0;
+  const float* c3b = p.c3 + (long long)b * p.H3 * p.W3 * 16;
+  const float* p00 = c3b + ((long long)y0 * p.W3 + x0) * 16;
+  const float* p01 = c3b + ((long long)y0 * p.W3 + x1) * 16;
+  const float* p10 = c3b + ((long long)y1 * p.W3 + x0) * 16;
+  const float* p11 = c3b + ((long long)y1 * p.W3 + x1) * 16;
+  float c1v[16];
+  {
+    const T* cp = reinterpret_cast<const T*>(p.c1) + pix * p.c1_stride + p.c1_coff;
+    float a[8], c[8];
+    load8(cp, a);
+    load8(cp + 8, c);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { c1v[j] = a[j]; c1v[8 + j] = c[j]; }
+  }
+  float s[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    // same association as ATen: rows first (top/bottom blend), then columns
+    const float top = p00[k] * (1.f - lx) + p01[k] * lx;
+    const float bot = p10[k] * (1.f - lx) + p11[k] * lx;
+    float v = top * (1.f - ly) + bot * ly;
+    float cf = s_bf[k];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) cf = fmaf(c1v[i], s_wf[i * 16 + k], cf);
+    s[k] = (k < p.f) ? (v + cf) : 0.f;
+  }
+  float xv[16];
+  {
+    const T* xp = reinterpret_cast<const T*>(p.x) + pix * p.x_stride + p.x_coff + g * 16;
+    float a[8], c[8];
+    load8(xp, a);
+    load8(xp + 8, c);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { xv[j] = a[j]; xv[8 + j] = c[j]; }
+  }
+  float o[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    float z = s_b4[g * 16 + j];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) z = fmaf(s[k], s_w4[k * 64 + g * 16 + j], z);
+    const float m = 1.f / (1.f + expf(-z));
+    o[j] = xv[j] * m;
+  }
+  T* op = reinterpret_cast<T*>(p.out) + pix * p.out_stride + p.out_coff + g * 16;
+  float a[8], c[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { a[j] = o[j]; c[j] = o[8 + j]; }
+  store8(op, a);
+  store8(op + 8, c);
+}
+
+}  // namespace esr
