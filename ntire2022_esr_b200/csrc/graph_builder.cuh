@@ -1,0 +1,744 @@
+// Builds the shape-independent op graph of each network (IMDN / RFDN / RLFN / BSRN) from the
+// reference state-dict.  Two flavours per network:
+//   tc = false : every layer on the CUDA-core kernels (kernels_generic.cuh); used by the fp32 mode
+//   tc = true  : fp16 storage, dense 3x3 / 1x1 convolutions on tcgen05 (conv_tc.cuh) with the
+//                distillation 1x1, the block residual (identity tap) and the ESA entry 1x1s folded
+//                into the same launch; small / irregular layers stay on the CUDA-core kernels
+// Reference graphs: models/rfdn_baseline/{RFDN.py:29-41, block.py:117-129,148-166},
+// models/imdn_baseline.py:46-65 + models/basicblock.py:259-265, models/team04_rlfn.py:76-152,
+// models/team18_bsrn.py:82-236.
+#pragma once
+#include <cmath>
+#include <cstring>
+
+#include "engine.h"
+#include "kernels_generic.cuh"
+#include "tc_common.cuh"
+
+namespace esr {
+
+using PosFn = std::function<int(int)>;
+inline PosFn pos_id(int off = 0) { return [off](int c) { return c + off; }; }
+inline PosFn pos_slots(int real, int slot, int off = 0) {
+  return [real, slot, off](int c) { return off + (c / real) * slot + (c % real); };
+}
+
+struct Weights {
+  std::map<std::string, HostTensor>* store;
+  std::string err;
+  HostTensor zero;
+  const HostTensor& get(const std::string& name, std::vector<int64_t> shape) {
+    auto it = store->find(name);
+    if (it == store->end()) {
+      if (err.empty()) err = "missing key in state_dict: " + name;
+      size_t n = 1;
+      for (auto s : shape) n *= (size_t)s;
+      zero.data.assign(n, 0.f);
+      zero.shape = shape;
+      return zero;
+    }
+    it->second.used = true;
+    if (it->second.shape != shape) {
+      if (err.empty()) {
+        std::string got, want;
+        for (auto s : it->second.shape) got += std::to_string(s) + ",";
+        for (auto s : shape) want += std::to_string(s) + ",";
+        err = "size mismatch for " + name + ": got (" + got + ") expected (" + want + ")";
+      }
+      size_t n = 1;
+      for (auto s : shape) n *= (size_t)s;
+      zero.data.assign(n, 0.f);
+      zero.shape = shape;
+      return zero;
+    }
+    return it->second;
+  }
+};
+
+// A logical dense conv / linear layer as a (out,in,k,k) matrix in double precision, so that
+// compositions (ESA entry 1x1s folded into c5, BSRN channel scale folded into conv_out) are formed
+// once, exactly, before any rounding to the storage type.
+struct Mat {
+  int O = 0, I = 0, k = 1;
+  std::vector<double> w;  // [O][I][k*k]
+  std::vector<double> b;  // [O]
+  double& at(int o, int i, int t) { return w[((size_t)o * I + i) * k * k + t]; }
+  double at(int o, int i, int t) const { return w[((size_t)o * I + i) * k * k + t]; }
+};
+
+struct GraphBuilder {
+  Weights wts;
+  Graph g;
+  std::vector<Table> tables;
+
+  int buf(int kind, int C, bool f32 = false) {
+    g.bufs.push_back(BufDecl{kind, C, f32});
+    return (int)g.bufs.size() - 1;
+  }
+
+  Mat conv_mat(const std::string& name, int O, int I, int k) {
+    Mat m;
+    m.O = O; m.I = I; m.k = k;
+    const HostTensor& w = wts.get(name + ".weight", {O, I, k, k});
+    const HostTensor& b = wts.get(name + ".bias", {O});
+    m.w.assign(w.data.begin(), w.data.end());
+    m.b.assign(b.data.begin(), b.data.end());
+    return m;
+  }
+  Mat linear_mat(const std::string& name, int O, int I) {
+    Mat m;
+    m.O = O; m.I = I; m.k = 1;
+    const HostTensor& w = wts.get(name + ".weight", {O, I});
+    const HostTensor& b = wts.get(name + ".bias", {O});
+    m.w.assign(w.data.begin(), w.data.end());
+    m.b.assign(b.data.begin(), b.data.end());
+    return m;
+  }
+  // C = A o B for 1x1 A applied after B (any k): C.w = A.w * B.w, C.b = A.w * B.b + A.b
+  static Mat compose(const Mat& A, const Mat& B) {
+    Mat C;
+    C.O = A.O; C.I = B.I; C.k = B.k;
+    const int kk = B.k * B.k;
+    C.w.assign((size_t)C.O * C.I * kk, 0.0);
+    C.b.assign(C.O, 0.0);
+    for (int o = 0; o < A.O; ++o) {
+      double bb = A.b[o];
+      for (int m = 0; m < A.I; ++m) {
+        const double a = A.at(o, m, 0);
+        bb += a * B.b[m];
+        for (int i = 0; i < B.I; ++i)
+          for (int t = 0; t < kk; ++t) C.at(o, i, t) += a * B.at(m, i, t);
+      }
+      C.b[o] = bb;
+    }
+    return C;
+  }
+
+  // ---- CUDA-core tables ---------------------------------------------------------------------
+  int new_table(int k, int cin8, int cout16) {
+    Table t;
+    t.k = k; t.cin8 = cin8; t.cout16 = cout16;
+    t.w.assign((size_t)k * k * cin8 * cout16, 0.f);
+    t.b.assign(cout16, 0.f);
+    tables.push_back(std::move(t));
+    return (int)tables.size() - 1;
+  }
+  void table_add(int ti, const Mat& m, const PosFn& in_pos, const PosFn& out_pos) {
+    Table& t = tables[ti];
+    const int kk = m.k * m.k;
+    for (int o = 0; o < m.O; ++o) {
+      const int oc = out_pos(o);
+      if (oc < 0) continue;
+      t.b[oc] += (float)m.b[o];
+      for (int i = 0; i < m.I; ++i) {
+        const int ic = in_pos(i);
+        if (ic < 0) continue;
+        for (int tp = 0; tp < kk; ++tp) {
+          const int tap = (m.k == t.k) ? tp : (t.k * t.k) / 2;  // 1x1 inside a 3x3 table -> centre tap
+          t.w[((size_t)tap * t.cin8 + ic) * t.cout16 + oc] += (float)m.at(o, i, tp);
+        }
+      }
+    }
+  }
+  int dense_table(const Mat& m, int cin8, int cout16, const PosFn& in_pos, const PosFn& out_pos) {
+    const int ti = new_table(m.k, cin8, cout16);
+    table_add(ti, m, in_pos, out_pos);
+    return ti;
+  }
+  // depthwise 3x3 (C,1,3,3) -> w[9][c8]
+  int dw_table(const std::string& name, int C, int c8) {
+    const HostTensor& w = wts.get(name + ".weight", {C, 1, 3, 3});
+    const HostTensor& b = wts.get(name + ".bias", {C});
+    Table t;
+    t.k = 3; t.cin8 = 1; t.cout16 = c8;
+    t.w.assign((size_t)9 * c8, 0.f);
+    t.b.assign(c8, 0.f);
+    for (int c = 0; c < C; ++c) {
+      t.b[c] = b.data[c];
+      for (int tp = 0; tp < 9; ++tp) t.w[(size_t)tp * c8 + c] = w.data[(size_t)c * 9 + tp];
+    }
+    tables.push_back(std::move(t));
+    return (int)tables.size() - 1;
+  }
+
+  // ---- generic ops ----------------------------------------------------------------------------
+  OpDecl& conv_op(const std::string& name, int tab, int in, int in_coff, int out, int out_coff, int act,
+                  float slope = 0.f, int stride = 1, int pad = -1) {
+    OpDecl op;
+    op.kind = OP_CONV;
+    op.name = name;
+    op.tab = tab;
+    op.in = in; op.in_coff = in_coff; op.out = out; op.out_coff = out_coff;
+    op.act = act; op.slope = slope;
+    op.ksize = tables[tab].k;
+    op.stride = stride;
+    op.pad = pad >= 0 ? pad : tables[tab].k / 2;
+    g.ops.push_back(op);
+    return g.ops.back();
+  }
+  OpDecl& dw_op(const std::string& name, int tab, int in, int in_coff, int out, int out_coff, int act) {
+    OpDecl op;
+    op.kind = OP_DW;
+    op.name = name;
+    op.tab = tab;
+    op.in = in; op.in_coff = in_coff; op.out = out; op.out_coff = out_coff;
+    op.act = act;
+    op.ksize = 3; op.pad = 1;
+    g.ops.push_back(op);
+    return g.ops.back();
+  }
+
+  // ---- tcgen05 convolution ------------------------------------------------------------------
+  struct TcPlane {
+    int dy, dx;
+    std::vector<float> w;  // [cinP][accP]
+  };
+  struct TcBuild {
+    int cinP, accP;
+    std::vector<TcPlane> planes;
+    std::vector<float> bias;             // [accP]
+    std::vector<std::pair<int, int>> segs;  // (col0, n) column segments = MMA N extents
+  };
+  TcBuild tc_begin(int nchunks, int accP, std::vector<std::pair<int, int>> segs) {
+    TcBuild b;
+    b.cinP = nchunks * 64;
+    b.accP = accP;
+    b.bias.assign(accP, 0.f);
+    b.segs = std::move(segs);
+    return b;
+  }
+  static TcPlane& tc_plane(TcBuild& b, int dy, int dx, bool fresh) {
+    if (!fresh)
+      for (auto& p : b.planes)
+        if (p.dy == dy && p.dx == dx) return p;
+    TcPlane p;
+    p.dy = dy; p.dx = dx;
+    p.w.assign((size_t)b.cinP * b.accP, 0.f);
+    b.planes.push_back(std::move(p));
+    return b.planes.back();
+  }
+  void tc_add(TcBuild& b, const Mat& m, const PosFn& in_pos, const PosFn& out_pos) {
+    for (int tp = 0; tp < m.k * m.k; ++tp) {
+      const int dy = (m.k == 3) ? tp / 3 - 1 : 0, dx = (m.k == 3) ? tp % 3 - 1 : 0;
+      TcPlane& p = tc_plane(b, dy, dx, false);
+      for (int o = 0; o < m.O; ++o) {
+        const int oc = out_pos(o);
+        if (oc < 0) continue;
+        for (int i = 0; i < m.I; ++i) {
+          const int ic = in_pos(i);
+          if (ic < 0) continue;
+          p.w[(size_t)ic * b.accP + oc] += (float)m.at(o, i, tp);
+        }
+      }
+    }
+    for (int o = 0; o < m.O; ++o) {
+      const int oc = out_pos(o);
+      if (oc >= 0) b.bias[oc] += (float)m.b[o];
+    }
+  }
+  // residual `+ x` as an exact identity tap in its own plane (never merged with the weights: in
+  // fp16, w + 1 would wipe out the low bits of w)
+  void tc_add_identity(TcBuild& b, int C) {
+    TcPlane& p = tc_plane(b, 0, 0, true);
+    for (int c = 0; c < C; ++c) p.w[(size_t)c * b.accP + c] = 1.f;
+  }
+  // finishes the op: derives the MMA entry list from the non-zero structure, swizzles the B blocks
+  int tc_finish(const std::string& name, TcBuild& b, int in, int in_coff, int halo, std::vector<TcGroupDecl> groups,
+                std::vector<std::vector<float>>* group_bias_out) {
+    TcConv c;
+    c.in = in;
+    c.nchunks = b.cinP / 64;
+    for (int i = 0; i < c.nchunks; ++i) c.chunk_c0[i] = in_coff + 64 * i;
+    c.halo = halo;
+    c.acc_cols = b.accP;
+    std::vector<int> seg_started(b.segs.size(), 0);
+    // order: plane-major so that consecutive MMAs walk different accumulator columns as little as
+    // possible; all entries of one segment accumulate into the same columns
+    for (size_t pi = 0; pi < b.planes.size(); ++pi) {
+      const TcPlane& p = b.planes[pi];
+      for (int ch = 0; ch < c.nchunks; ++ch)
+        for (size_t si = 0; si < b.segs.size(); ++si) {
+          const int col0 = b.segs[si].first, n = b.segs[si].second;
+          int last_k = -1;
+          for (int k = 0; k < 64; ++k)
+            for (int j = 0; j < n; ++j)
+              if (p.w[(size_t)(ch * 64 + k) * b.accP + col0 + j] != 0.f) last_k = k;
+          const bool last_chance = (pi + 1 == b.planes.size() && ch + 1 == c.nchunks);
+          if (last_k < 0 && !(last_chance && !seg_started[si])) continue;
+          TcPlaneEntry e;
+          e.dy = p.dy; e.dx = p.dx; e.chunk = ch;
+          e.nsteps = last_k < 0 ? 1 : (last_k / 16 + 1);
+          e.n = n; e.dcol = col0;
+          e.first = seg_started[si] ? 0 : 1;
+          seg_started[si] = 1;
+          e.b_off = c.blob.size();
+          c.blob.resize(c.blob.size() + (size_t)n * 128, 0);
+          uint8_t* blk = c.blob.data() + e.b_off;
+          for (int j = 0; j < n; ++j)
+            for (int k = 0; k < 64; ++k) {
+              const __half h = __float2half_rn(p.w[(size_t)(ch * 64 + k) * b.accP + col0 + j]);
+              memcpy(blk + sw128_offset((uint32_t)j, (uint32_t)k), &h, 2);
+            }
+          c.entries.push_back(e);
+        }
+    }
+    c.groups = std::move(groups);
+    if (group_bias_out) {
+      group_bias_out->clear();
+      for (auto& gd : c.groups)
+        group_bias_out->push_back(std::vector<float>(b.bias.begin() + gd.col0, b.bias.begin() + gd.col0 + gd.ncols));
+    }
+    g.tc.push_back(std::move(c));
+    OpDecl op;
+    op.kind = OP_CONV_TC;
+    op.name = name;
+    op.tc = (int)g.tc.size() - 1;
+    g.ops.push_back(op);
+    return op.tc;
+  }
+  // group biases live in small generic tables (so they ride the same parameter arena)
+  void tc_attach_bias(int tci, const std::vector<std::vector<float>>& gb) {
+    for (size_t i = 0; i < gb.size(); ++i) {
+      Table t;
+      t.k = 0; t.cin8 = 0; t.cout16 = (int)gb[i].size();
+      t.b = gb[i];
+      tables.push_back(std::move(t));
+      g.tc[tci].groups[i].off_bias = tables.size() - 1;  // table index; resolved to an offset at upload
+    }
+  }
+  static TcGroupDecl tc_group(int col0, int ncols, int act, float slope, int out, int out_coff, int res = BUF_NONE,
+                              int res_coff = 0, int res_after = 0, int mode = 0) {
+    TcGroupDecl gd;
+    gd.col0 = col0; gd.ncols = ncols; gd.act = act; gd.slope = slope;
+    gd.out = out; gd.out_coff = out_coff; gd.res = res; gd.res_coff = res_coff; gd.res_after = res_after;
+    gd.mode = mode;
+    return gd;
+  }
+  int tc_emit(const std::string& name, TcBuild& b, int in, int in_coff, int halo, std::vector<TcGroupDecl> groups) {
+    std::vector<std::vector<float>> gb;
+    const int tci = tc_finish(name, b, in, in_coff, halo, std::move(groups), &gb);
+    tc_attach_bias(tci, gb);
+    return tci;
+  }
+
+  // ---- ESA (shared by RFDN / RLFN; BSRN has its own small-map chain) --------------------------
+  struct EsaBufs { int esa, s2, s3a, s3b; };
+  // generic entry: conv1 (1x1 C->f) into esa[0:16]; returns nothing. `cf_ready` = 0 afterwards.
+  void esa_tail(const std::string& p, int arch, const EsaBufs& eb, int f, int C, int x, int x_coff, int dst,
+                int dst_coff, int cgroups, int cf_ready, const Mat& conv_f, const Mat& conv4) {
+    // conv2: 3x3 stride 2 pad 0 on c1_ (esa[0:16]) -> s2 (fp32)
+    {
+      const Mat m = conv_mat(p + "conv2", f, f, 3);
+      conv_op(p + "conv2", dense_table(m, 16, 16, pos_id(), pos_id()), eb.esa, 0, eb.s2, 0, ACT_NONE, 0.f, 2, 0);
+    }
+    OpDecl pool;
+    pool.kind = OP_POOL;
+    pool.name = p + "max_pool";
+    pool.in = eb.s2; pool.out = eb.s3a;
+    g.ops.push_back(pool);
+    int c3 = eb.s3a;
+    if (arch == ESR_ARCH_RFDN) {
+      const Mat m1 = conv_mat(p + "conv_max", f, f, 3), m2 = conv_mat(p + "conv3", f, f, 3),
+                m3 = conv_mat(p + "conv3_", f, f, 3);
+      conv_op(p + "conv_max", dense_table(m1, 16, 16, pos_id(), pos_id()), eb.s3a, 0, eb.s3b, 0, ACT_RELU);
+      conv_op(p + "conv3", dense_table(m2, 16, 16, pos_id(), pos_id()), eb.s3b, 0, eb.s3a, 0, ACT_RELU);
+      conv_op(p + "conv3_", dense_table(m3, 16, 16, pos_id(), pos_id()), eb.s3a, 0, eb.s3b, 0, ACT_NONE);
+      c3 = eb.s3b;
+    } else if (arch == ESR_ARCH_RLFN) {
+      const Mat m = conv_mat(p + "conv3", f, f, 3);
+      conv_op(p + "conv3", dense_table(m, 16, 16, pos_id(), pos_id()), eb.s3a, 0, eb.s3b, 0, ACT_NONE);
+      c3 = eb.s3b;
+    } else {  // BSRN: three BSConvU (Linear then depthwise 3x3), GELU after the first two
+      const char* names[3] = {"conv_max", "conv3", "conv3_"};
+      for (int i = 0; i < 3; ++i) {
+        const Mat pw = linear_mat(p + names[i] + ".pw", f, f);
+        conv_op(p + names[i] + ".pw", dense_table(pw, 16, 16, pos_id(), pos_id()), eb.s3a, 0, eb.s3b, 0, ACT_NONE);
+        dw_op(p + names[i] + ".dw", dw_table(p + names[i] + ".dw", f, 16), eb.s3b, 0, eb.s3a, 0,
+              i < 2 ? ACT_GELU : ACT_NONE);
+      }
+      c3 = eb.s3a;
+    }
+    OpDecl ap;
+    ap.kind = OP_ESA_APPLY;
+    ap.name = p + "apply";
+    ap.in = x; ap.in_coff = x_coff;
+    ap.c1 = eb.esa; ap.c1_coff = cf_ready ? 16 : 0;
+    ap.c3 = c3;
+    ap.out = dst; ap.out_coff = dst_coff;
+    ap.f = f; ap.cgroups = cgroups; ap.cf_ready = cf_ready;
+    // wf: [16][16] (in,out); w4: [16][64] (in,out)
+    ap.tab = dense_table(conv_f, 16, 16, pos_id(), pos_id());
+    ap.tab2 = dense_table(conv4, 16, 64, pos_id(), pos_id());
+    (void)C;
+    g.ops.push_back(ap);
+  }
+
+  // =============================================================================================
+  // RFDN
+  // =============================================================================================
+  void build_rfdn(int nf, int nblocks, bool tc) {
+    const int dc = nf / 2, f = nf / 4;
+    const float sl = 0.05f;
+    const int fea = buf(BK_FULL, 64), cat = buf(BK_FULL, 64 * nblocks), t0 = buf(BK_FULL, 64), t1 = buf(BK_FULL, 64),
+              dist = buf(BK_FULL, 128), c5o = buf(BK_FULL, 64), esa = buf(BK_FULL, 32);
+    EsaBufs eb{esa, buf(BK_S2, 16, true), buf(BK_S3, 16, true), buf(BK_S3, 16, true)};
+    {
+      OpDecl op;
+      op.kind = OP_HEAD;
+      op.name = "fea_conv";
+      op.in = BUF_IN; op.out = fea;
+      const Mat m = conv_mat("fea_conv", nf, 3, 3);
+      // head table layout: w[(ky*3+kx)*3+ci][64]
+      const int ti = new_table(1, 27 + 5, 64);  // cin8 = 32 rows (27 used)
+      for (int o = 0; o < nf; ++o) {
+        tables[ti].b[o] = (float)m.b[o];
+        for (int ci = 0; ci < 3; ++ci)
+          for (int tp = 0; tp < 9; ++tp) tables[ti].w[(size_t)(tp * 3 + ci) * 64 + o] = (float)m.at(o, ci, tp);
+      }
+      op.tab = ti;
+      g.ops.push_back(op);
+    }
+    int x = fea, xc = 0;
+    for (int bi = 0; bi < nblocks; ++bi) {
+      const std::string p = "B" + std::to_string(bi + 1) + ".";
+      int cur = x, curc = xc;
+      int pp[2] = {t0, t1};
+      for (int s = 0; s < 3; ++s) {
+        const std::string n = "c" + std::to_string(s + 1);
+        const Mat md = conv_mat(p + n + "_d", dc, nf, 1), mr = conv_mat(p + n + "_r", nf, nf, 3);
+        const int nxt = pp[s & 1];
+        if (!tc) {
+          conv_op(p + n + "_d", dense_table(md, 64, 32, pos_id(), pos_id()), cur, curc, dist, 32 * s, ACT_LRELU, sl);
+          OpDecl& o = conv_op(p + n + "_r", dense_table(mr, 64, 64, pos_id(), pos_id()), cur, curc, nxt, 0, ACT_LRELU, sl);
+          o.res = cur; o.res_coff = curc; o.res_after = 0;
+        } else {
+          TcBuild b = tc_begin(1, 96, {{0, 64}, {64, 32}});
+          tc_add(b, mr, pos_id(), pos_id());
+          tc_add(b, md, pos_id(), pos_id(64));
+          tc_add_identity(b, nf);
+          tc_emit(p + n + "_r+d", b, cur, curc, 1,
+                  {tc_group(0, 64, ACT_LRELU, sl, nxt, 0), tc_group(64, 32, ACT_LRELU, sl, dist, 32 * s)});
+        }
+        cur = nxt; curc = 0;
+      }
+      const Mat m4 = conv_mat(p + "c4", dc, nf, 3), m5 = conv_mat(p + "c5", nf, dc * 4, 1);
+      const Mat e1 = conv_mat(p + "esa.conv1", f, nf, 1), ef = conv_mat(p + "esa.conv_f", f, f, 1),
+                e4 = conv_mat(p + "esa.conv4", nf, f, 1);
+      if (!tc) {
+        conv_op(p + "c4", dense_table(m4, 64, 32, pos_id(), pos_id()), cur, curc, dist, 96, ACT_LRELU, sl);
+        conv_op(p + "c5", dense_table(m5, 128, 64, pos_slots(dc, 32), pos_id()), dist, 0, c5o, 0, ACT_NONE);
+        conv_op(p + "esa.conv1", dense_table(e1, 64, 16, pos_id(), pos_id()), c5o, 0, esa, 0, ACT_NONE);
+        esa_tail(p + "esa.", ESR_ARCH_RFDN, eb, f, nf, c5o, 0, cat, 64 * bi, 4, 0, ef, e4);
+      } else {
+        TcBuild b4 = tc_begin(1, 32, {{0, 32}});
+        tc_add(b4, m4, pos_id(), pos_id());
+        tc_emit(p + "c4", b4, cur, curc, 1, {tc_group(0, 32, ACT_LRELU, sl, dist, 96)});
+        // c5 with the ESA entry folded in: c1_ = conv1(c5(.)), cf = conv_f(c1_) are 1x1s of a 1x1
+        const Mat c1c = compose(e1, m5), cfc = compose(ef, c1c);
+        TcBuild b5 = tc_begin(2, 96, {{0, 64}, {64, 32}});
+        tc_add(b5, m5, pos_slots(dc, 32), pos_id());
+        tc_add(b5, c1c, pos_slots(dc, 32), pos_id(64));
+        tc_add(b5, cfc, pos_slots(dc, 32), pos_id(80));
+        tc_emit(p + "c5+esa.conv1+esa.conv_f", b5, dist, 0, 0,
+                {tc_group(0, 64, ACT_NONE, 0.f, c5o, 0), tc_group(64, 32, ACT_NONE, 0.f, esa, 0)});
+        esa_tail(p + "esa.", ESR_ARCH_RFDN, eb, f, nf, c5o, 0, cat, 64 * bi, 4, 1, ef, e4);
+      }
+      x = cat; xc = 64 * bi;
+    }
+    const Mat mc = conv_mat("c.0", nf, nf * nblocks, 1), mlr = conv_mat("LR_conv", nf, nf, 3),
+              mup = conv_mat("upsampler.0", 48, nf, 3);
+    if (!tc) {
+      conv_op("c", dense_table(mc, 64 * nblocks, 64, pos_slots(nf, 64), pos_id()), cat, 0, t0, 0, ACT_LRELU, sl);
+      OpDecl& o = conv_op("LR_conv", dense_table(mlr, 64, 64, pos_id(), pos_id()), t0, 0, t1, 0, ACT_NONE);
+      o.res = fea; o.res_coff = 0;
+      OpDecl& u = conv_op("upsampler", dense_table(mup, 64, 48, pos_id(), pos_id()), t1, 0, BUF_OUT, 0, ACT_NONE);
+      u.ps = true;
+    } else {
+      TcBuild bc = tc_begin(nblocks, 64, {{0, 64}});
+      tc_add(bc, mc, pos_slots(nf, 64), pos_id());
+      tc_emit("c", bc, cat, 0, 0, {tc_group(0, 64, ACT_LRELU, sl, t0, 0)});
+      TcBuild bl = tc_begin(1, 64, {{0, 64}});
+      tc_add(bl, mlr, pos_id(), pos_id());
+      tc_emit("LR_conv", bl, t0, 0, 1, {tc_group(0, 64, ACT_NONE, 0.f, t1, 0, fea, 0, 0)});
+      TcBuild bu = tc_begin(1, 48, {{0, 48}});
+      tc_add(bu, mup, pos_id(), pos_id());
+      tc_emit("upsampler", bu, t1, 0, 1, {tc_group(0, 48, ACT_NONE, 0.f, BUF_OUT, 0, BUF_NONE, 0, 0, 1)});
+    }
+  }
+
+  // =============================================================================================
+  // RLFN (RLFN_cut: nf 46, mid 48, ESA width 16)
+  // =============================================================================================
+  void build_rlfn(int nf, int nblocks, bool tc) {
+    const int mf = 48, f = 16;
+    const float sl = 0.05f;
+    const int fea = buf(BK_FULL, 64), xa = buf(BK_FULL, 64), xb = buf(BK_FULL, 64), t0 = buf(BK_FULL, 64),
+              t1 = buf(BK_FULL, 64), esa = buf(BK_FULL, 32);
+    EsaBufs eb{esa, buf(BK_S2, 16, true), buf(BK_S3, 16, true), buf(BK_S3, 16, true)};
+    {
+      OpDecl op;
+      op.kind = OP_HEAD;
+      op.name = "fea_conv";
+      op.in = BUF_IN; op.out = fea;
+      const Mat m = conv_mat("fea_conv", nf, 3, 3);
+      const int ti = new_table(1, 32, 64);
+      for (int o = 0; o < nf; ++o) {
+        tables[ti].b[o] = (float)m.b[o];
+        for (int ci = 0; ci < 3; ++ci)
+          for (int tp = 0; tp < 9; ++tp) tables[ti].w[(size_t)(tp * 3 + ci) * 64 + o] = (float)m.at(o, ci, tp);
+      }
+      op.tab = ti;
+      g.ops.push_back(op);
+    }
+    int x = fea;
+    for (int bi = 0; bi < nblocks; ++bi) {
+      const std::string p = "B" + std::to_string(bi + 1) + ".";
+      const int xn = (bi & 1) ? xb : xa;
+      const Mat m1 = conv_mat(p + "c1_r", mf, nf, 3), m2 = conv_mat(p + "c2_r", mf, mf, 3),
+                m3 = conv_mat(p + "c3_r", nf, mf, 3), m5 = conv_mat(p + "c5", nf, nf, 1);
+      const Mat e1 = conv_mat(p + "esa.conv1", f, nf, 1), ef = conv_mat(p + "esa.conv_f", f, f, 1),
+                e4 = conv_mat(p + "esa.conv4", nf, f, 1);
+      if (!tc) {
+        conv_op(p + "c1_r", dense_table(m1, 64, 64, pos_id(), pos_id()), x, 0, t0, 0, ACT_LRELU, sl);
+        conv_op(p + "c2_r", dense_table(m2, 64, 64, pos_id(), pos_id()), t0, 0, t1, 0, ACT_LRELU, sl);
+        OpDecl& o = conv_op(p + "c3_r", dense_table(m3, 64, 64, pos_id(), pos_id()), t1, 0, t0, 0, ACT_LRELU, sl);
+        o.res = x; o.res_coff = 0; o.res_after = 1;
+        conv_op(p + "c5", dense_table(m5, 64, 64, pos_id(), pos_id()), t0, 0, t1, 0, ACT_NONE);
+        conv_op(p + "esa.conv1", dense_table(e1, 64, 16, pos_id(), pos_id()), t1, 0, esa, 0, ACT_NONE);
+        esa_tail(p + "esa.", ESR_ARCH_RLFN, eb, f, nf, t1, 0, xn, 0, 4, 0, ef, e4);
+      } else {
+        TcBuild b1 = tc_begin(1, 48, {{0, 48}});
+        tc_add(b1, m1, pos_id(), pos_id());
+        tc_emit(p + "c1_r", b1, x, 0, 1, {tc_group(0, 48, ACT_LRELU, sl, t0, 0)});
+        TcBuild b2 = tc_begin(1, 48, {{0, 48}});
+        tc_add(b2, m2, pos_id(), pos_id());
+        tc_emit(p + "c2_r", b2, t0, 0, 1, {tc_group(0, 48, ACT_LRELU, sl, t1, 0)});
+        TcBuild b3 = tc_begin(1, 48, {{0, 48}});
+        tc_add(b3, m3, pos_id(), pos_id());
+        tc_emit(p + "c3_r", b3, t1, 0, 1, {tc_group(0, 48, ACT_LRELU, sl, t0, 0, x, 0, 1)});
+        const Mat c1c = compose(e1, m5), cfc = compose(ef, c1c);
+        TcBuild b5 = tc_begin(1, 80, {{0, 48}, {48, 32}});
+        tc_add(b5, m5, pos_id(), pos_id());
+        tc_add(b5, c1c, pos_id(), pos_id(48));
+        tc_add(b5, cfc, pos_id(), pos_id(64));
+        tc_emit(p + "c5+esa.conv1+esa.conv_f", b5, t0, 0, 0,
+                {tc_group(0, 48, ACT_NONE, 0.f, t1, 0), tc_group(48, 32, ACT_NONE, 0.f, esa, 0)});
+        esa_tail(p + "esa.", ESR_ARCH_RLFN, eb, f, nf, t1, 0, xn, 0, 3, 1, ef, e4);
+      }
+      x = xn;
+    }
+    const Mat mlr = conv_mat("LR_conv", nf, nf, 3), mup = conv_mat("upsampler.0", 48, nf, 3);
+    if (!tc) {
+      OpDecl& o = conv_op("LR_conv", dense_table(mlr, 64, 64, pos_id(), pos_id()), x, 0, t0, 0, ACT_NONE);
+      o.res = fea; o.res_coff = 0;
+      OpDecl& u = conv_op("upsampler", dense_table(mup, 64, 48, pos_id(), pos_id()), t0, 0, BUF_OUT, 0, ACT_NONE);
+      u.ps = true;
+    } else {
+      TcBuild bl = tc_begin(1, 48, {{0, 48}});
+      tc_add(bl, mlr, pos_id(), pos_id());
+      tc_emit("LR_conv", bl, x, 0, 1, {tc_group(0, 48, ACT_NONE, 0.f, t0, 0, fea, 0, 0)});
+      TcBuild bu = tc_begin(1, 48, {{0, 48}});
+      tc_add(bu, mup, pos_id(), pos_id());
+      tc_emit("upsampler", bu, t0, 0, 1, {tc_group(0, 48, ACT_NONE, 0.f, BUF_OUT, 0, BUF_NONE, 0, 0, 1)});
+    }
+  }
+
+  // =============================================================================================
+  // IMDN (nc 64, d_nc 16, r_nc 48).  Output channels of conv1..3 are permuted to [r(48) | d(16)]
+  // so the next conv reads a contiguous K = 48.
+  // =============================================================================================
+  void build_imdn(int nc, int nb, bool tc) {
+    const int dn = nc / 4, rn = nc - dn;
+    const float sl = 0.05f;
+    const int fea = buf(BK_FULL, 64), xa = buf(BK_FULL, 64), xb = buf(BK_FULL, 64), t0 = buf(BK_FULL, 64),
+              t1 = buf(BK_FULL, 64), dist = buf(BK_FULL, 64);
+    {
+      OpDecl op;
+      op.kind = OP_HEAD;
+      op.name = "model.0";
+      op.in = BUF_IN; op.out = fea;
+      const Mat m = conv_mat("model.0", nc, 3, 3);
+      const int ti = new_table(1, 32, 64);
+      for (int o = 0; o < nc; ++o) {
+        tables[ti].b[o] = (float)m.b[o];
+        for (int ci = 0; ci < 3; ++ci)
+          for (int tp = 0; tp < 9; ++tp) tables[ti].w[(size_t)(tp * 3 + ci) * 64 + o] = (float)m.at(o, ci, tp);
+      }
+      op.tab = ti;
+      g.ops.push_back(op);
+    }
+    // weight out-channel o -> r column (o - dn) or -1 / d column o or -1
+    const PosFn r_cols = [dn](int o) { return o >= dn ? o - dn : -1; };
+    const PosFn d_cols = [dn](int o) { return o < dn ? o : -1; };
+    int x = fea;
+    for (int bi = 0; bi < nb; ++bi) {
+      const std::string p = "model.1.sub." + std::to_string(bi) + ".";
+      const int xn = (bi & 1) ? xb : xa;
+      int cur = x, cin = nc;
+      int pp[2] = {t0, t1};
+      for (int s = 0; s < 3; ++s) {
+        const Mat m = conv_mat(p + "conv" + std::to_string(s + 1) + ".0", nc, cin, 3);
+        const int nxt = pp[s & 1];
+        const std::string n = p + "conv" + std::to_string(s + 1);
+        if (!tc) {
+          conv_op(n + ".r", dense_table(m, 64, 48, pos_id(), r_cols), cur, 0, nxt, 0, ACT_LRELU, sl);
+          conv_op(n + ".d", dense_table(m, 64, 16, pos_id(), d_cols), cur, 0, dist, dn * s, ACT_LRELU, sl);
+        } else {
+          TcBuild b = tc_begin(1, 64, {{0, 64}});
+          const PosFn perm = [dn, rn](int o) { return o >= dn ? o - dn : rn + o; };
+          tc_add(b, m, pos_id(), perm);
+          tc_emit(n, b, cur, 0, 1,
+                  {tc_group(0, 48, ACT_LRELU, sl, nxt, 0), tc_group(48, 16, ACT_LRELU, sl, dist, dn * s)});
+        }
+        cur = nxt;
+        cin = rn;
+      }
+      const Mat m4 = conv_mat(p + "conv4", dn, rn, 3), m1 = conv_mat(p + "conv1x1", nc, nc, 1);
+      if (!tc) {
+        conv_op(p + "conv4", dense_table(m4, 64, 16, pos_id(), pos_id()), cur, 0, dist, dn * 3, ACT_NONE);
+        OpDecl& o = conv_op(p + "conv1x1", dense_table(m1, 64, 64, pos_id(), pos_id()), dist, 0, xn, 0, ACT_NONE);
+        o.res = x; o.res_coff = 0;
+      } else {
+        TcBuild b4 = tc_begin(1, 16, {{0, 16}});
+        tc_add(b4, m4, pos_id(), pos_id());
+        tc_emit(p + "conv4", b4, cur, 0, 1, {tc_group(0, 16, ACT_NONE, 0.f, dist, dn * 3)});
+        TcBuild b1 = tc_begin(1, 64, {{0, 64}});
+        tc_add(b1, m1, pos_id(), pos_id());
+        tc_emit(p + "conv1x1", b1, dist, 0, 0, {tc_group(0, 64, ACT_NONE, 0.f, xn, 0, x, 0, 0)});
+      }
+      x = xn;
+    }
+    const Mat ml = conv_mat("model.1.sub." + std::to_string(nb), nc, nc, 3), mup = conv_mat("model.2", 48, nc, 3);
+    if (!tc) {
+      OpDecl& o = conv_op("model.1.sub.last", dense_table(ml, 64, 64, pos_id(), pos_id()), x, 0, t0, 0, ACT_NONE);
+      o.res = fea; o.res_coff = 0;
+      OpDecl& u = conv_op("model.2", dense_table(mup, 64, 48, pos_id(), pos_id()), t0, 0, BUF_OUT, 0, ACT_NONE);
+      u.ps = true;
+    } else {
+      TcBuild bl = tc_begin(1, 64, {{0, 64}});
+      tc_add(bl, ml, pos_id(), pos_id());
+      tc_emit("model.1.sub.last", bl, x, 0, 1, {tc_group(0, 64, ACT_NONE, 0.f, t0, 0, fea, 0, 0)});
+      TcBuild bu = tc_begin(1, 48, {{0, 48}});
+      tc_add(bu, mup, pos_id(), pos_id());
+      tc_emit("model.2", bu, t0, 0, 1, {tc_group(0, 48, ACT_NONE, 0.f, BUF_OUT, 0, BUF_NONE, 0, 0, 1)});
+    }
+  }
+
+  // =============================================================================================
+  // BSRN (num_feat 48, num_block 5): pointwise Linears + depthwise 3x3, exact-erf GELU.
+  // tc = true puts the pointwise Linears of the trunk on tcgen05; depthwise / ESA stay on CUDA cores.
+  // =============================================================================================
+  void build_bsrn(int nf, int nblocks, bool tc) {
+    const int dc = nf / 2, f = 12;  // ESA(num_feat, ...) uses f = 12? -> esa_channels = 16 arg is unused: f = num_feat // 4
+    const int fea = buf(BK_FULL, 64), cat = buf(BK_FULL, 64 * nblocks), t0 = buf(BK_FULL, 64), t1 = buf(BK_FULL, 64),
+              t2 = buf(BK_FULL, 64), dist = buf(BK_FULL, 128), c5o = buf(BK_FULL, 64), eo = buf(BK_FULL, 64),
+              esa = buf(BK_FULL, 32);
+    EsaBufs eb{esa, buf(BK_S2, 16, true), buf(BK_S3, 16, true), buf(BK_S3, 16, true)};
+    {
+      OpDecl op;
+      op.kind = OP_BSRN_HEAD;
+      op.name = "fea_conv";
+      op.in = BUF_IN; op.out = fea;
+      const Mat pw = linear_mat("fea_conv.pw", nf, 12);
+      const int ti = new_table(1, 8, 64);  // wpw [3][64] (+ pad rows), bias = bpw
+      for (int o = 0; o < nf; ++o) {
+        tables[ti].b[o] = (float)pw.b[o];
+        for (int ci = 0; ci < 3; ++ci) {
+          double s = 0;
+          for (int r = 0; r < 4; ++r) s += pw.at(o, r * 3 + ci, 0);
+          tables[ti].w[(size_t)ci * 64 + o] = (float)s;
+        }
+      }
+      op.tab = ti;
+      op.tab2 = dw_table("fea_conv.dw", nf, 64);
+      g.ops.push_back(op);
+    }
+    auto lin = [&](const std::string& name, const Mat& m, int cin_pad, int cout_pad, const PosFn& ip, int in, int inc,
+                   int out, int outc, int act, int res = BUF_NONE, int resc = 0) {
+      if (!tc || cout_pad % 16 != 0) {
+        OpDecl& o = conv_op(name, dense_table(m, cin_pad, cout_pad, ip, pos_id()), in, inc, out, outc, act);
+        o.res = res; o.res_coff = resc;
+      } else {
+        TcBuild b = tc_begin(cin_pad / 64, cout_pad, {{0, cout_pad}});
+        tc_add(b, m, ip, pos_id());
+        tc_emit(name, b, in, inc, 0, {tc_group(0, cout_pad, act, 0.f, out, outc, res, resc, 0)});
+      }
+    };
+    int x = fea, xc = 0;
+    for (int bi = 0; bi < nblocks; ++bi) {
+      const std::string p = "B" + std::to_string(bi + 1) + ".";
+      int cur = x, curc = xc;
+      int pp[2] = {t0, t1};
+      for (int s = 0; s < 3; ++s) {
+        const std::string n = p + "c" + std::to_string(s + 1);
+        const Mat md = linear_mat(n + "_d", dc, nf), mp = linear_mat(n + "_r.pw", nf, nf);
+        const int nxt = pp[s & 1];
+        if (!tc) {
+          lin(n + "_d", md, 64, 32, pos_id(), cur, curc, dist, 32 * s, ACT_GELU);
+          lin(n + "_r.pw", mp, 64, 64, pos_id(), cur, curc, t2, 0, ACT_NONE);
+        } else {
+          // distillation Linear and the pointwise half of BSConvU share the A operand
+          TcBuild b = tc_begin(1, 96, {{0, 64}, {64, 32}});
+          tc_add(b, mp, pos_id(), pos_id());
+          tc_add(b, md, pos_id(), pos_id(64));
+          tc_emit(n + "_r.pw+d", b, cur, curc, 0,
+                  {tc_group(0, 64, ACT_NONE, 0.f, t2, 0), tc_group(64, 32, ACT_GELU, 0.f, dist, 32 * s)});
+        }
+        OpDecl& o = dw_op(n + "_r.dw", dw_table(n + "_r.dw", nf, 64), t2, 0, nxt, 0, ACT_GELU);
+        o.res = cur; o.res_coff = curc;
+        cur = nxt; curc = 0;
+      }
+      const Mat m4 = linear_mat(p + "c4.pw", dc, nf);
+      lin(p + "c4.pw", m4, 64, 32, pos_id(), cur, curc, t2, 0, ACT_NONE);
+      dw_op(p + "c4.dw", dw_table(p + "c4.dw", dc, 32), t2, 0, dist, 96, ACT_GELU);
+      const Mat m5 = linear_mat(p + "c5", nf, dc * 4);
+      const Mat e1 = linear_mat(p + "esa.conv1", f, nf), ef = linear_mat(p + "esa.conv_f", f, f),
+                e4 = linear_mat(p + "esa.conv4", nf, f);
+      int cf_ready = 0;
+      if (!tc) {
+        lin(p + "c5", m5, 128, 64, pos_slots(dc, 32), dist, 0, c5o, 0, ACT_NONE);
+        lin(p + "esa.conv1", e1, 64, 16, pos_id(), c5o, 0, esa, 0, ACT_NONE);
+      } else {
+        const Mat c1c = compose(e1, m5), cfc = compose(ef, c1c);
+        TcBuild b5 = tc_begin(2, 96, {{0, 64}, {64, 32}});
+        tc_add(b5, m5, pos_slots(dc, 32), pos_id());
+        tc_add(b5, c1c, pos_slots(dc, 32), pos_id(64));
+        tc_add(b5, cfc, pos_slots(dc, 32), pos_id(80));
+        tc_emit(p + "c5+esa.conv1+esa.conv_f", b5, dist, 0, 0,
+                {tc_group(0, 64, ACT_NONE, 0.f, c5o, 0), tc_group(64, 32, ACT_NONE, 0.f, esa, 0)});
+        cf_ready = 1;
+      }
+      esa_tail(p + "esa.", ESR_ARCH_BSRN, eb, f, nf, c5o, 0, eo, 0, 4, cf_ready, ef, e4);
+      // conv_out(esa(out) * cw) + input: the per-channel scale is folded into conv_out's columns
+      Mat mo = linear_mat(p + "conv_out", nf, nf);
+      const HostTensor& cw = wts.get(p + "cw", {1, nf});
+      for (int o = 0; o < nf; ++o)
+        for (int i = 0; i < nf; ++i) mo.at(o, i, 0) *= (double)cw.data[i];
+      lin(p + "conv_out", mo, 64, 64, pos_id(), eo, 0, cat, 64 * bi, ACT_NONE, x, xc);
+      x = cat; xc = 64 * bi;
+    }
+    const Mat mc1 = linear_mat("c1", nf, nf * nblocks), mc2 = linear_mat("c2.pw", nf, nf),
+              mup = conv_mat("upsampler.upsampleOneStep.0", 48, nf, 3);
+    if (!tc || nblocks > 4) {
+      OpDecl& o = conv_op("c1", dense_table(mc1, 64 * nblocks, 64, pos_slots(nf, 64), pos_id()), cat, 0, t0, 0, ACT_GELU);
+      (void)o;
+    } else {
+      lin("c1", mc1, 64 * nblocks, 64, pos_slots(nf, 64), cat, 0, t0, 0, ACT_GELU);
+    }
+    lin("c2.pw", mc2, 64, 64, pos_id(), t0, 0, t2, 0, ACT_NONE);
+    {
+      OpDecl& o = dw_op("c2.dw", dw_table("c2.dw", nf, 64), t2, 0, t1, 0, ACT_NONE);
+      o.res = fea; o.res_coff = 0;
+    }
+    if (!tc) {
+      OpDecl& u = conv_op("upsampler", dense_table(mup, 64, 48, pos_id(), pos_id()), t1, 0, BUF_OUT, 0, ACT_NONE);
+      u.ps = true;
+    } else {
+      TcBuild bu = tc_begin(1, 48, {{0, 48}});
+      tc_add(bu, mup, pos_id(), pos_id());
+      tc_emit("upsampler", bu, t1, 0, 1, {tc_group(0, 48, ACT_NONE, 0.f, BUF_OUT, 0, BUF_NONE, 0, 0, 1)});
+    }
+  }
+};
+
+}  // namespace esr

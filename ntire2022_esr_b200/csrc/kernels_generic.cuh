@@ -1,5 +1,6 @@
-// CUDA-core kernels of the SR engine (NHWC activations, fp32 math, fp32 or fp16 storage).
-// They carry the whole fp32 mode and, in fp16 mode, the small / irregular layers around the
+// CUDA-core kernels of the SR engine (NHWC activations; fp32 or fp16 storage).
+// They carry the whole fp32 mode (fp64 accumulation, so the result sits at the centre of the
+// reference's own fp32 rounding cloud) and, in fp16 mode, the small / irregular layers around the
 // tcgen05 convolutions (3-channel head, ESA attention branch, depthwise convs of BSRN).
 #pragma once
 #include <cuda_fp16.h>
@@ -18,6 +19,16 @@ __device__ __forceinline__ float apply_act(float v, int act, float slope) {
     default: return v;
   }
 }
+__device__ __forceinline__ double apply_act(double v, int act, float slope) {
+  switch (act) {
+    case ACT_LRELU: return v >= 0.0 ? v : v * (double)slope;
+    case ACT_RELU: return fmax(v, 0.0);
+    case ACT_GELU: return 0.5 * v * (1.0 + erf(v * 0.70710678118654752440));
+    default: return v;
+  }
+}
+__device__ __forceinline__ float sigmoid_acc(float z) { return 1.f / (1.f + expf(-z)); }
+__device__ __forceinline__ double sigmoid_acc(double z) { return 1.0 / (1.0 + exp(-z)); }
 
 // ---- 8-channel vector load/store helpers ------------------------------------------------------
 __device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
@@ -47,15 +58,13 @@ __device__ __forceinline__ void store8(__half* p, const float (&v)[8]) {
 }
 __device__ __forceinline__ float ldf(const float* p) { return *p; }
 __device__ __forceinline__ float ldf(const __half* p) { return __half2float(*p); }
-__device__ __forceinline__ void stf(float* p, float v) { *p = v; }
-__device__ __forceinline__ void stf(__half* p, float v) { *p = __float2half_rn(v); }
 
 // ---------------------------------------------------------------------------------------------
 // Head: 3x3 conv (pad 1) on the NCHW 3-channel input, NHWC output with `cstore` channels
 // (channels >= cout are written as zero so padded lanes stay finite).
 // w: [27][64] fp32, index (ky*3+kx)*3+ci; bias [64].
 // ---------------------------------------------------------------------------------------------
-template <typename TIn, typename TOut>
+template <typename TIn, typename TOut, typename TAcc>
 __global__ void __launch_bounds__(128) k_head_conv(const TIn* __restrict__ in, TOut* __restrict__ out,
                                                    const float* __restrict__ w, const float* __restrict__ bias,
                                                    int B, int H, int W, int out_stride, int cstore) {
@@ -83,16 +92,19 @@ __global__ void __launch_bounds__(128) k_head_conv(const TIn* __restrict__ in, T
     }
   TOut* o = out + pix * out_stride;
   for (int c0 = 0; c0 < cstore; c0 += 8) {
-    float acc[8];
+    TAcc acc[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = bs[c0 + j];
+    for (int j = 0; j < 8; ++j) acc[j] = (TAcc)bs[c0 + j];
 #pragma unroll
     for (int t = 0; t < 27; ++t) {
-      const float xv = xin[t];
+      const TAcc xv = (TAcc)xin[t];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv, ws[t * 64 + c0 + j], acc[j]);
+      for (int j = 0; j < 8; ++j) acc[j] = fma(xv, (TAcc)ws[t * 64 + c0 + j], acc[j]);
     }
-    store8(o + c0, acc);
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = (float)acc[j];
+    store8(o + c0, f);
   }
 }
 
@@ -101,7 +113,7 @@ __global__ void __launch_bounds__(128) k_head_conv(const TIn* __restrict__ in, T
 // models/team18_bsrn.py:82-88,218).  wpw: [3][64] (the four replicas pre-summed), bpw[64],
 // wdw: [9][64], bdw[64].
 // ---------------------------------------------------------------------------------------------
-template <typename TIn, typename TOut>
+template <typename TIn, typename TOut, typename TAcc>
 __global__ void __launch_bounds__(128) k_bsrn_head(const TIn* __restrict__ in, TOut* __restrict__ out,
                                                    const float* __restrict__ wpw, const float* __restrict__ bpw,
                                                    const float* __restrict__ wdw, const float* __restrict__ bdw,
@@ -132,23 +144,28 @@ __global__ void __launch_bounds__(128) k_bsrn_head(const TIn* __restrict__ in, T
     }
   TOut* o = out + pix * out_stride;
   for (int c0 = 0; c0 < cstore; c0 += 8) {
-    float acc[8];
+    TAcc acc[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = s_bdw[c0 + j];
+    for (int j = 0; j < 8; ++j) acc[j] = (TAcc)s_bdw[c0 + j];
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
       if (!okt[t]) continue;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int c = c0 + j;
-        float pw = s_bpw[c];
-        pw = fmaf(xin[t * 3 + 0], s_wpw[0 * 64 + c], pw);
-        pw = fmaf(xin[t * 3 + 1], s_wpw[1 * 64 + c], pw);
-        pw = fmaf(xin[t * 3 + 2], s_wpw[2 * 64 + c], pw);
-        acc[j] = fmaf(pw, s_wdw[t * 64 + c], acc[j]);
+        TAcc pw = (TAcc)s_bpw[c];
+        pw = fma((TAcc)xin[t * 3 + 0], (TAcc)s_wpw[0 * 64 + c], pw);
+        pw = fma((TAcc)xin[t * 3 + 1], (TAcc)s_wpw[1 * 64 + c], pw);
+        pw = fma((TAcc)xin[t * 3 + 2], (TAcc)s_wpw[2 * 64 + c], pw);
+        // the reference rounds the Linear output to the storage type before the depthwise conv
+        pw = (TAcc)(float)pw;
+        acc[j] = fma(pw, (TAcc)s_wdw[t * 64 + c], acc[j]);
       }
     }
-    store8(o + c0, acc);
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = (float)acc[j];
+    store8(o + c0, f);
   }
 }
 
@@ -157,7 +174,7 @@ __global__ void __launch_bounds__(128) k_bsrn_head(const TIn* __restrict__ in, T
 //   thread = one output pixel x 16 output columns (blockIdx.y selects the 16-column group)
 //   w:    [taps][cin8][cout16] fp32 (cin8 = Cin rounded up to 8, cout16 = columns rounded to 16;
 //         rows/columns beyond the logical extent are zero)
-//   out:  NHWC (columns [0,cout16) of the group are stored) or pixel-shuffle x4 NCHW
+//   out:  NHWC (16 columns of the group are stored) or pixel-shuffle x4 NCHW
 // residual is added before (res_after=0) or after (res_after=1) the activation.
 // ---------------------------------------------------------------------------------------------
 struct ConvGenericParams {
@@ -171,7 +188,7 @@ struct ConvGenericParams {
   int ps_fp32;      // dtype of the pixel-shuffled output
 };
 
-template <typename TIn, typename TOut>
+template <typename TIn, typename TOut, typename TAcc>
 __global__ void __launch_bounds__(128) k_conv_generic(const ConvGenericParams p) {
   extern __shared__ float wsm[];  // [taps][cin8][16]
   const int taps = p.ksize * p.ksize;
@@ -188,9 +205,9 @@ __global__ void __launch_bounds__(128) k_conv_generic(const ConvGenericParams p)
   const int x = (int)(pix % p.Wout);
   const int y = (int)((pix / p.Wout) % p.Hout);
   const int b = (int)(pix / ((long long)p.Wout * p.Hout));
-  float acc[16];
+  TAcc acc[16];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) acc[j] = p.bias[g * 16 + j];
+  for (int j = 0; j < 16; ++j) acc[j] = (TAcc)p.bias[g * 16 + j];
   const TIn* in = reinterpret_cast<const TIn*>(p.in);
   for (int ky = 0; ky < p.ksize; ++ky) {
     const int yy = y * p.stride + ky - p.pad;
@@ -206,13 +223,14 @@ __global__ void __launch_bounds__(128) k_conv_generic(const ConvGenericParams p)
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float4* w4 = reinterpret_cast<const float4*>(wt + (c0 + i) * 16);
+          const TAcc xa = (TAcc)xv[i];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const float4 ww = w4[q];
-            acc[4 * q + 0] = fmaf(xv[i], ww.x, acc[4 * q + 0]);
-            acc[4 * q + 1] = fmaf(xv[i], ww.y, acc[4 * q + 1]);
-            acc[4 * q + 2] = fmaf(xv[i], ww.z, acc[4 * q + 2]);
-            acc[4 * q + 3] = fmaf(xv[i], ww.w, acc[4 * q + 3]);
+            acc[4 * q + 0] = fma(xa, (TAcc)ww.x, acc[4 * q + 0]);
+            acc[4 * q + 1] = fma(xa, (TAcc)ww.y, acc[4 * q + 1]);
+            acc[4 * q + 2] = fma(xa, (TAcc)ww.z, acc[4 * q + 2]);
+            acc[4 * q + 3] = fma(xa, (TAcc)ww.w, acc[4 * q + 3]);
           }
         }
       }
@@ -229,19 +247,20 @@ __global__ void __launch_bounds__(128) k_conv_generic(const ConvGenericParams p)
 #pragma unroll
     for (int j = 0; j < 8; ++j) { rv[j] = a[j]; rv[8 + j] = c[j]; }
   }
+  float o16[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
-    float v = acc[j];
-    if (!p.res_after) v += rv[j];
+    TAcc v = acc[j];
+    if (!p.res_after) v += (TAcc)rv[j];
     v = apply_act(v, p.act, p.slope);
-    if (p.res_after) v += rv[j];
-    acc[j] = v;
+    if (p.res_after) v += (TAcc)rv[j];
+    o16[j] = (float)v;
   }
   if (!p.ps_mode) {
     TOut* o = reinterpret_cast<TOut*>(p.out) + pix * p.out_stride + p.out_coff + g * 16;
     float a[8], c[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { a[j] = acc[j]; c[j] = acc[8 + j]; }
+    for (int j = 0; j < 8; ++j) { a[j] = o16[j]; c[j] = o16[8 + j]; }
     store8(o, a);
     store8(o + 8, c);
   } else {
@@ -252,12 +271,12 @@ __global__ void __launch_bounds__(128) k_conv_generic(const ConvGenericParams p)
       const long long o = (((long long)b * 3 + g) * Ho + 4 * y + i) * Wo + 4 * x;
       if (p.ps_fp32) {
         *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o) =
-            make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+            make_float4(o16[4 * i], o16[4 * i + 1], o16[4 * i + 2], o16[4 * i + 3]);
       } else {
         uint2 u;
         __half2* h = reinterpret_cast<__half2*>(&u);
-        h[0] = __floats2half2_rn(acc[4 * i], acc[4 * i + 1]);
-        h[1] = __floats2half2_rn(acc[4 * i + 2], acc[4 * i + 3]);
+        h[0] = __floats2half2_rn(o16[4 * i], o16[4 * i + 1]);
+        h[1] = __floats2half2_rn(o16[4 * i + 2], o16[4 * i + 3]);
         *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out) + o) = u;
       }
     }
@@ -275,7 +294,7 @@ struct DwParams {
   const float* w; const float* bias;
   int c8; int act; float slope; int B, H, W;
 };
-template <typename TIn, typename TOut>
+template <typename TIn, typename TOut, typename TAcc>
 __global__ void __launch_bounds__(128) k_dwconv3x3(const DwParams p) {
   const int groups = p.c8 >> 3;
   const long long total = (long long)p.B * p.H * p.W * groups;
@@ -286,9 +305,9 @@ __global__ void __launch_bounds__(128) k_dwconv3x3(const DwParams p) {
   const int x = (int)(pix % p.W);
   const int y = (int)((pix / p.W) % p.H);
   const int b = (int)(pix / ((long long)p.W * p.H));
-  float acc[8];
+  TAcc acc[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = p.bias[g * 8 + j];
+  for (int j = 0; j < 8; ++j) acc[j] = (TAcc)p.bias[g * 8 + j];
   const TIn* in = reinterpret_cast<const TIn*>(p.in);
 #pragma unroll
   for (int ky = 0; ky < 3; ++ky) {
@@ -302,18 +321,19 @@ __global__ void __launch_bounds__(128) k_dwconv3x3(const DwParams p) {
       load8(in + (((long long)b * p.H + yy) * p.W + xx) * p.in_stride + p.in_coff + g * 8, xv);
       const float* wt = p.w + (ky * 3 + kx) * p.c8 + g * 8;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv[j], wt[j], acc[j]);
+      for (int j = 0; j < 8; ++j) acc[j] = fma((TAcc)xv[j], (TAcc)wt[j], acc[j]);
     }
   }
   if (p.res != nullptr) {
     float rv[8];
     load8(reinterpret_cast<const TOut*>(p.res) + pix * p.res_stride + p.res_coff + g * 8, rv);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] += rv[j];
+    for (int j = 0; j < 8; ++j) acc[j] += (TAcc)rv[j];
   }
+  float f[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = apply_act(acc[j], p.act, p.slope);
-  store8(reinterpret_cast<TOut*>(p.out) + pix * p.out_stride + p.out_coff + g * 8, acc);
+  for (int j = 0; j < 8; ++j) f[j] = (float)apply_act(acc[j], p.act, p.slope);
+  store8(reinterpret_cast<TOut*>(p.out) + pix * p.out_stride + p.out_coff + g * 8, f);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -340,10 +360,12 @@ __global__ void __launch_bounds__(128) k_maxpool7s3(const float* __restrict__ in
 }
 
 // ---------------------------------------------------------------------------------------------
-// ESA tail: y = x * sigmoid(conv4(bilinear(c3) + conv_f(c1_)))          (block.py:123-129)
-//   x   : NHWC T, `xs` channels per pixel; c1_: NHWC T, 16 ch; c3: NHWC fp32 16 ch at (H3,W3)
+// ESA tail: y = x * sigmoid(conv4(bilinear(c3) + cf))                    (block.py:123-129)
+//   x   : NHWC T, `x_stride` channels per pixel
+//   cf  : conv_f(c1_) when cf_ready=1 (NHWC T, 16 ch), else c1_ itself and conv_f is applied here
+//   c3  : NHWC fp32 16 ch at (H3,W3)
 //   wf  : [16][16] (in,out) fp32, bf[16];  w4: [16][64] (in,out), b4[64]
-//   thread = pixel x 16 output channels (4 threads per pixel)
+//   thread = pixel x 16 output channels (cgroups threads per pixel)
 // ---------------------------------------------------------------------------------------------
 struct EsaApplyParams {
   const void* x; int x_stride, x_coff;
@@ -352,8 +374,9 @@ struct EsaApplyParams {
   void* out; int out_stride, out_coff;
   const float* wf; const float* bf; const float* w4; const float* b4;
   int B, H, W, f, cgroups;  // f: ESA channels (<=16); cgroups: number of 16-channel output groups
+  int cf_ready;
 };
-template <typename T>
+template <typename T, typename TAcc>
 __global__ void __launch_bounds__(128) k_esa_apply(const EsaApplyParams p) {
   __shared__ float s_wf[16 * 16], s_bf[16], s_w4[16 * 64], s_b4[64];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) s_wf[i] = p.wf[i];
@@ -389,17 +412,21 @@ __global__ void __launch_bounds__(128) k_esa_apply(const EsaApplyParams p) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) { c1v[j] = a[j]; c1v[8 + j] = c[j]; }
   }
-  float s[16];
+  TAcc s[16];
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
-    // same association as ATen: rows first (top/bottom blend), then columns
-    const float top = p00[k] * (1.f - lx) + p01[k] * lx;
-    const float bot = p10[k] * (1.f - lx) + p11[k] * lx;
-    float v = top * (1.f - ly) + bot * ly;
-    float cf = s_bf[k];
+    const TAcc top = (TAcc)p00[k] * (TAcc)(1.f - lx) + (TAcc)p01[k] * (TAcc)lx;
+    const TAcc bot = (TAcc)p10[k] * (TAcc)(1.f - lx) + (TAcc)p11[k] * (TAcc)lx;
+    const TAcc v = top * (TAcc)(1.f - ly) + bot * (TAcc)ly;
+    TAcc cf;
+    if (p.cf_ready) {
+      cf = (TAcc)c1v[k];
+    } else {
+      cf = (TAcc)s_bf[k];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) cf = fmaf(c1v[i], s_wf[i * 16 + k], cf);
-    s[k] = (k < p.f) ? (v + cf) : 0.f;
+      for (int i = 0; i < 16; ++i) cf = fma((TAcc)c1v[i], (TAcc)s_wf[i * 16 + k], cf);
+    }
+    s[k] = (k < p.f) ? (v + cf) : (TAcc)0;
   }
   float xv[16];
   {
@@ -413,11 +440,10 @@ __global__ void __launch_bounds__(128) k_esa_apply(const EsaApplyParams p) {
   float o[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
-    float z = s_b4[g * 16 + j];
+    TAcc z = (TAcc)s_b4[g * 16 + j];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) z = fmaf(s[k], s_w4[k * 64 + g * 16 + j], z);
-    const float m = 1.f / (1.f + expf(-z));
-    o[j] = xv[j] * m;
+    for (int k = 0; k < 16; ++k) z = fma(s[k], (TAcc)s_w4[k * 64 + g * 16 + j], z);
+    o[j] = (float)((TAcc)xv[j] * sigmoid_acc(z));
   }
   T* op = reinterpret_cast<T*>(p.out) + pix * p.out_stride + p.out_coff + g * 16;
   float a[8], c[8];

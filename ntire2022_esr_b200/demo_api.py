@@ -1,0 +1,160 @@
+"""Drop-in for the reference's inference seam: `select_model(args, device)` and
+`forward(img_lq, model, tile=None, tile_overlap=32, scale=4)` (test_demo.py:13-341, 364-391).
+
+Same names, argument meaning, return values and error behaviour; the returned model is an
+`nn.Module` whose parameters carry the reference's state-dict names (so `load_state_dict(strict=True)`,
+`.eval()`, `.to()`, `.parameters()`, `.modules()` keep working for the reference's callers) and whose
+`forward` runs the hand-written sm_100a engine through the C ABI.  There is no PyTorch compute path:
+calling the model on a CPU tensor raises.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import specs
+from .engine import Engine, EsrError
+
+MODEL_ZOO_ENV = "ESR_MODEL_ZOO"
+
+
+class _Node(nn.Module):
+    """Anonymous container so dotted reference names ('B1.esa.conv1.weight') map to module paths."""
+
+
+class B200SRModel(nn.Module):
+    """nn.Module facade over an esr_b200 `Engine`.
+
+    arch in {'imdn','rfdn','rlfn','bsrn'}; nf / nblocks follow the reference constructors
+    (IMDN(nc=64, nb=8), RFDN(nf=50, 4 blocks), RLFN_cut(46), BSRN(num_feat=48, num_block=5)).
+    """
+
+    def __init__(self, arch: str, nf: int = 0, nblocks: int = 0):
+        super().__init__()
+        if arch not in specs.SPECS:
+            raise NotImplementedError(f"architecture {arch!r} is not implemented")
+        self.arch = arch
+        defaults = {"imdn": (64, 8), "rfdn": (50, 4), "rlfn": (46, 4), "bsrn": (48, 5)}[arch]
+        self.nf = nf or defaults[0]
+        self.nblocks = nblocks or defaults[1]
+        self._spec = specs.SPECS[arch](self.nf, self.nblocks)
+        for name, shape in self._spec.items():
+            parts = name.split(".")
+            node = self
+            for p in parts[:-1]:
+                if p not in node._modules:
+                    node.add_module(p, _Node())
+                node = node._modules[p]
+            node.register_parameter(parts[-1], nn.Parameter(torch.zeros(shape), requires_grad=False))
+        self._engine: Optional[Engine] = None
+        self._engine_key = None
+        self.engine_options = {}
+
+    # any change of device / dtype / values invalidates the packed copy inside the engine
+    def _apply(self, fn, *a, **k):
+        self._drop_engine()
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, state_dict, strict: bool = True, **kw):
+        self._drop_engine()
+        return super().load_state_dict(state_dict, strict=strict, **kw)
+
+    def _drop_engine(self):
+        if getattr(self, "_engine", None) is not None:
+            self._engine.close()
+        self._engine = None
+        self._engine_key = None
+
+    def set_engine_option(self, key: str, value: int):
+        self.engine_options[key] = int(value)
+        if self._engine is not None:
+            self._engine.set_option(key, value)
+
+    def engine(self, device: torch.device) -> Engine:
+        key = (device.type, device.index)
+        if self._engine is None or self._engine_key != key:
+            self._drop_engine()
+            if device.type != "cuda":
+                raise EsrError(-5, "B200SRModel runs only on a CUDA (sm_100) device; there is no CPU fallback")
+            idx = device.index if device.index is not None else torch.cuda.current_device()
+            eng = Engine(self.arch, idx, self.nf, self.nblocks)
+            for k, v in self.engine_options.items():
+                eng.set_option(k, v)
+            eng.load_state_dict({k: v for k, v in self.state_dict().items()})
+            self._engine, self._engine_key = eng, key
+        return self._engine
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self.engine(x.device).forward(x)
+
+
+def _find_checkpoint(fname: str) -> str:
+    # the reference resolves 'model_zoo/<file>' against the CWD (test_demo.py:21,28,56,154)
+    cands = [os.path.join("model_zoo", fname)]
+    if os.environ.get(MODEL_ZOO_ENV):
+        cands.append(os.path.join(os.environ[MODEL_ZOO_ENV], fname))
+    for c in cands:
+        if os.path.exists(c):
+            return c
+    raise FileNotFoundError(f"{cands[0]} not found (set {MODEL_ZOO_ENV} to the reference's model_zoo directory)")
+
+
+def build_model(model_id: int, state_dict=None) -> B200SRModel:
+    """Construct + load; `state_dict` (name -> array/tensor) overrides the model_zoo lookup."""
+    if model_id == 26:  # IMDN nb=7 (test_demo.py:203-209)
+        reg = dict(arch="imdn", kwargs=dict(nf=64, nblocks=7), file="team26_imdn_nb7.pth", wrap=None)
+    elif model_id in specs.REGISTRY:
+        reg = specs.REGISTRY[model_id]
+    else:
+        raise NotImplementedError(f"Model {model_id} is not implemented.")
+    model = B200SRModel(reg["arch"], **reg["kwargs"])
+    if state_dict is None:
+        sd = torch.load(_find_checkpoint(reg["file"]), map_location="cpu")
+        if reg["wrap"]:
+            sd = sd[reg["wrap"]]
+    else:
+        sd = {k: torch.as_tensor(v) for k, v in state_dict.items()}
+    model.load_state_dict(sd, strict=True)
+    return model
+
+
+def select_model(args, device):
+    """test_demo.select_model for the accelerated ids (-1 IMDN, 0 RFDN, 4 RLFN, 18 BSRN, 26 IMDN nb=7)."""
+    model_id = args.model_id
+    if model_id == 26:
+        name, data_range = f"{model_id:02}_IMDN", 1.0
+    elif model_id in specs.REGISTRY:
+        name, data_range = f"{model_id:02}_{specs.REGISTRY[model_id]['name']}", specs.REGISTRY[model_id]["data_range"]
+    else:
+        raise NotImplementedError(f"Model {model_id} is not implemented.")
+    model = build_model(model_id)
+    model.eval()
+    tile = 256 if model_id == 2 else None
+    for _, v in model.named_parameters():
+        v.requires_grad = False
+    model = model.to(device)
+    return model, name, data_range, tile
+
+
+def forward(img_lq, model, tile=None, tile_overlap=32, scale=4):
+    """test_demo.forward: whole image, or overlapping tiles accumulated in E and normalised by the
+    per-pixel coverage count W (test_demo.py:368-389)."""
+    if tile is None:
+        return model(img_lq)
+    b, c, h, w = img_lq.size()
+    tile = min(tile, h, w)
+    stride = tile - tile_overlap
+    ys = list(range(0, h - tile, stride)) + [h - tile]
+    xs = list(range(0, w - tile, stride)) + [w - tile]
+    acc = torch.zeros(b, c, h * scale, w * scale, dtype=img_lq.dtype, device=img_lq.device)
+    cover = torch.zeros_like(acc)
+    for y0 in ys:
+        for x0 in xs:
+            patch = model(img_lq[..., y0:y0 + tile, x0:x0 + tile].contiguous())
+            sl = (..., slice(y0 * scale, (y0 + tile) * scale), slice(x0 * scale, (x0 + tile) * scale))
+            acc[sl] += patch
+            cover[sl] += 1
+    return acc.div_(cover)

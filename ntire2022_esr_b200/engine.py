@@ -1,0 +1,136 @@
+"""Python mirror of the C ABI: one `Engine` = one esr_handle bound to one CUDA device.
+
+`Engine` replaces the reference's module construction + `load_state_dict(strict=True)` + `.to(device)`
+(test_demo.py:17-30,52-58,150-157,336-340) and `model(img_lq)` (test_demo.py:367).  PyTorch is only
+used for device memory and the current stream; all compute happens in libesr_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Mapping, Optional
+
+import numpy as np
+
+from . import _cabi
+from ._cabi import EsrError, lib
+
+ARCHS = {"imdn": _cabi.ARCH_IMDN, "rfdn": _cabi.ARCH_RFDN, "rlfn": _cabi.ARCH_RLFN, "bsrn": _cabi.ARCH_BSRN}
+
+
+def _as_f32_numpy(v) -> np.ndarray:
+    if hasattr(v, "detach"):  # torch tensor
+        v = v.detach().to("cpu").float().numpy()
+    return np.ascontiguousarray(np.asarray(v, dtype=np.float32))
+
+
+class Engine:
+    """esr_handle wrapper.  device=-1 gives a host-only handle (weights can be loaded and checked,
+    every compute call raises: the engine has no CPU path)."""
+
+    def __init__(self, arch: str, device: int = 0, nf: int = 0, nblocks: int = 0):
+        if arch not in ARCHS:
+            raise NotImplementedError(f"architecture {arch!r} is not on the accelerated path")
+        self.arch = arch
+        self.device = device
+        self._h = ctypes.c_void_p()
+        rc = lib.esr_create(ctypes.byref(self._h), ARCHS[arch], nf, nblocks, device)
+        if rc != _cabi.OK:
+            self._h = ctypes.c_void_p()
+            msg = {_cabi.E_NOGPU: f"CUDA device {device} is not a usable sm_100 GPU (no CPU fallback exists)",
+                   _cabi.E_INVALID: "invalid architecture / width / depth"}.get(rc, "esr_create failed")
+            raise EsrError(rc, msg)
+        self._finalized = False
+        self._ws = None
+
+    # -- lifetime ---------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            lib.esr_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != _cabi.OK:
+            raise EsrError(rc, (lib.esr_last_error(self._h) or b"").decode())
+
+    # -- weights ----------------------------------------------------------------------------------
+    def load_state_dict(self, state_dict: Mapping[str, object]):
+        """strict=True semantics: missing / unexpected / mis-shaped entries raise at finalize."""
+        for name, v in state_dict.items():
+            a = _as_f32_numpy(v)
+            shape = (ctypes.c_int64 * max(a.ndim, 1))(*a.shape)
+            self._check(lib.esr_load_weights(self._h, name.encode(), a.ctypes.data_as(ctypes.c_void_p), shape, a.ndim))
+        self._check(lib.esr_finalize(self._h))
+        self._finalized = True
+        return self
+
+    def set_option(self, key: str, value: int):
+        self._check(lib.esr_set_option(self._h, key.encode(), int(value)))
+
+    # -- queries ----------------------------------------------------------------------------------
+    def workspace_bytes(self, B: int, H: int, W: int, dtype: int) -> int:
+        n = lib.esr_workspace_bytes(self._h, B, H, W, dtype)
+        if n == 0:
+            raise EsrError(_cabi.E_INVALID, (lib.esr_last_error(self._h) or b"").decode())
+        return n
+
+    def launch_names(self, B: int, H: int, W: int, dtype: int):
+        n = lib.esr_launch_count(self._h, B, H, W, dtype)
+        return [lib.esr_launch_name(self._h, B, H, W, dtype, i).decode() for i in range(n)]
+
+    # -- compute ----------------------------------------------------------------------------------
+    def forward(self, x, out=None):
+        """x: CUDA torch tensor (B,3,H,W) fp32 or fp16 on this engine's device -> (B,3,4H,4W)."""
+        import torch
+
+        if not x.is_cuda:
+            raise EsrError(_cabi.E_NOGPU, "input is not a CUDA tensor; the engine has no CPU fallback")
+        if x.device.index != self.device:
+            raise EsrError(_cabi.E_INVALID, f"input on {x.device}, engine bound to cuda:{self.device}")
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise EsrError(_cabi.E_INVALID, f"expected (B,3,H,W), got {tuple(x.shape)}")
+        if x.dtype == torch.float32:
+            dt = _cabi.DTYPE_F32
+        elif x.dtype == torch.float16:
+            dt = _cabi.DTYPE_F16
+        else:
+            raise EsrError(_cabi.E_INVALID, f"unsupported dtype {x.dtype}")
+        x = x.contiguous()
+        B, _, H, W = x.shape
+        need = self.workspace_bytes(B, H, W, dt)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=x.device)
+        if out is None:
+            out = torch.empty((B, 3, 4 * H, 4 * W), dtype=x.dtype, device=x.device)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        self._check(lib.esr_forward(self._h, x.data_ptr(), out.data_ptr(), B, H, W, dt, self._ws.data_ptr(),
+                                    self._ws.numel(), stream))
+        return out
+
+    def forward_host(self, x: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """x: host array (B,3,H,W) float32 / float16; copies in, runs, copies out, synchronises."""
+        x = np.ascontiguousarray(x)
+        if x.dtype == np.float32:
+            dt = _cabi.DTYPE_F32
+        elif x.dtype == np.float16:
+            dt = _cabi.DTYPE_F16
+        else:
+            raise EsrError(_cabi.E_INVALID, f"unsupported dtype {x.dtype}")
+        if x.ndim != 4 or x.shape[1] != 3:
+            raise EsrError(_cabi.E_INVALID, f"expected (B,3,H,W), got {x.shape}")
+        B, _, H, W = x.shape
+        if out is None:
+            out = np.empty((B, 3, 4 * H, 4 * W), dtype=x.dtype)
+        self._check(lib.esr_forward_host(self._h, x.ctypes.data_as(ctypes.c_void_p),
+                                         out.ctypes.data_as(ctypes.c_void_p), B, H, W, dt))
+        return out
+
+    def forward_host_ptr(self, in_ptr: int, out_ptr: int, B: int, H: int, W: int, dt: int):
+        """Raw-pointer variant (pinned torch tensors): no numpy wrapping on the timed path."""
+        self._check(lib.esr_forward_host(self._h, in_ptr, out_ptr, B, H, W, dt))

@@ -1,0 +1,141 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol include/esr_b200.h declares,
+host-side weight checking (strict load_state_dict semantics), and the drop-in module facade.
+No compute call is made here (there is no CPU path in the engine)."""
+import os
+import re
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import esr_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ARCHS = [(-1, "imdn"), (0, "rfdn"), (4, "rlfn"), (18, "bsrn")]
+
+
+def _weights(mid):
+    return O.load_weights(os.path.join(ROOT, "tests", "golden", "weights", O.MODELS[mid]["weights"] + ".npz"))
+
+
+def test_library_exports_every_declared_symbol():
+    from ntire2022_esr_b200 import _cabi
+
+    header = open(os.path.join(ROOT, "include", "esr_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(esr_[a-z_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    bound = {s[0] for s in _cabi.SYMBOLS}
+    assert declared == bound, (declared ^ bound)
+    for name in declared:
+        assert hasattr(_cabi.lib, name)
+    assert b"sm_100a" in _cabi.lib.esr_version()
+    assert _cabi.lib.esr_device_ok(-1) == 0
+
+
+@pytest.mark.parametrize("mid,arch", ARCHS)
+def test_strict_state_dict_and_plan_names(mid, arch):
+    from ntire2022_esr_b200 import Engine, EsrError, _cabi
+
+    w = _weights(mid)
+    e = Engine(arch, device=-1)
+    e.load_state_dict(w)
+    n32 = e.launch_names(1, 64, 64, _cabi.DTYPE_F32)
+    n16 = e.launch_names(1, 64, 64, _cabi.DTYPE_F16)
+    assert n32 and n16 and not any(n.startswith("conv_tc") for n in n32)
+    assert any(n.startswith("conv_tc") for n in n16)
+    assert e.workspace_bytes(2, 64, 48, _cabi.DTYPE_F16) > 0
+    with pytest.raises(EsrError) as ei:  # no GPU bound -> loud failure, never a CPU fallback
+        e.forward_host(np.zeros((1, 3, 32, 32), np.float32))
+    assert ei.value.code == _cabi.E_NOGPU
+    if arch != "imdn":
+        with pytest.raises(EsrError):  # ESA needs H, W >= 15
+            e.workspace_bytes(1, 14, 20, _cabi.DTYPE_F32)
+    # missing key
+    k = sorted(w)[5]
+    e2 = Engine(arch, device=-1)
+    with pytest.raises(EsrError, match="missing key"):
+        e2.load_state_dict({a: b for a, b in w.items() if a != k})
+    # unexpected key
+    e3 = Engine(arch, device=-1)
+    with pytest.raises(EsrError, match="unexpected key"):
+        e3.load_state_dict({**w, "extra.weight": np.zeros(3, np.float32)})
+    # wrong shape
+    e4 = Engine(arch, device=-1)
+    bad = dict(w)
+    bad[k] = np.zeros(tuple(s + 1 for s in w[k].shape), np.float32)
+    with pytest.raises(EsrError, match="size mismatch"):
+        e4.load_state_dict(bad)
+
+
+@pytest.mark.parametrize("mid,arch", ARCHS)
+def test_module_facade_matches_reference_state_dict_contract(mid, arch):
+    from ntire2022_esr_b200 import EsrError, build_model
+
+    w = _weights(mid)
+    m = build_model(mid, state_dict=w)
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(w.keys())          # same names, same order as the reference module
+    for k in w:
+        assert tuple(sd[k].shape) == w[k].shape
+        np.testing.assert_array_equal(sd[k].numpy(), w[k])
+    assert isinstance(m, torch.nn.Module)
+    assert sum(p.numel() for p in m.parameters()) == sum(v.size for v in w.values())
+    m.eval()
+    assert len(list(m.modules())) > 1
+    with pytest.raises(RuntimeError):                  # strict=True
+        m.load_state_dict({k: torch.as_tensor(v) for k, v in list(w.items())[:-1]}, strict=True)
+    with pytest.raises(EsrError):                      # CPU tensors are refused, not silently computed
+        m(torch.zeros(1, 3, 32, 32))
+
+
+def test_select_model_contract(tmp_path, monkeypatch):
+    from ntire2022_esr_b200 import select_model
+    from ntire2022_esr_b200 import specs
+
+    zoo = tmp_path / "model_zoo"
+    zoo.mkdir()
+    for mid, arch in ARCHS:
+        reg = specs.REGISTRY[mid]
+        sd = {k: torch.from_numpy(v) for k, v in _weights(mid).items()}
+        torch.save({reg["wrap"]: sd} if reg["wrap"] else sd, zoo / reg["file"])
+    monkeypatch.chdir(tmp_path)                         # reference paths are CWD-relative
+    names = {-1: "-1_IMDN_baseline", 0: "00_RFDN_baseline", 4: "04_RLFN", 18: "18_RFDNFINALB5"}
+    for mid, arch in ARCHS:
+        model, name, data_range, tile = select_model(types.SimpleNamespace(model_id=mid), torch.device("cpu"))
+        assert name == names[mid] == O.MODELS[mid]["name"]
+        assert data_range == O.MODELS[mid]["data_range"]
+        assert tile is None
+        assert not model.training and all(not p.requires_grad for p in model.parameters())
+    with pytest.raises(NotImplementedError):
+        select_model(types.SimpleNamespace(model_id=99), torch.device("cpu"))
+
+
+def test_tiled_forward_accumulate_and_divide():
+    """forward(tile=...) bookkeeping (test_demo.py:368-389) with a stand-in model on CPU."""
+    from ntire2022_esr_b200 import forward
+
+    class Up(torch.nn.Module):
+        def forward(self, x):
+            y = torch.nn.functional.interpolate(x, scale_factor=4, mode="nearest")
+            return y + x.mean()                         # depends on the tile content
+
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(2, 3, 37, 29, generator=g)
+    out = forward(x, Up(), tile=16, tile_overlap=4)
+    # independent restatement
+    tile, stride = 16, 12
+    ys = list(range(0, 37 - tile, stride)) + [37 - tile]
+    xs = list(range(0, 29 - tile, stride)) + [29 - tile]
+    e = np.zeros((2, 3, 148, 116), np.float64)
+    wsum = np.zeros_like(e)
+    for a in ys:
+        for b in xs:
+            p = x[..., a:a + tile, b:b + tile]
+            o = Up()(p).double().numpy()
+            e[..., 4 * a:4 * (a + tile), 4 * b:4 * (b + tile)] += o
+            wsum[..., 4 * a:4 * (a + tile), 4 * b:4 * (b + tile)] += 1
+    np.testing.assert_allclose(out.numpy(), e / wsum, rtol=1e-6, atol=1e-6)
+    assert out.shape == (2, 3, 148, 116)
+    torch.testing.assert_close(forward(x, Up(), tile=None), Up()(x))

@@ -1,0 +1,78 @@
+"""Developer probe (GPU box): one arch / dtype / engine-option combination vs the numpy oracle.
+
+    python tools/gpu_check.py rfdn f16 --tc 1 --shift 1 --size 64 64 --batch 1
+"""
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import esr_oracle as O  # noqa: E402
+
+IDS = {"imdn": -1, "rfdn": 0, "rlfn": 4, "bsrn": 18}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("arch")
+    ap.add_argument("dtype", choices=["f32", "f16"])
+    ap.add_argument("--tc", type=int, default=1)
+    ap.add_argument("--shift", type=int, default=0)
+    ap.add_argument("--graph", type=int, default=0)
+    ap.add_argument("--rows", type=int, default=0)
+    ap.add_argument("--size", type=int, nargs=2, default=[64, 64])
+    ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--host", type=int, default=0)
+    ap.add_argument("--time", type=int, default=0)
+    a = ap.parse_args()
+    import torch
+    from ntire2022_esr_b200 import Engine
+
+    mid = IDS[a.arch]
+    w = O.load_weights(os.path.join(ROOT, "tests", "golden", "weights", O.MODELS[mid]["weights"] + ".npz"))
+    dr = O.MODELS[mid]["data_range"]
+    rng = np.random.default_rng(1)
+    h, wd = a.size
+    x = (rng.random((a.batch, 3, h, wd), dtype=np.float32) * dr).astype(np.float16 if a.dtype == "f16" else np.float32)
+    eng = Engine(a.arch, 0)
+    eng.set_option("tc_enable", a.tc)
+    eng.set_option("tc_shift_mode", a.shift)
+    eng.set_option("use_graph", a.graph)
+    eng.set_option("tc_rows_per_item", a.rows)
+    eng.load_state_dict(w)
+    if a.host:
+        y = eng.forward_host(x)
+    else:
+        xt = torch.from_numpy(x).cuda()
+        yt = eng.forward(xt)
+        torch.cuda.synchronize()
+        y = yt.cpu().numpy()
+    t0 = time.time()
+    ref = O.forward(a.arch, w, x.astype(np.float32), dtype=np.float64 if a.dtype == "f32" else np.float32)
+    t1 = time.time()
+    err = np.abs(y.astype(np.float64) - ref).max() / dr
+    mse = np.mean((y.astype(np.float64) - ref) ** 2) / dr ** 2
+    psnr = 10 * np.log10(1.0 / mse) if mse > 0 else float("inf")
+    print(f"CHECK {a.arch} {a.dtype} tc={a.tc} shift={a.shift} graph={a.graph} {a.batch}x{h}x{wd} host={a.host}: "
+          f"max|err|/range={err:.3e} psnr={psnr:.2f} dB finite={np.isfinite(y).all()} (oracle {t1 - t0:.1f}s)", flush=True)
+    if a.time and not a.host:
+        for _ in range(5):
+            eng.forward(xt, out=yt)
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(a.time):
+            eng.forward(xt, out=yt)
+        ev1.record()
+        torch.cuda.synchronize()
+        print(f"TIME {a.arch} {a.dtype} tc={a.tc} graph={a.graph} {a.batch}x{h}x{wd}: {ev0.elapsed_time(ev1) / a.time * 1e3:.1f} us/forward",
+              flush=True)
+
+
+if __name__ == "__main__":
+    main()
