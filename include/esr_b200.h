@@ -72,8 +72,23 @@ int esr_launch_count(esr_handle* h, int B, int H, int W, int dtype);
 /* Name of the i-th launch of that plan ("conv_tc", "conv_generic", ...), or NULL. */
 const char* esr_launch_name(esr_handle* h, int B, int H, int W, int dtype, int i);
 
-/* Runtime knobs (tuning / A-B measurements): "tc_shift_mode", "use_graph", "tc_rows_per_item". */
+/* Algorithmic FLOPs (2 x un-padded MACs) of the i-th launch of that plan. */
+double esr_launch_flops(esr_handle* h, int B, int H, int W, int dtype, int i);
+
+/* Measurement aid for bench.py's roofline: runs the plan of one forward launch by launch, each launch
+ * repeated `reps` times between two CUDA events on `stream`, and writes the mean milliseconds of
+ * every launch to ms_out[0..n).  Returns the number of launches (>0) or a negative ESR_E_* code.
+ * Same arguments as esr_forward; synchronises the stream. */
+int esr_profile_launches(esr_handle* h, const void* in_nchw, void* out_nchw, int B, int H, int W, int dtype,
+                         void* workspace, size_t workspace_bytes, int reps, float* ms_out, int n, void* stream);
+
+/* Runtime knobs (tuning / A-B measurements): "tc_enable" (fp16: tcgen05 convolutions on/off),
+ * "tc_shift_mode", "use_graph", "tc_rows_per_item", "tc_timeline". */
 int esr_set_option(esr_handle* h, const char* key, int value);
+
+/* Debug aid: with option "tc_timeline" = 1 every tcgen05 launch records clock64 stamps of block 0
+ * (128 per launch: 4 roles x 32 events); copies the first n_launches records to `out`. */
+int esr_debug_timeline(esr_handle* h, long long* out, int n_launches);
 
 const char* esr_last_error(esr_handle* h);
 void esr_destroy(esr_handle* h);

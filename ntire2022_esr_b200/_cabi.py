@@ -1,6 +1,6 @@
 """ctypes binding of the C ABI declared in include/esr_b200.h (libesr_b200.so).
 
-The library is built in-tree by `__graft_entry__.build()` / `python -m ntire2022_esr_b200.build`.
+The library is built in-tree by `__graft_entry__.build()` / `python ntire2022_esr_b200/build.py`.
 There is deliberately no fallback: if the shared object is missing, importing this module raises.
 """
 from __future__ import annotations
@@ -27,7 +27,11 @@ SYMBOLS = [
     ("esr_forward_host", _c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int]),
     ("esr_launch_count", _c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int]),
     ("esr_launch_name", _c.c_char_p, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int]),
+    ("esr_launch_flops", _c.c_double, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int]),
+    ("esr_profile_launches", _c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
+                                        _c.c_void_p, _c.c_size_t, _c.c_int, _c.POINTER(_c.c_float), _c.c_int, _c.c_void_p]),
     ("esr_set_option", _c.c_int, [_c.c_void_p, _c.c_char_p, _c.c_int]),
+    ("esr_debug_timeline", _c.c_int, [_c.c_void_p, _c.POINTER(_c.c_longlong), _c.c_int]),
     ("esr_last_error", _c.c_char_p, [_c.c_void_p]),
     ("esr_destroy", None, [_c.c_void_p]),
     ("esr_version", _c.c_char_p, []),
@@ -38,7 +42,7 @@ SYMBOLS = [
 def load_library(path: str = LIB_PATH) -> ctypes.CDLL:
     if not os.path.exists(path):
         raise ImportError(
-            f"{path} not found: build the CUDA extension first (python -m ntire2022_esr_b200.build); "
+            f"{path} not found: build the CUDA extension first (python ntire2022_esr_b200/build.py); "
             "this engine has no CPU / PyTorch fallback")
     lib = ctypes.CDLL(path)
     for name, restype, argtypes in SYMBOLS:

@@ -1,6 +1,6 @@
 """In-tree build of libesr_b200.so (hand-written sm_100a CUDA + the C ABI) with nvcc.
 
-    python -m ntire2022_esr_b200.build [--force]
+    python ntire2022_esr_b200/build.py [--force] [-v]
 
 nvcc cross-compiles without a GPU; the .so is git-ignored but travels with the repo snapshot.
 """

@@ -5,15 +5,21 @@
 // image-row strip [130 px x 64 ch] lands in shared memory through ONE TMA box load in exactly the
 // K-major SWIZZLE_128B layout tcgen05.mma wants (one pixel = one 128-byte row).  The 3x3 taps are
 // not materialised: tap (dy,dx) is the same strip ring with the descriptor start address moved by
-// dy strips and dx rows, so every input row is read from L2 once per strip (im2col-free, and the
-// zero padding is TMA out-of-bounds fill).  A persistent CTA walks down a column strip keeping a
-// ring of row strips in shared memory; weights are staged once per CTA as pre-swizzled blocks.
+// dy strips and dx rows (the swizzle is a function of the absolute shared-memory address, so a
+// row-shifted start needs no re-layout), so every input row is read from L2 once per strip
+// (im2col-free, and the zero padding is TMA out-of-bounds fill).  A persistent CTA walks down a
+// column strip keeping a ring of row strips in shared memory; weights are staged once per CTA as
+// pre-swizzled blocks.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
-// warps 2..5 = epilogue (TMEM -> registers -> bias/residual/activation -> fp16 -> swizzled staging
-// -> TMA store, or the fused pixel-shuffle store of the network tail).  Two TMEM accumulator slots
-// let the epilogue of tile t overlap the MMAs of tile t+1.
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (one elected
+// lane each), warps 2..5 = epilogue (TMEM -> registers -> bias/residual/activation -> fp16 ->
+// swizzled staging -> TMA store, or the fused pixel-shuffle store of the network tail).  Two TMEM
+// accumulator slots let the epilogue of tile t overlap the MMAs of tile t+1.
+//
+// Measured on B200 (tools/micro/mma_bench.cu): an M=128, K=16 SS-mode MMA costs 32 + N/4 cycles for
+// N <= 128 (A and B are both fetched from shared memory at 128 B/clk), i.e. 48 cycles at N = 64.
 #pragma once
+#include "kernels_generic.cuh"
 #include "tc_common.cuh"
 
 namespace esr {
@@ -23,20 +29,18 @@ constexpr int TC_TILE_PX = 128;
 constexpr int TC_MAX_SLOTS = 8;
 constexpr int TC_THREADS = 192;
 
-struct TcEntry {
-  int16_t row;     // strip of the tile's row window (0 .. 2*halo)
-  int16_t px_off;  // first pixel of the strip used by this tap (dx + halo)
-  int16_t chunk;   // 64-channel chunk of the strip
-  int16_t nsteps;  // K=16 steps issued (ceil(real channels / 16))
-  int32_t b_off;   // byte offset of the [n x 64] pre-swizzled weight block
-  int16_t n;       // MMA N (multiple of 16)
-  int16_t dcol;    // first accumulator column
-  int32_t first;   // 1: first MMA of the entry overwrites the accumulator columns
+struct __align__(16) TcEntry {
+  uint32_t a_off;   // chunk * chunk_bytes + px_off * 128 (bytes inside a ring slot)
+  uint32_t b_off;   // byte offset of the [n x 64] pre-swizzled weight block inside the blob
+  uint32_t idesc;   // instruction descriptor (M = 128, N = n)
+  uint16_t dcol;    // first accumulator column
+  uint8_t row;      // strip of the tile's row window (0 .. 2*halo)
+  uint8_t steps_first;  // bits 0-3: K=16 steps issued, bit 7: first MMA overwrites the accumulator
 };
 
 struct TcOutGroup {
   int32_t col0;        // first accumulator column of the group
-  int32_t ncols;       // columns stored (multiple of 8, <= 64)
+  int32_t ncols;       // columns stored (multiple of 16, <= 64)
   int32_t act;         // Act
   float slope;
   int32_t res_after;   // residual added after (1) or before (0) the activation
@@ -46,7 +50,7 @@ struct TcOutGroup {
   int32_t swizzle;     // staging layout of the store tensor map (1 = SWIZZLE_128B, 0 = linear)
   int32_t stage_off;   // smem offset of the two staging buffers
   int32_t stage_bytes; // bytes of one staging buffer
-  int32_t pad_;
+  int32_t bias_off;    // float offset of this group's bias inside the kernel's bias table
   const float* bias;   // [ncols]
   const __half* res;   // nullptr = none
 };
@@ -65,24 +69,101 @@ struct TcParams {
   int32_t tmem_cols;     // TMEM allocation (power of two >= 2*acc_cols)
   int32_t acc_cols;      // columns of one accumulator slot
   int32_t w_off, w_bytes, ring_off;
-  int32_t shift_mode;    // 0: base_offset 0 for shifted starts, 1: base_offset = row phase
   int32_t ps_fp32;
+  int32_t dbg_flags;     // experiments: 1 = issue no MMA, 2 = epilogue does no work
   int32_t chunk_c0[4];   // channel coordinate of each chunk in the A tensor
   const uint8_t* wblob;
   void* ps_out;
+  long long* dbg;        // optional timeline buffer (block 0 only): [role][event] clock64 stamps
   TcEntry e[TC_MAX_ENTRIES];
   TcOutGroup g[2];
 };
 
-__device__ __forceinline__ void tc_decode_item(const TcParams& p, int item, int& b, int& y0, int& y1, int& x0) {
-  const int per_img = p.strips_x * p.segs_y;
-  b = item / per_img;
-  const int rem = item - b * per_img;
-  const int seg = rem / p.strips_x;
-  const int sx = rem - seg * p.strips_x;
-  y0 = seg * p.rows_per_item;
-  y1 = min(y0 + p.rows_per_item, p.H);
-  x0 = sx * TC_TILE_PX;
+#define TC_STAMP(role, idx)                                                                        \
+  do {                                                                                             \
+    if (dbg != nullptr && blockIdx.x == 0 && (idx) < 32) dbg[(role) * 32 + (idx)] = clock64();      \
+  } while (0)
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16_nc(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+// MMA without a memory clobber: ordering against the barrier waits / commits comes from `volatile`
+__device__ __forceinline__ void umma_f16_ss_nc(uint32_t tmem_d, uint32_t adesc_lo, uint32_t bdesc_lo, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "r"(adesc_lo), "r"(bdesc_lo), "r"(idesc), "r"(accumulate), "r"(0x40004040u));
+}
+
+// One output group of one tile: 16 or 32 accumulator columns at a time.
+template <int NC>
+__device__ __forceinline__ void tc_epi_chunk(uint32_t taddr, const float* __restrict__ bias_s, int act, float slope,
+                                             const uint4* res_v, bool has_res, int res_after, float (&f)[NC]) {
+  uint32_t v[NC];
+  if constexpr (NC == 32) {
+    tmem_ld32(taddr, *reinterpret_cast<uint32_t(*)[32]>(v));
+  } else {
+    tmem_ld16_nc(taddr, v);
+  }
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < NC; j += 4) {
+    const float4 b4 = *reinterpret_cast<const float4*>(bias_s + j);
+    f[j] = __uint_as_float(v[j]) + b4.x;
+    f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+    f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
+    f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+  }
+  float rv[NC];
+  if (has_res) {
+#pragma unroll
+    for (int q = 0; q < NC / 8; ++q) {
+      const __half2* h = reinterpret_cast<const __half2*>(&res_v[q]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 a = __half22float2(h[j]);
+        rv[q * 8 + 2 * j] = a.x;
+        rv[q * 8 + 2 * j + 1] = a.y;
+      }
+    }
+    if (!res_after) {
+#pragma unroll
+      for (int j = 0; j < NC; ++j) f[j] += rv[j];
+    }
+  }
+  if (act == ACT_LRELU) {
+#pragma unroll
+    for (int j = 0; j < NC; ++j) f[j] = fmaxf(f[j], f[j] * slope);   // slope < 1
+  } else if (act == ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < NC; ++j) f[j] = 0.5f * f[j] * (1.f + erff(f[j] * 0.70710678118654752440f));
+  } else if (act == ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < NC; ++j) f[j] = fmaxf(f[j], 0.f);
+  }
+  if (has_res && res_after) {
+#pragma unroll
+    for (int j = 0; j < NC; ++j) f[j] += rv[j];
+  }
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -91,20 +172,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[TC_MAX_SLOTS], empty_bar[TC_MAX_SLOTS], tfull_bar[2], tempty_bar[2], w_bar;
   __shared__ uint32_t tmem_base_s;
-  __shared__ float bias_s[2][64];
+  __shared__ __align__(16) float bias_s[2][64];
+  __shared__ __align__(16) TcEntry ent_s[TC_MAX_ENTRIES];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long* const dbg = p.dbg;
+  if (threadIdx.x == 0) TC_STAMP(0, 0);
   // 1024-byte aligned view of dynamic shared memory (SWIZZLE_128B atoms)
   const uint32_t raw_u32 = smem_u32(smem_raw);
   const uint32_t pad = (1024u - (raw_u32 & 1023u)) & 1023u;
-  uint8_t* smem = smem_raw + pad;
+  uint8_t* const smem = smem_raw + pad;
   const uint32_t smem_base = raw_u32 + pad;
+
+  // hoist every parameter the role loops touch into registers once (the param bank is re-read after
+  // each asm volatile with a memory clobber otherwise)
+  const int S = p.nslots, halo = p.halo, nchunks = p.nchunks, strip_bytes = p.strip_bytes, chunk_bytes = p.chunk_bytes;
+  const int n_items = p.n_items, strips_x = p.strips_x, segs_y = p.segs_y, rows_per_item = p.rows_per_item;
+  const int H = p.H, W = p.W, ring_off = p.ring_off, acc_cols = p.acc_cols, n_entries = p.n_entries, ngroups = p.ngroups;
+  const int dbg_flags = p.dbg_flags;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmO0);
     tma_prefetch_desc(&tmO1);
-    for (int i = 0; i < p.nslots; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < S; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
     mbar_init(&w_bar, 1);
     fence_mbar_init();
@@ -112,76 +203,106 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) tmem_alloc(&tmem_base_s, (uint32_t)p.tmem_cols);
   for (int i = threadIdx.x; i < 128; i += blockDim.x) {
     const int g = i >> 6, c = i & 63;
-    bias_s[g][c] = (g < p.ngroups && c < p.g[g].ncols) ? p.g[g].bias[c] : 0.f;
+    bias_s[g][c] = (g < ngroups && c < p.g[g].ncols) ? p.g[g].bias[c] : 0.f;
   }
+  if (threadIdx.x < TC_MAX_ENTRIES) ent_s[threadIdx.x] = p.e[threadIdx.x];
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_s;
-  const int S = p.nslots;
+  if (threadIdx.x == 0) TC_STAMP(0, 1);
+
+  auto decode = [&](int item, int& b, int& y0, int& y1, int& x0) {
+    const int per_img = strips_x * segs_y;
+    b = item / per_img;
+    const int rem = item - b * per_img;
+    const int seg = rem / strips_x;
+    const int sx = rem - seg * strips_x;
+    y0 = seg * rows_per_item;
+    y1 = min(y0 + rows_per_item, H);
+    x0 = sx * TC_TILE_PX;
+  };
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_arrive_expect_tx(&w_bar, (uint32_t)p.w_bytes);
       bulk_load_1d(smem + p.w_off, p.wblob, (uint32_t)p.w_bytes, &w_bar);
-      const uint32_t strip_tx = (uint32_t)(p.nchunks * p.strip_px * 128);
-      uint32_t seq = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      const uint32_t strip_tx = (uint32_t)(nchunks * p.strip_px * 128);
+      const int c0 = p.chunk_c0[0], c1 = p.chunk_c0[1], c2 = p.chunk_c0[2], c3 = p.chunk_c0[3];
+      uint32_t slot = 0, par = 0, seq = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         int b, y0, y1, x0;
-        tc_decode_item(p, item, b, y0, y1, x0);
-        for (int row = y0 - p.halo; row < y1 + p.halo; ++row, ++seq) {
-          const uint32_t slot = seq % S, par = (seq / S) & 1;
+        decode(item, b, y0, y1, x0);
+        for (int row = y0 - halo; row < y1 + halo; ++row, ++seq) {
           mbar_wait(&empty_bar[slot], par ^ 1);
           mbar_arrive_expect_tx(&full_bar[slot], strip_tx);
-          for (int c = 0; c < p.nchunks; ++c)
-            tma_load_4d(&tmA, &full_bar[slot], smem + p.ring_off + slot * p.strip_bytes + c * p.chunk_bytes,
-                        p.chunk_c0[c], x0 - p.halo, row, b);
+          uint8_t* dst = smem + ring_off + slot * strip_bytes;
+          tma_load_4d(&tmA, &full_bar[slot], dst, c0, x0 - halo, row, b);
+          if (nchunks > 1) tma_load_4d(&tmA, &full_bar[slot], dst + chunk_bytes, c1, x0 - halo, row, b);
+          if (nchunks > 2) tma_load_4d(&tmA, &full_bar[slot], dst + 2 * chunk_bytes, c2, x0 - halo, row, b);
+          if (nchunks > 3) tma_load_4d(&tmA, &full_bar[slot], dst + 3 * chunk_bytes, c3, x0 - halo, row, b);
+          TC_STAMP(1, seq);
+          if (++slot == (uint32_t)S) { slot = 0; par ^= 1; }
         }
       }
+      TC_STAMP(0, 2);
     }
+    __syncwarp();
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_wait(&w_bar, 0);
-      const uint32_t ring_base = smem_base + p.ring_off;
-      const uint32_t w_base = smem_base + p.w_off;
-      uint32_t waited = 0, released = 0, seq_base = 0, t = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      TC_STAMP(0, 3);
+      const uint32_t ring_base = smem_base + ring_off;
+      const uint32_t w_lo = 0x10000u | ((smem_base + p.w_off) >> 4);   // descriptor low word: LBO = 1, start >> 4
+      // strips are consumed in order: `wslot/wpar` = next strip to wait for, `rslot` = next to release,
+      // `tslot` = ring slot of the top row of the current tile's window
+      uint32_t wslot = 0, wpar = 0, waited = 0, rslot = 0, released = 0, tslot = 0, seq_base = 0, t = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         int b, y0, y1, x0;
-        tc_decode_item(p, item, b, y0, y1, x0);
+        decode(item, b, y0, y1, x0);
         const int nrows = y1 - y0;
         for (int r = 0; r < nrows; ++r, ++t) {
-          const uint32_t need_hi = seq_base + r + 2 * p.halo;
+          const uint32_t need_hi = seq_base + r + 2 * halo;
           while (waited <= need_hi) {
-            mbar_wait(&full_bar[waited % S], (waited / S) & 1);
+            mbar_wait(&full_bar[wslot], wpar);
+            if (++wslot == (uint32_t)S) { wslot = 0; wpar ^= 1; }
             ++waited;
           }
           const uint32_t aslot = t & 1;
+          TC_STAMP(2, 2 * t);
           mbar_wait(&tempty_bar[aslot], ((t >> 1) & 1) ^ 1);
           tc_fence_after_sync();
-          const uint32_t d_base = tmem_base + aslot * p.acc_cols;
-          for (int ei = 0; ei < p.n_entries; ++ei) {
-            const TcEntry e = p.e[ei];
-            const uint32_t sq = seq_base + r + e.row;
-            const uint32_t a_addr =
-                ring_base + (sq % S) * p.strip_bytes + e.chunk * p.chunk_bytes + e.px_off * 128;
-            const uint32_t b_addr = w_base + e.b_off;
-            const uint32_t idesc = umma_idesc_f16((uint32_t)e.n);
-            const uint32_t bo = p.shift_mode ? (uint32_t)(e.px_off & 7) : 0u;
-            for (int ks = 0; ks < e.nsteps; ++ks) {
-              umma_f16_ss(d_base + e.dcol, umma_desc_sw128(a_addr + ks * 32, bo), umma_desc_sw128(b_addr + ks * 32),
-                          idesc, (e.first && ks == 0) ? 0u : 1u);
-            }
+          const uint32_t d_base = tmem_base + aslot * acc_cols;
+          const int ne = (dbg_flags & 1) ? 0 : n_entries;
+          for (int ei = 0; ei < ne; ++ei) {
+            const TcEntry e = ent_s[ei];
+            uint32_t sl = tslot + e.row;
+            if (sl >= (uint32_t)S) sl -= S;
+            const uint32_t a_lo = 0x10000u | ((ring_base + sl * strip_bytes + e.a_off) >> 4);
+            const uint32_t b_lo = w_lo + (e.b_off >> 4);
+            const uint32_t steps = e.steps_first & 15u;
+            const uint32_t d = d_base + e.dcol;
+            umma_f16_ss_nc(d, a_lo, b_lo, e.idesc, (e.steps_first & 0x80u) ? 0u : 1u);
+            if (steps > 1) umma_f16_ss_nc(d, a_lo + 2, b_lo + 2, e.idesc, 1u);
+            if (steps > 2) umma_f16_ss_nc(d, a_lo + 4, b_lo + 4, e.idesc, 1u);
+            if (steps > 3) umma_f16_ss_nc(d, a_lo + 6, b_lo + 6, e.idesc, 1u);
           }
           umma_commit(&tfull_bar[aslot]);
+          TC_STAMP(2, 2 * t + 1);
           const uint32_t limit = (r == nrows - 1) ? need_hi + 1 : seq_base + r + 1;
           while (released < limit) {
-            umma_commit(&empty_bar[released % S]);
+            umma_commit(&empty_bar[rslot]);
+            if (++rslot == (uint32_t)S) rslot = 0;
             ++released;
           }
+          if (++tslot == (uint32_t)S) tslot = 0;
         }
-        seq_base += nrows + 2 * p.halo;
+        // the next item starts 2*halo strips further down the ring
+        seq_base += nrows + 2 * halo;
+        tslot += 2 * halo;
+        if (tslot >= (uint32_t)S) tslot -= S;
       }
     }
     __syncwarp();
@@ -189,91 +310,113 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ================================ epilogue ====================================
     const int q = warp & 3;           // TMEM lane quadrant this warp may read
     const int m = q * 32 + lane;      // pixel of the tile == TMEM lane
-    const bool issuer = (threadIdx.x == 64);
+    const bool store_warp = (warp == 2);
+    // group parameters in registers
+    const TcOutGroup g0 = p.g[0];
+    const TcOutGroup g1 = p.g[ngroups > 1 ? 1 : 0];
+    const int ps_fp32 = p.ps_fp32;
+    void* const ps_out = p.ps_out;
+    const int ng = (dbg_flags & 2) ? 0 : ngroups;
     uint32_t t = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       int b, y0, y1, x0;
-      tc_decode_item(p, item, b, y0, y1, x0);
+      decode(item, b, y0, y1, x0);
       for (int y = y0; y < y1; ++y, ++t) {
         const int x = x0 + m;
-        const bool valid = x < p.W;
-        const long long pix = ((long long)b * p.H + y) * p.W + x;
+        const bool valid = x < W;
+        const long long pix = ((long long)b * H + y) * W + x;
         const uint32_t aslot = t & 1, sbuf = t & 1;
+        // residual rows are fetched before the accumulator is ready so their latency hides behind the MMAs
+        // (only group 0 may carry a residual)
+        uint4 res0[8];
+        if (g0.res != nullptr) {
+          const uint4* rp = reinterpret_cast<const uint4*>(g0.res + pix * g0.res_stride + g0.res_coff);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) res0[i] = (valid && i * 8 < g0.ncols) ? rp[i] : make_uint4(0, 0, 0, 0);
+        }
         // staging buffer `sbuf` was last read by the TMA store of tile t-2
-        if (issuer) tma_store_wait_read<1>();
+        if (store_warp && lane == 0) tma_store_wait_read<1>();
         named_bar_sync(1, 128);
+        if (threadIdx.x == 64) TC_STAMP(3, 3 * t);
         mbar_wait(&tfull_bar[aslot], (t >> 1) & 1);
         tc_fence_after_sync();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + aslot * p.acc_cols;
-        for (int gi = 0; gi < p.ngroups; ++gi) {
-          const TcOutGroup& g = p.g[gi];
+        if (threadIdx.x == 64) TC_STAMP(3, 3 * t + 1);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + aslot * acc_cols;
+#pragma unroll
+        for (int gi = 0; gi < 2; ++gi) {
+          if (gi >= ng) break;
+          const TcOutGroup& g = gi == 0 ? g0 : g1;
+          const uint4* resv = res0;
+          const bool has_res = gi == 0 && g.res != nullptr;
           uint8_t* stage = smem + g.stage_off + sbuf * g.stage_bytes;
           const int row_bytes = g.ncols * 2;
-          for (int c0 = 0; c0 < g.ncols; c0 += 16) {
-            uint32_t v[16];
-            tmem_ld16(taddr + g.col0 + c0, v);
-            tmem_ld_wait();
-            float f[16];
+          for (int c0 = 0; c0 < g.ncols; c0 += 32) {
+            if (g.ncols - c0 >= 32) {
+              float f[32];
+              tc_epi_chunk<32>(taddr + g.col0 + c0, &bias_s[gi][c0], g.act, g.slope, resv + (c0 >> 3), has_res, g.res_after, f);
+              if (g.mode == 0) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + bias_s[gi][c0 + j];
-            if (g.res != nullptr) {
-              float rv[16];
+                for (int hseg = 0; hseg < 4; ++hseg) {
+                  uint4 u;
+                  __half2* h = reinterpret_cast<__half2*>(&u);
 #pragma unroll
-              for (int j = 0; j < 16; ++j) rv[j] = 0.f;
-              if (valid) {
-                const __half* rp = g.res + pix * g.res_stride + g.res_coff + c0;
-                const uint4 u0 = *reinterpret_cast<const uint4*>(rp);
-                const uint4 u1 = *reinterpret_cast<const uint4*>(rp + 8);
-                const __half2* h0 = reinterpret_cast<const __half2*>(&u0);
-                const __half2* h1 = reinterpret_cast<const __half2*>(&u1);
+                  for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(f[hseg * 8 + 2 * j], f[hseg * 8 + 2 * j + 1]);
+                  const int chunk = (c0 >> 3) + hseg;
+                  const int pos = g.swizzle ? (chunk ^ (m & 7)) : chunk;
+                  *reinterpret_cast<uint4*>(stage + m * row_bytes + pos * 16) = u;
+                }
+              } else if (valid) {
+                // fused PixelShuffle(4): column 16*c + 4*i + j of pixel (y,x) -> out[b, c, 4y+i, 4x+j]
+                const int Ho = 4 * H, Wo = 4 * W;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float2 a = __half22float2(h0[j]);
-                  const float2 c = __half22float2(h1[j]);
-                  rv[2 * j] = a.x; rv[2 * j + 1] = a.y; rv[8 + 2 * j] = c.x; rv[8 + 2 * j + 1] = c.y;
+                for (int cc = 0; cc < 2; ++cc) {
+                  const int ch = (c0 >> 4) + cc;
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const long long o = (((long long)b * 3 + ch) * Ho + 4 * y + i) * Wo + 4 * x;
+                    const float* ff = f + cc * 16 + 4 * i;
+                    if (ps_fp32) {
+                      *reinterpret_cast<float4*>(reinterpret_cast<float*>(ps_out) + o) = make_float4(ff[0], ff[1], ff[2], ff[3]);
+                    } else {
+                      uint2 u;
+                      __half2* h = reinterpret_cast<__half2*>(&u);
+                      h[0] = __floats2half2_rn(ff[0], ff[1]);
+                      h[1] = __floats2half2_rn(ff[2], ff[3]);
+                      *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(ps_out) + o) = u;
+                    }
+                  }
                 }
               }
+            } else {
+              float f[16];
+              tc_epi_chunk<16>(taddr + g.col0 + c0, &bias_s[gi][c0], g.act, g.slope, resv + (c0 >> 3), has_res, g.res_after, f);
+              if (g.mode == 0) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                float z = f[j];
-                if (!g.res_after) z += rv[j];
-                z = (g.act == 1) ? (z >= 0.f ? z : z * g.slope) : z;
-                if (g.res_after) z += rv[j];
-                f[j] = z;
-              }
-            } else if (g.act == 1) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) f[j] = f[j] >= 0.f ? f[j] : f[j] * g.slope;
-            }
-            if (g.mode == 0) {
-              // two 16-byte chunks of this pixel's row in the staging tile
-#pragma unroll
-              for (int hseg = 0; hseg < 2; ++hseg) {
-                if (c0 + hseg * 8 >= g.ncols) break;
-                uint4 u;
-                __half2* h = reinterpret_cast<__half2*>(&u);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(f[hseg * 8 + 2 * j], f[hseg * 8 + 2 * j + 1]);
-                const int chunk = (c0 >> 3) + hseg;
-                const int pos = g.swizzle ? (chunk ^ (m & 7)) : chunk;
-                *reinterpret_cast<uint4*>(stage + m * row_bytes + pos * 16) = u;
-              }
-            } else if (valid) {
-              // fused PixelShuffle(4): column 16*c + 4*i + j of pixel (y,x) -> out[b, c, 4y+i, 4x+j]
-              const int ch = c0 >> 4;
-              const int Ho = 4 * p.H, Wo = 4 * p.W;
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const long long o = (((long long)b * 3 + ch) * Ho + 4 * y + i) * Wo + 4 * x;
-                if (p.ps_fp32) {
-                  *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.ps_out) + o) =
-                      make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-                } else {
-                  uint2 u;
+                for (int hseg = 0; hseg < 2; ++hseg) {
+                  uint4 u;
                   __half2* h = reinterpret_cast<__half2*>(&u);
-                  h[0] = __floats2half2_rn(f[4 * i], f[4 * i + 1]);
-                  h[1] = __floats2half2_rn(f[4 * i + 2], f[4 * i + 3]);
-                  *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.ps_out) + o) = u;
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(f[hseg * 8 + 2 * j], f[hseg * 8 + 2 * j + 1]);
+                  const int chunk = (c0 >> 3) + hseg;
+                  const int pos = g.swizzle ? (chunk ^ (m & 7)) : chunk;
+                  *reinterpret_cast<uint4*>(stage + m * row_bytes + pos * 16) = u;
+                }
+              } else if (valid) {
+                const int Ho = 4 * H, Wo = 4 * W;
+                const int ch = c0 >> 4;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const long long o = (((long long)b * 3 + ch) * Ho + 4 * y + i) * Wo + 4 * x;
+                  const float* ff = f + 4 * i;
+                  if (ps_fp32) {
+                    *reinterpret_cast<float4*>(reinterpret_cast<float*>(ps_out) + o) = make_float4(ff[0], ff[1], ff[2], ff[3]);
+                  } else {
+                    uint2 u;
+                    __half2* h = reinterpret_cast<__half2*>(&u);
+                    h[0] = __floats2half2_rn(ff[0], ff[1]);
+                    h[1] = __floats2half2_rn(ff[2], ff[3]);
+                    *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(ps_out) + o) = u;
+                  }
                 }
               }
             }
@@ -285,21 +428,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) mbar_arrive(&tempty_bar[aslot]);
         fence_proxy_async_smem();
         named_bar_sync(2, 128);
-        if (issuer) {
-          for (int gi = 0; gi < p.ngroups; ++gi) {
-            const TcOutGroup& g = p.g[gi];
-            if (g.mode != 0) continue;
-            tma_store_4d(gi == 0 ? &tmO0 : &tmO1, smem + g.stage_off + sbuf * g.stage_bytes, 0, x0, y, b);
-          }
+        if (store_warp && lane == 0) {
+          if (ng > 0 && g0.mode == 0) tma_store_4d(&tmO0, smem + g0.stage_off + sbuf * g0.stage_bytes, 0, x0, y, b);
+          if (ng > 1 && g1.mode == 0) tma_store_4d(&tmO1, smem + g1.stage_off + sbuf * g1.stage_bytes, 0, x0, y, b);
           tma_store_commit();
+          TC_STAMP(3, 3 * t + 2);
         }
       }
     }
-    if (issuer) tma_store_wait_all<0>();
+    if (store_warp && lane == 0) {
+      tma_store_wait_all<0>();
+      TC_STAMP(0, 4);
+    }
   }
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  if (threadIdx.x == 0) TC_STAMP(0, 5);
 }
 
 }  // namespace esr

@@ -80,6 +80,8 @@ struct OpDecl {
   // ESA apply
   int c1 = BUF_NONE, c1_coff = 0, c3 = BUF_NONE, f = 0, cgroups = 0, cf_ready = 0;
   int tc = -1;  // OP_CONV_TC: index into Graph::tc
+  double macs_pp = 0;  // algorithmic (unpadded) multiply-accumulates per output pixel
+  int macs_res = BK_FULL;  // spatial class the MAC count applies to
 };
 
 struct Graph {

@@ -26,6 +26,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 struct Launch {
   std::string name;
   std::function<cudaError_t(cudaStream_t)> fn;
+  double flops = 0;  // algorithmic FLOPs (2 x unpadded MACs) of this launch
 };
 
 struct Plan {
@@ -55,7 +56,8 @@ struct Engine {
   DevGraph graphs[2];  // 0: CUDA-core graph (fp32 mode, and fp16 when tc is off), 1: tcgen05 graph
   std::string err;
   // options
-  int opt_tc = 1, opt_shift_mode = 0, opt_use_graph = 1, opt_rows_per_item = 0;
+  int opt_tc = 1, opt_shift_mode = 0, opt_use_graph = 1, opt_rows_per_item = 0, opt_timeline = 0, opt_dbg_flags = 0;
+  long long* d_timeline = nullptr;  // 128 stamps per tcgen05 launch (debug option tc_timeline)
   std::list<Plan> plans;
   // host-buffer path
   void* h_in = nullptr; void* h_out = nullptr; void* h_ws = nullptr;
@@ -152,7 +154,7 @@ static WsLayout ws_layout(const Graph& g, int B, int H, int W, int dtype) {
     const size_t bytes = (size_t)B * h * w * b.C * (b.f32 ? 4 : elt);
     off += (bytes + 1023) / 1024 * 1024;
   }
-  L.total = off + 1024;
+  L.total = off + 2048;
   return L;
 }
 
@@ -175,6 +177,13 @@ static int make_tensor_map(Engine* e, CUtensorMap* m, void* base, int C_stride_e
                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(e, ESR_E_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
   return ESR_OK;
+}
+
+static double op_flops(const OpDecl& op, int B, int H, int W) {
+  int H2, W2, H3, W3;
+  esa_dims(H, W, H2, W2, H3, W3);
+  const double px = op.macs_res == BK_FULL ? (double)H * W : (op.macs_res == BK_S2 ? (double)H2 * W2 : (double)H3 * W3);
+  return 2.0 * op.macs_pp * px * B;
 }
 
 static const size_t kMaxSmem = 232448 - 1024;  // 227 KB minus the kernel's static shared memory (barriers, bias)
@@ -203,11 +212,21 @@ static int plan_tc(Engine* e, const DevGraph& dg, const TcConv& c, const std::st
   while (tm < 2 * p.acc_cols) tm *= 2;
   if (tm > 512) return fail(e, ESR_E_INVALID, name + ": accumulator does not fit TMEM");
   p.tmem_cols = tm;
-  p.shift_mode = e->opt_shift_mode;
   p.ps_fp32 = 0;
   p.ps_out = pl.out;
   for (int i = 0; i < 4; ++i) p.chunk_c0[i] = c.chunk_c0[i];
   p.wblob = dg.d_blobs + c.off_blob;
+  p.dbg = nullptr;
+  p.dbg_flags = e->opt_dbg_flags;
+  if (e->opt_timeline) {
+    if (!e->d_timeline) {
+      CUDA_TRY(e, cudaMalloc(&e->d_timeline, 256 * 128 * sizeof(long long)));
+      CUDA_TRY(e, cudaMemset(e->d_timeline, 0, 256 * 128 * sizeof(long long)));
+    }
+    int idx = 0;
+    for (auto& l : pl.launches) idx += l.name.rfind("conv_tc", 0) == 0 ? 1 : 0;
+    if (idx < 256) p.dbg = e->d_timeline + (size_t)idx * 128;
+  }
   // shared memory carve-up
   size_t off = 0;
   p.w_off = 0;
@@ -222,6 +241,7 @@ static int plan_tc(Engine* e, const DevGraph& dg, const TcConv& c, const std::st
     g.swizzle = gd.ncols == 64 ? 1 : 0;
     g.bias = dg.d_params + gd.off_bias;
     g.res = nullptr;
+    if (gd.res != BUF_NONE && gi != 0) return fail(e, ESR_E_INVALID, name + ": only the first output group may carry a residual");
     if (gd.res != BUF_NONE) {
       g.res = reinterpret_cast<const __half*>(ws + L.off[gd.res]);
       g.res_stride = dg.g.bufs[gd.res].C;
@@ -275,14 +295,12 @@ static int plan_tc(Engine* e, const DevGraph& dg, const TcConv& c, const std::st
   for (int i = 0; i < p.n_entries; ++i) {
     const TcPlaneEntry& s = c.entries[i];
     TcEntry& d = p.e[i];
-    d.row = (int16_t)(s.dy + c.halo);
-    d.px_off = (int16_t)(s.dx + c.halo);
-    d.chunk = (int16_t)s.chunk;
-    d.nsteps = (int16_t)s.nsteps;
-    d.b_off = (int32_t)s.b_off;
-    d.n = (int16_t)s.n;
-    d.dcol = (int16_t)s.dcol;
-    d.first = s.first;
+    d.a_off = (uint32_t)(s.chunk * p.chunk_bytes + (s.dx + c.halo) * 128);
+    d.b_off = (uint32_t)s.b_off;
+    d.idesc = umma_idesc_f16((uint32_t)s.n);
+    d.dcol = (uint16_t)s.dcol;
+    d.row = (uint8_t)(s.dy + c.halo);
+    d.steps_first = (uint8_t)((s.nsteps & 15) | (s.first ? 0x80 : 0));
   }
   const int grid = std::min(p.n_items, e->num_sms);
   static size_t attr_set = 0;
@@ -452,6 +470,7 @@ static int build_plan(Engine* e, Plan& pl) {
       }
       default: return fail(e, ESR_E_INVALID, "unknown op");
     }
+    pl.launches.back().flops = op_flops(op, B, H, W);
   }
   return ESR_OK;
 }
@@ -618,15 +637,16 @@ int esr_forward(esr_handle* h, const void* in_nchw, void* out_nchw, int B, int H
   const size_t need = esr_workspace_bytes(h, B, H, W, dtype);
   if (workspace_bytes < need)
     return fail(h, ESR_E_INVALID, "workspace too small: need " + std::to_string(need) + " bytes");
-  if ((reinterpret_cast<uintptr_t>(workspace) & 1023) || (reinterpret_cast<uintptr_t>(in_nchw) & 15) ||
-      (reinterpret_cast<uintptr_t>(out_nchw) & 15))
-    return fail(h, ESR_E_INVALID, "workspace must be 1024-byte aligned, input/output 16-byte aligned");
+  if ((reinterpret_cast<uintptr_t>(in_nchw) & 15) || (reinterpret_cast<uintptr_t>(out_nchw) & 15))
+    return fail(h, ESR_E_INVALID, "input / output must be 16-byte aligned");
+  // internal buffers need 1024-byte alignment (TMA, swizzle atoms); esr_workspace_bytes includes the slack
+  workspace = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   CUDA_TRY(h, cudaSetDevice(h->device));
   if (h->ws_zeroed != workspace || h->ws_zeroed_sz < need) {
     // padded channel lanes are never written by some layers and are multiplied by zero weights later:
     // they must hold finite values
-    CUDA_TRY(h, cudaMemsetAsync(workspace, 0, need, s));
+    CUDA_TRY(h, cudaMemsetAsync(workspace, 0, need - 1024, s));
     h->ws_zeroed = workspace;
     h->ws_zeroed_sz = need;
   }
@@ -703,7 +723,7 @@ static Plan* dry_plan(esr_handle* h, int B, int H, int W, int dtype, Plan& tmp) 
   tmp.launches.clear();
   for (auto& op : h->graphs[gid].g.ops) {
     static const char* kn[] = {"head", "bsrn_head", "conv_generic", "dwconv", "maxpool", "esa_apply", "conv_tc"};
-    tmp.launches.push_back(Launch{std::string(kn[op.kind]) + ":" + op.name, nullptr});
+    tmp.launches.push_back(Launch{std::string(kn[op.kind]) + ":" + op.name, nullptr, op_flops(op, B, H, W)});
   }
   return &tmp;
 }
@@ -723,6 +743,50 @@ const char* esr_launch_name(esr_handle* h, int B, int H, int W, int dtype, int i
   return name.c_str();
 }
 
+double esr_launch_flops(esr_handle* h, int B, int H, int W, int dtype, int i) {
+  Plan tmp;
+  Plan* p = dry_plan(h, B, H, W, dtype, tmp);
+  if (!p || i < 0 || i >= (int)p->launches.size()) return 0.0;
+  return p->launches[i].flops;
+}
+
+int esr_profile_launches(esr_handle* h, const void* in_nchw, void* out_nchw, int B, int H, int W, int dtype,
+                         void* workspace, size_t workspace_bytes, int reps, float* ms_out, int n, void* stream) {
+  if (!h) return ESR_E_INVALID;
+  if (!ms_out || reps < 1) return fail(h, ESR_E_INVALID, "bad argument");
+  // one ordinary forward first: validates the arguments, zeroes the workspace, builds the plan
+  const int saved = h->opt_use_graph;
+  h->opt_use_graph = 0;
+  int rc = esr_forward(h, in_nchw, out_nchw, B, H, W, dtype, workspace, workspace_bytes, stream);
+  h->opt_use_graph = saved;
+  if (rc) return rc;
+  Plan* pl = get_plan(h, in_nchw, out_nchw, B, H, W, dtype, workspace, rc);
+  if (!pl) return rc;
+  if ((int)pl->launches.size() > n) return fail(h, ESR_E_INVALID, "ms_out too small");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  cudaEvent_t e0, e1;
+  CUDA_TRY(h, cudaEventCreate(&e0));
+  CUDA_TRY(h, cudaEventCreate(&e1));
+  for (size_t i = 0; i < pl->launches.size(); ++i) {
+    // every launch is idempotent (no op writes a buffer it reads), so repeating it in place is safe
+    cudaError_t err = pl->launches[i].fn(s);  // warm
+    cudaEventRecord(e0, s);
+    for (int r = 0; r < reps && err == cudaSuccess; ++r) err = pl->launches[i].fn(s);
+    cudaEventRecord(e1, s);
+    if (err == cudaSuccess) err = cudaEventSynchronize(e1);
+    if (err != cudaSuccess) {
+      cudaEventDestroy(e0); cudaEventDestroy(e1);
+      return fail(h, ESR_E_CUDA, pl->launches[i].name + ": " + cudaGetErrorString(err));
+    }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    ms_out[i] = ms / reps;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return (int)pl->launches.size();
+}
+
 int esr_set_option(esr_handle* h, const char* key, int value) {
   if (!h || !key) return ESR_E_INVALID;
   const std::string k = key;
@@ -730,8 +794,19 @@ int esr_set_option(esr_handle* h, const char* key, int value) {
   else if (k == "tc_shift_mode") h->opt_shift_mode = value ? 1 : 0;
   else if (k == "use_graph") h->opt_use_graph = value ? 1 : 0;
   else if (k == "tc_rows_per_item") h->opt_rows_per_item = value;
+  else if (k == "tc_timeline") h->opt_timeline = value ? 1 : 0;
+  else if (k == "tc_dbg_flags") h->opt_dbg_flags = value;
   else return fail(h, ESR_E_INVALID, "unknown option: " + k);
   drop_plans(h);
+  return ESR_OK;
+}
+
+int esr_debug_timeline(esr_handle* h, long long* out, int n_launches) {
+  if (!h || !out) return ESR_E_INVALID;
+  if (!h->d_timeline) return fail(h, ESR_E_STATE, "tc_timeline option was not enabled");
+  if (n_launches > 256) n_launches = 256;
+  CUDA_TRY(h, cudaDeviceSynchronize());
+  CUDA_TRY(h, cudaMemcpy(out, h->d_timeline, (size_t)n_launches * 128 * sizeof(long long), cudaMemcpyDeviceToHost));
   return ESR_OK;
 }
 
@@ -750,6 +825,7 @@ void esr_destroy(esr_handle* h) {
     if (h->h_out) cudaFree(h->h_out);
     if (h->h_ws) cudaFree(h->h_ws);
     if (h->h_stream) cudaStreamDestroy(h->h_stream);
+    if (h->d_timeline) cudaFree(h->d_timeline);
   }
   delete h;
 }

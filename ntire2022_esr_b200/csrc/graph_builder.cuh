@@ -71,6 +71,9 @@ struct GraphBuilder {
   Graph g;
   std::vector<Table> tables;
 
+  double pend_macs = 0;  // algorithmic MACs per output pixel of the op being assembled
+  double take_macs() { const double m = pend_macs; pend_macs = 0; return m; }
+
   int buf(int kind, int C, bool f32 = false) {
     g.bufs.push_back(BufDecl{kind, C, f32});
     return (int)g.bufs.size() - 1;
@@ -125,6 +128,8 @@ struct GraphBuilder {
   }
   void table_add(int ti, const Mat& m, const PosFn& in_pos, const PosFn& out_pos) {
     Table& t = tables[ti];
+    for (int o = 0; o < m.O; ++o)
+      if (out_pos(o) >= 0) pend_macs += (double)m.I * m.k * m.k;
     const int kk = m.k * m.k;
     for (int o = 0; o < m.O; ++o) {
       const int oc = out_pos(o);
@@ -158,8 +163,10 @@ struct GraphBuilder {
       for (int tp = 0; tp < 9; ++tp) t.w[(size_t)tp * c8 + c] = w.data[(size_t)c * 9 + tp];
     }
     tables.push_back(std::move(t));
+    dw_real[(int)tables.size() - 1] = C;
     return (int)tables.size() - 1;
   }
+  std::map<int, int> dw_real;  // depthwise table -> real channel count
 
   // ---- generic ops ----------------------------------------------------------------------------
   OpDecl& conv_op(const std::string& name, int tab, int in, int in_coff, int out, int out_coff, int act,
@@ -173,6 +180,8 @@ struct GraphBuilder {
     op.ksize = tables[tab].k;
     op.stride = stride;
     op.pad = pad >= 0 ? pad : tables[tab].k / 2;
+    op.macs_pp = take_macs();
+    op.macs_res = out >= 0 ? g.bufs[out].kind : BK_FULL;
     g.ops.push_back(op);
     return g.ops.back();
   }
@@ -184,6 +193,9 @@ struct GraphBuilder {
     op.in = in; op.in_coff = in_coff; op.out = out; op.out_coff = out_coff;
     op.act = act;
     op.ksize = 3; op.pad = 1;
+    op.macs_pp = 9.0 * dw_real[tab];
+    op.macs_res = g.bufs[out].kind;
+    pend_macs = 0;
     g.ops.push_back(op);
     return g.ops.back();
   }
@@ -217,7 +229,8 @@ struct GraphBuilder {
     b.planes.push_back(std::move(p));
     return b.planes.back();
   }
-  void tc_add(TcBuild& b, const Mat& m, const PosFn& in_pos, const PosFn& out_pos) {
+  void tc_add(TcBuild& b, const Mat& m, const PosFn& in_pos, const PosFn& out_pos, double macs = -1) {
+    pend_macs += macs >= 0 ? macs : (double)m.O * m.I * m.k * m.k;
     for (int tp = 0; tp < m.k * m.k; ++tp) {
       const int dy = (m.k == 3) ? tp / 3 - 1 : 0, dx = (m.k == 3) ? tp % 3 - 1 : 0;
       TcPlane& p = tc_plane(b, dy, dx, false);
@@ -293,6 +306,7 @@ struct GraphBuilder {
     op.kind = OP_CONV_TC;
     op.name = name;
     op.tc = (int)g.tc.size() - 1;
+    op.macs_pp = take_macs();
     g.ops.push_back(op);
     return op.tc;
   }
@@ -368,7 +382,9 @@ struct GraphBuilder {
     ap.f = f; ap.cgroups = cgroups; ap.cf_ready = cf_ready;
     // wf: [16][16] (in,out); w4: [16][64] (in,out)
     ap.tab = dense_table(conv_f, 16, 16, pos_id(), pos_id());
+    if (cf_ready) pend_macs = 0;
     ap.tab2 = dense_table(conv4, 16, 64, pos_id(), pos_id());
+    ap.macs_pp = take_macs();
     (void)C;
     g.ops.push_back(ap);
   }
@@ -396,6 +412,7 @@ struct GraphBuilder {
           for (int tp = 0; tp < 9; ++tp) tables[ti].w[(size_t)(tp * 3 + ci) * 64 + o] = (float)m.at(o, ci, tp);
       }
       op.tab = ti;
+      op.macs_pp = 27.0 * nf;
       g.ops.push_back(op);
     }
     int x = fea, xc = 0;
@@ -437,8 +454,8 @@ struct GraphBuilder {
         const Mat c1c = compose(e1, m5), cfc = compose(ef, c1c);
         TcBuild b5 = tc_begin(2, 96, {{0, 64}, {64, 32}});
         tc_add(b5, m5, pos_slots(dc, 32), pos_id());
-        tc_add(b5, c1c, pos_slots(dc, 32), pos_id(64));
-        tc_add(b5, cfc, pos_slots(dc, 32), pos_id(80));
+        tc_add(b5, c1c, pos_slots(dc, 32), pos_id(64), (double)e1.O * e1.I);
+        tc_add(b5, cfc, pos_slots(dc, 32), pos_id(80), (double)ef.O * ef.I);
         tc_emit(p + "c5+esa.conv1+esa.conv_f", b5, dist, 0, 0,
                 {tc_group(0, 64, ACT_NONE, 0.f, c5o, 0), tc_group(64, 32, ACT_NONE, 0.f, esa, 0)});
         esa_tail(p + "esa.", ESR_ARCH_RFDN, eb, f, nf, c5o, 0, cat, 64 * bi, 4, 1, ef, e4);
@@ -488,6 +505,7 @@ struct GraphBuilder {
           for (int tp = 0; tp < 9; ++tp) tables[ti].w[(size_t)(tp * 3 + ci) * 64 + o] = (float)m.at(o, ci, tp);
       }
       op.tab = ti;
+      op.macs_pp = 27.0 * nf;
       g.ops.push_back(op);
     }
     int x = fea;
@@ -519,8 +537,8 @@ struct GraphBuilder {
         const Mat c1c = compose(e1, m5), cfc = compose(ef, c1c);
         TcBuild b5 = tc_begin(1, 80, {{0, 48}, {48, 32}});
         tc_add(b5, m5, pos_id(), pos_id());
-        tc_add(b5, c1c, pos_id(), pos_id(48));
-        tc_add(b5, cfc, pos_id(), pos_id(64));
+        tc_add(b5, c1c, pos_id(), pos_id(48), (double)e1.O * e1.I);
+        tc_add(b5, cfc, pos_id(), pos_id(64), (double)ef.O * ef.I);
         tc_emit(p + "c5+esa.conv1+esa.conv_f", b5, t0, 0, 0,
                 {tc_group(0, 48, ACT_NONE, 0.f, t1, 0), tc_group(48, 32, ACT_NONE, 0.f, esa, 0)});
         esa_tail(p + "esa.", ESR_ARCH_RLFN, eb, f, nf, t1, 0, xn, 0, 3, 1, ef, e4);
@@ -565,6 +583,7 @@ struct GraphBuilder {
           for (int tp = 0; tp < 9; ++tp) tables[ti].w[(size_t)(tp * 3 + ci) * 64 + o] = (float)m.at(o, ci, tp);
       }
       op.tab = ti;
+      op.macs_pp = 27.0 * nc;
       g.ops.push_back(op);
     }
     // weight out-channel o -> r column (o - dn) or -1 / d column o or -1
@@ -651,6 +670,7 @@ struct GraphBuilder {
       }
       op.tab = ti;
       op.tab2 = dw_table("fea_conv.dw", nf, 64);
+      op.macs_pp = 12.0 * nf + 9.0 * nf;
       g.ops.push_back(op);
     }
     auto lin = [&](const std::string& name, const Mat& m, int cin_pad, int cout_pad, const PosFn& ip, int in, int inc,
@@ -702,8 +722,8 @@ struct GraphBuilder {
         const Mat c1c = compose(e1, m5), cfc = compose(ef, c1c);
         TcBuild b5 = tc_begin(2, 96, {{0, 64}, {64, 32}});
         tc_add(b5, m5, pos_slots(dc, 32), pos_id());
-        tc_add(b5, c1c, pos_slots(dc, 32), pos_id(64));
-        tc_add(b5, cfc, pos_slots(dc, 32), pos_id(80));
+        tc_add(b5, c1c, pos_slots(dc, 32), pos_id(64), (double)e1.O * e1.I);
+        tc_add(b5, cfc, pos_slots(dc, 32), pos_id(80), (double)ef.O * ef.I);
         tc_emit(p + "c5+esa.conv1+esa.conv_f", b5, dist, 0, 0,
                 {tc_group(0, 64, ACT_NONE, 0.f, c5o, 0), tc_group(64, 32, ACT_NONE, 0.f, esa, 0)});
         cf_ready = 1;

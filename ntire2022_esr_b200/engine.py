@@ -83,6 +83,32 @@ class Engine:
         n = lib.esr_launch_count(self._h, B, H, W, dtype)
         return [lib.esr_launch_name(self._h, B, H, W, dtype, i).decode() for i in range(n)]
 
+    def launch_flops(self, B: int, H: int, W: int, dtype: int):
+        n = lib.esr_launch_count(self._h, B, H, W, dtype)
+        return [lib.esr_launch_flops(self._h, B, H, W, dtype, i) for i in range(n)]
+
+    def profile_launches(self, x, out, reps: int = 20):
+        """[(launch name, algorithmic FLOPs, mean ms)] for one forward of the CUDA tensor x."""
+        import torch
+
+        B, _, H, W = x.shape
+        dt = _cabi.DTYPE_F16 if x.dtype == torch.float16 else _cabi.DTYPE_F32
+        self.forward(x, out=out)  # sizes the workspace
+        names = self.launch_names(B, H, W, dt)
+        flops = self.launch_flops(B, H, W, dt)
+        ms = (ctypes.c_float * len(names))()
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        n = lib.esr_profile_launches(self._h, x.data_ptr(), out.data_ptr(), B, H, W, dt, self._ws.data_ptr(),
+                                     self._ws.numel(), reps, ms, len(names), stream)
+        if n < 0:
+            self._check(n)
+        return [(names[i], flops[i], float(ms[i])) for i in range(n)]
+
+    def debug_timeline(self, n_launches: int):
+        buf = (ctypes.c_longlong * (128 * n_launches))()
+        self._check(lib.esr_debug_timeline(self._h, buf, n_launches))
+        return np.frombuffer(buf, dtype=np.int64).reshape(n_launches, 4, 32).copy()
+
     # -- compute ----------------------------------------------------------------------------------
     def forward(self, x, out=None):
         """x: CUDA torch tensor (B,3,H,W) fp32 or fp16 on this engine's device -> (B,3,4H,4W)."""
@@ -101,6 +127,8 @@ class Engine:
         else:
             raise EsrError(_cabi.E_INVALID, f"unsupported dtype {x.dtype}")
         x = x.contiguous()
+        if x.data_ptr() % 16:
+            x = x.clone()
         B, _, H, W = x.shape
         need = self.workspace_bytes(B, H, W, dt)
         if self._ws is None or self._ws.numel() < need:

@@ -1,0 +1,68 @@
+"""Batched-image path: independent LR images sharded over the ranks of one box.
+
+Images never interact (no BatchNorm; ESA statistics are per image), so the partition is the batch axis
+and the only communication is the scatter of inputs / gather of outputs around the forward - there is
+no collective inside the kernels and results are bit-identical to the single-GPU run of the same images
+(tests/test_parity_gpu.py::test_batch_invariance...).  One process per GPU, `torch.distributed` (NCCL on
+GPUs, gloo in the CPU tests of this host logic).
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_images: int, world: int) -> List[Tuple[int, int]]:
+    """Contiguous, balanced [start, end) image ranges; the first n % world ranks get one extra image."""
+    base, extra = divmod(n_images, world)
+    out, s = [], 0
+    for r in range(world):
+        e = s + base + (1 if r < extra else 0)
+        out.append((s, e))
+        s = e
+    return out
+
+
+def forward_sharded(model: Callable[[torch.Tensor], torch.Tensor], images: Optional[torch.Tensor], n_images: int,
+                    shape_chw: Sequence[int], dtype: torch.dtype, device: torch.device, root: int = 0,
+                    gather: bool = True, group=None) -> Optional[torch.Tensor]:
+    """Rank `root` holds `images` (n_images, 3, H, W); every rank runs `model` on its shard.
+
+    Returns the (n_images, 3, 4H, 4W) result on `root` when gather=True (None elsewhere); with
+    gather=False every rank returns its own shard (true data-parallel serving: outputs stay sharded).
+    """
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    c, h, w = shape_chw
+    bounds = shard_bounds(n_images, world)
+    s, e = bounds[rank]
+    if world == 1:
+        x = images.to(device)
+    else:
+        x = torch.empty((e - s, c, h, w), dtype=dtype, device=device)
+        if rank == root:
+            reqs = []
+            for r, (rs, re_) in enumerate(bounds):
+                if r == root:
+                    x.copy_(images[rs:re_])
+                elif re_ > rs:
+                    reqs.append(dist.isend(images[rs:re_].contiguous().to(device), dst=r, group=group))
+            for q in reqs:
+                q.wait()
+        elif e > s:
+            dist.recv(x, src=root, group=group)
+    y = model(x) if e > s else torch.empty((0, c, 4 * h, 4 * w), dtype=dtype, device=device)
+    if not gather or world == 1:
+        return y
+    if rank == root:
+        out = torch.empty((n_images, c, 4 * h, 4 * w), dtype=dtype, device=device)
+        out[s:e].copy_(y)
+        for r, (rs, re_) in enumerate(bounds):
+            if r != root and re_ > rs:
+                dist.recv(out[rs:re_], src=r, group=group)
+        return out
+    if e > s:
+        dist.send(y.contiguous(), dst=root, group=group)
+    return None

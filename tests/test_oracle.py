@@ -81,3 +81,21 @@ def test_primitives_against_torch():
     np.testing.assert_array_equal(O.pixel_shuffle(xps, 4), F.pixel_shuffle(torch.from_numpy(xps), 4).numpy())
     np.testing.assert_allclose(O.gelu(xs), F.gelu(torch.from_numpy(xs)).numpy(), atol=1e-14)
     np.testing.assert_allclose(O.leaky_relu(xs, 0.05), F.leaky_relu(torch.from_numpy(xs), 0.05).numpy(), atol=0)
+
+
+@pytest.mark.parametrize("mid,arch", ARCHS)
+def test_torch_port_matches_reference_small_inputs(golden_dir, mid, arch):
+    """oracle/esr_oracle_torch.py (the CPU-baseline port timed by bench.py) against the same goldens."""
+    torch = pytest.importorskip("torch")
+    from oracle import esr_oracle_torch as OT
+
+    z = np.load(os.path.join(golden_dir, f"ref_{arch}_small.npz"))
+    dr = float(z["data_range"])
+    w = OT.prepare(_weights(golden_dir, mid))
+    for i in range(4):
+        y = OT.forward(arch, w, z[f"x{i}"]).numpy()
+        # same ATen kernels as the reference: agreement is at fp32 round-off of the thread partition
+        assert np.abs(y - z[f"y{i}"]).max() / dr < 1e-5, (arch, i)
+    yd = OT.forward(arch, OT.prepare(_weights(golden_dir, mid), torch.float64), z["x3"], torch.float64).numpy()
+    yn = O.forward(arch, _weights(golden_dir, mid), z["x3"], dtype=np.float64)
+    assert np.abs(yd - yn).max() / dr < 1e-11     # the two restatements agree in fp64

@@ -1,0 +1,208 @@
+"""Parity tests proper (B200 only): the CUDA engine, called through the C ABI, against
+ (1) golden outputs of the UNMODIFIED reference (tests/golden/*.npz),
+ (2) the numpy oracle on seeded inputs incl. odd / minimum sizes and batches,
+ (3) size-independent properties at the BASELINE.json sizes (batch invariance, determinism, graph replay,
+     host-buffer path == device path, tiled forward == oracle's tiled forward).
+Bars: fp32 mode  max|ours - ref| / data_range <= 1e-5  (north_star);
+      fp16 mode  PSNR(ours, ref_fp32) >= 60 dB and |PSNR(ours,HR) - PSNR(ref,HR)| <= 1e-3 dB on a pseudo pair.
+"""
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import esr_oracle as O  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ARCHS = [(-1, "imdn"), (0, "rfdn"), (4, "rlfn"), (18, "bsrn")]
+FP32_BAR = 1e-5
+FP16_PSNR_BAR = 60.0
+
+
+def _weights(mid):
+    return O.load_weights(os.path.join(ROOT, "tests", "golden", "weights", O.MODELS[mid]["weights"] + ".npz"))
+
+
+_models = {}
+
+
+def _model(mid):
+    from ntire2022_esr_b200 import build_model
+
+    if mid not in _models:
+        _models[mid] = build_model(mid, state_dict=_weights(mid)).eval().to("cuda:0")
+    return _models[mid]
+
+
+def _run(mid, x, half=False):
+    xt = torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    if half:
+        xt = xt.half()
+    y = _model(mid)(xt)
+    torch.cuda.synchronize()
+    return y.float().cpu().numpy()
+
+
+def _psnr(a, b, peak):
+    mse = np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2)
+    return float("inf") if mse == 0 else 10 * np.log10(peak * peak / mse)
+
+
+def test_extension_is_loaded_and_gpu_is_blackwell():
+    from ntire2022_esr_b200 import _cabi
+
+    assert os.path.exists(_cabi.LIB_PATH)
+    assert _cabi.lib.esr_device_ok(0) == 1, "needs an sm_100 GPU"
+
+
+@pytest.mark.parametrize("mid,arch", ARCHS)
+def test_fp32_matches_reference_golden_small(mid, arch):
+    z = np.load(os.path.join(ROOT, "tests", "golden", f"ref_{arch}_small.npz"))
+    dr = float(z["data_range"])
+    for i in range(4):  # 15x15 (ESA minimum), 2x24x20, 33x47, 64x64
+        y = _run(mid, z[f"x{i}"])
+        assert y.shape == z[f"y{i}"].shape
+        err = np.abs(y - z[f"y{i}"]).max() / dr
+        assert err <= FP32_BAR, (arch, i, err)
+
+
+@pytest.mark.parametrize("mid,arch", ARCHS)
+def test_fp32_matches_reference_golden_test_bmp_256(mid, arch):
+    z = np.load(os.path.join(ROOT, "tests", "golden", f"ref_{arch}_256.npz"))
+    img = np.load(os.path.join(ROOT, "tests", "golden", "test_bmp.npz"))["img"]
+    dr = float(z["data_range"])
+    y = _run(mid, O.uint2tensor4(img, dr))
+    assert y.shape == (1, 3, 1024, 1024)
+    for (a, b), crop in zip(z["crops_yx"], z["crops"]):
+        assert np.abs(y[0, :, a:a + 32, b:b + 32] - crop).max() / dr <= FP32_BAR
+    assert np.abs(y[0, :, ::16, ::16] - z["sub16"]).max() / dr <= FP32_BAR
+    np.testing.assert_allclose(y.astype(np.float64).sum(axis=(0, 2, 3)), z["sum_c"], rtol=2e-6)
+    u8 = O.tensor2uint(y, dr)[::8, ::8]
+    assert (u8 != z["uint8_sub"]).mean() < 1e-3
+
+
+@pytest.mark.parametrize("mid,arch", ARCHS)
+def test_fp16_tcgen05_path_vs_oracle(mid, arch):
+    dr = O.MODELS[mid]["data_range"]
+    rng = np.random.default_rng(5)
+    w = _weights(mid)
+    for shape in [(1, 3, 64, 64), (2, 3, 33, 47), (1, 3, 15, 15), (1, 3, 130, 260)]:
+        x = (rng.random(shape, dtype=np.float32) * dr).astype(np.float16)
+        y = _run(mid, x)
+        ref = O.forward(arch, w, x.astype(np.float32), dtype=np.float32)
+        assert np.isfinite(y).all()
+        p = _psnr(y, ref, dr)
+        assert p >= FP16_PSNR_BAR, (arch, shape, p)
+    names = _model(mid).engine(torch.device("cuda:0")).launch_names(1, 64, 64, 1)
+    assert any(n.startswith("conv_tc") for n in names)
+
+
+@pytest.mark.parametrize("mid,arch", [(0, "rfdn"), (4, "rlfn")])
+def test_fp16_psnr_delta_on_pseudo_pair(mid, arch):
+    """HR = test.bmp (256x256), LR = 4x4 box average -> 64x64; PSNR through tensor2uint like the
+    reference's run() (test_demo.py:434-447, border 4)."""
+    img = np.load(os.path.join(ROOT, "tests", "golden", "test_bmp.npz"))["img"]
+    dr = O.MODELS[mid]["data_range"]
+    lr = img.reshape(64, 4, 64, 4, 3).astype(np.float64).mean(axis=(1, 3)).round().astype(np.uint8)
+    x = O.uint2tensor4(lr, dr)
+    ref = O.forward(arch, _weights(mid), x, dtype=np.float32)
+    ours = _run(mid, x.astype(np.float16))
+    p_ref = O.psnr(O.tensor2uint(ref, dr), img, border=4)
+    p_ours = O.psnr(O.tensor2uint(ours, dr), img, border=4)
+    assert abs(p_ref - p_ours) <= 1e-3, (p_ref, p_ours)
+
+
+@pytest.mark.parametrize("mid,arch", ARCHS)
+def test_fp16_cuda_core_path_close_to_tcgen05_path(mid, arch):
+    from ntire2022_esr_b200 import build_model
+
+    dr = O.MODELS[mid]["data_range"]
+    x = (np.random.default_rng(9).random((1, 3, 48, 80), dtype=np.float32) * dr).astype(np.float16)
+    m2 = build_model(mid, state_dict=_weights(mid)).eval().to("cuda:0")
+    m2.set_engine_option("tc_enable", 0)
+    xt = torch.from_numpy(x).cuda()
+    a = m2(xt).float().cpu().numpy()
+    b = _run(mid, x)
+    assert not any(n.startswith("conv_tc") for n in m2.engine(torch.device("cuda:0")).launch_names(1, 48, 80, 1))
+    assert _psnr(a, b, dr) >= FP16_PSNR_BAR
+
+
+def test_batch_invariance_and_determinism_full_size():
+    """configs[1]/[3] sizes: every image of a batch equals its own single-image run bit for bit (this is
+    what makes batch sharding across GPUs exact), and repeated runs are bit-identical."""
+    for mid, half in [(0, True), (4, True), (0, False)]:
+        dr = O.MODELS[mid]["data_range"]
+        g = torch.Generator().manual_seed(0)
+        x = (torch.rand(3, 3, 256, 256, generator=g) * dr).cuda()
+        x = x.half() if half else x
+        m = _model(mid)
+        yb = m(x).clone()
+        for i in range(3):
+            yi = m(x[i:i + 1].contiguous())
+            assert torch.equal(yi[0], yb[i]), (mid, half, i)
+        assert torch.equal(m(x), yb)
+        assert torch.isfinite(yb).all()
+
+
+def test_cuda_graph_replay_equals_direct_launches():
+    from ntire2022_esr_b200 import build_model
+
+    x = (torch.rand(2, 3, 96, 72, generator=torch.Generator().manual_seed(1)) * 255).cuda().half()
+    outs = []
+    for graph in (0, 1):
+        m = build_model(0, state_dict=_weights(0)).eval().to("cuda:0")
+        m.set_engine_option("use_graph", graph)
+        y1 = m(x).clone()
+        y2 = m(x).clone()          # second call replays the captured graph when enabled
+        assert torch.equal(y1, y2)
+        outs.append(y1)
+    assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("half", [False, True])
+def test_host_buffer_entry_point_equals_device_path(half):
+    m = _model(0)
+    x = (np.random.default_rng(2).random((2, 3, 40, 56), dtype=np.float32) * 255.0)
+    x = x.astype(np.float16) if half else x
+    eng = m.engine(torch.device("cuda:0"))
+    yh = eng.forward_host(x)
+    yd = m(torch.from_numpy(x).cuda()).cpu().numpy()
+    assert yh.dtype == x.dtype and np.array_equal(yh, yd)
+
+
+def test_tiled_forward_matches_reference_tiled_golden():
+    from ntire2022_esr_b200 import forward
+
+    z = np.load(os.path.join(ROOT, "tests", "golden", "ref_rfdn_tiled.npz"))
+    y = forward(torch.from_numpy(z["x"]).cuda(), _model(0), tile=32, tile_overlap=8).cpu().numpy()
+    assert np.abs(y - z["y"]).max() / 255.0 <= FP32_BAR
+
+
+def test_errors_are_loud():
+    from ntire2022_esr_b200 import EsrError
+
+    m = _model(0)
+    with pytest.raises(EsrError):          # below the ESA minimum extent: the reference raises here too
+        m(torch.zeros(1, 3, 14, 20, device="cuda"))
+    with pytest.raises(EsrError):
+        m(torch.zeros(1, 3, 32, 32))        # CPU tensor
+    with pytest.raises(EsrError):
+        m(torch.zeros(1, 4, 32, 32, device="cuda"))
+    with pytest.raises(EsrError):
+        m(torch.zeros(1, 3, 32, 32, device="cuda", dtype=torch.bfloat16))
+
+
+def test_div2k_shaped_input_fp16_finite_and_close():
+    """configs[2] shape (339x510 LR): odd extents, partial 128-pixel strips, rows not a multiple of the
+    row segment; compared with the fp32 CUDA-core path of the same engine (oracle too slow at this size
+    for every CI run, and the fp32 path is itself pinned on the reference goldens above)."""
+    m = _model(0)
+    x = (torch.rand(1, 3, 339, 510, generator=torch.Generator().manual_seed(4)) * 255).cuda()
+    y32 = m(x)
+    y16 = m(x.half()).float()
+    assert torch.isfinite(y16).all()
+    mse = torch.mean((y32 - y16) ** 2).item() / 255.0 ** 2
+    assert 10 * np.log10(1.0 / mse) >= FP16_PSNR_BAR

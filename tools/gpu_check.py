@@ -29,6 +29,9 @@ def main():
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--host", type=int, default=0)
     ap.add_argument("--time", type=int, default=0)
+    ap.add_argument("--profile", type=int, default=0)
+    ap.add_argument("--timeline", type=int, default=0)
+    ap.add_argument("--dbg", type=int, default=0)
     a = ap.parse_args()
     import torch
     from ntire2022_esr_b200 import Engine
@@ -44,6 +47,8 @@ def main():
     eng.set_option("tc_shift_mode", a.shift)
     eng.set_option("use_graph", a.graph)
     eng.set_option("tc_rows_per_item", a.rows)
+    eng.set_option("tc_timeline", a.timeline)
+    eng.set_option("tc_dbg_flags", a.dbg)
     eng.load_state_dict(w)
     if a.host:
         y = eng.forward_host(x)
@@ -72,6 +77,33 @@ def main():
         torch.cuda.synchronize()
         print(f"TIME {a.arch} {a.dtype} tc={a.tc} graph={a.graph} {a.batch}x{h}x{wd}: {ev0.elapsed_time(ev1) / a.time * 1e3:.1f} us/forward",
               flush=True)
+    if not a.host:
+        extras(a, eng, xt, yt)
+
+
+def extras(a, eng, xt, yt):
+    import torch
+    if a.profile:
+        for _ in range(200):
+            eng.forward(xt, out=yt)
+        torch.cuda.synchronize()
+        for name, fl, ms in eng.profile_launches(xt, yt, reps=a.profile):
+            print(f"PROF {name:45s} {ms * 1e3:8.2f} us  {fl / 1e9:7.3f} GF  {fl / (ms * 1e-3) / 1e12 if ms > 0 else 0:7.1f} TF/s", flush=True)
+    if a.timeline:
+        names = [n for n in eng.launch_names(a.batch, a.size[0], a.size[1], 1) if n.startswith("conv_tc")]
+        eng.set_option("use_graph", 0)
+        for _ in range(3):
+            eng.forward(xt, out=yt)
+        tl = eng.debug_timeline(len(names))
+        for i, n in enumerate(names[: a.timeline]):
+            t = tl[i]
+            t0 = t[0, 0]
+            fmt = lambda v: " ".join(f"{int(x - t0):6d}" if x else "     -" for x in v)
+            print(f"TL {n}")
+            print("   cta: start,setup,prod_done,w_ready,store_done,end:", fmt(t[0, :6]))
+            print("   tma strips issued:", fmt(t[1, :12]))
+            print("   mma (begin,commit) per tile:", fmt(t[2, :10]))
+            print("   epi (wait,got,stored) per tile:", fmt(t[3, :15]), flush=True)
 
 
 if __name__ == "__main__":
