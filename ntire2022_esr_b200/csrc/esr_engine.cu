@@ -324,6 +324,13 @@ static cudaError_t launch_conv_generic(bool in_f32, bool out_f32, dim3 grid, siz
   return cudaErrorInvalidValue;
 }
 template <typename TAcc>
+static cudaError_t launch_conv16(bool in_f32, bool out_f32, dim3 grid, cudaStream_t s, const ConvGenericParams& p) {
+  if (in_f32 && out_f32) return launch1(k_conv16<float, float, TAcc>, grid, dim3(128), 0, s, p);
+  if (!in_f32 && !out_f32) return launch1(k_conv16<__half, __half, TAcc>, grid, dim3(128), 0, s, p);
+  if (!in_f32 && out_f32) return launch1(k_conv16<__half, float, TAcc>, grid, dim3(128), 0, s, p);
+  return cudaErrorInvalidValue;
+}
+template <typename TAcc>
 static cudaError_t launch_dw(bool in_f32, bool out_f32, dim3 grid, cudaStream_t s, const DwParams& p) {
   if (in_f32 && out_f32) return launch1(k_dwconv3x3<float, float, TAcc>, grid, dim3(128), 0, s, p);
   if (!in_f32 && !out_f32) return launch1(k_dwconv3x3<__half, __half, TAcc>, grid, dim3(128), 0, s, p);
@@ -404,6 +411,13 @@ static int build_plan(Engine* e, Plan& pl) {
         if (smem > 48 * 1024) return fail(e, ESR_E_INVALID, op.name + ": generic conv weight tile too large");
         const bool in32 = is_f32(op.in), out32 = op.ps ? in32 : is_f32(op.out);
         const bool dbl = !f16;
+        if (t.cin8 == 16 && t.cout16 == 16 && !op.ps) {  // ESA branch: small-conv kernel
+          const dim3 grid16((unsigned)((npix * 4 + 127) / 128));
+          pl.launches.push_back(Launch{"conv16:" + op.name, [=](cudaStream_t s) {
+            return dbl ? launch_conv16<double>(in32, out32, grid16, s, p) : launch_conv16<float>(in32, out32, grid16, s, p);
+          }});
+          break;
+        }
         pl.launches.push_back(Launch{"conv_generic:" + op.name, [=](cudaStream_t s) {
           return dbl ? launch_conv_generic<double>(in32, out32, grid, smem, s, p)
                      : launch_conv_generic<float>(in32, out32, grid, smem, s, p);
@@ -723,7 +737,10 @@ static Plan* dry_plan(esr_handle* h, int B, int H, int W, int dtype, Plan& tmp) 
   tmp.launches.clear();
   for (auto& op : h->graphs[gid].g.ops) {
     static const char* kn[] = {"head", "bsrn_head", "conv_generic", "dwconv", "maxpool", "esa_apply", "conv_tc"};
-    tmp.launches.push_back(Launch{std::string(kn[op.kind]) + ":" + op.name, nullptr, op_flops(op, B, H, W)});
+    std::string kname = kn[op.kind];
+    if (op.kind == OP_CONV && !op.ps && h->graphs[gid].tables[op.tab].cin8 == 16 && h->graphs[gid].tables[op.tab].cout16 == 16)
+      kname = "conv16";
+    tmp.launches.push_back(Launch{kname + ":" + op.name, nullptr, op_flops(op, B, H, W)});
   }
   return &tmp;
 }

@@ -58,6 +58,8 @@ __device__ __forceinline__ void store8(__half* p, const float (&v)[8]) {
 }
 __device__ __forceinline__ float ldf(const float* p) { return *p; }
 __device__ __forceinline__ float ldf(const __half* p) { return __half2float(*p); }
+__device__ __forceinline__ void stf(float* p, float v) { *p = v; }
+__device__ __forceinline__ void stf(__half* p, float v) { *p = __float2half_rn(v); }
 
 // ---------------------------------------------------------------------------------------------
 // Head: 3x3 conv (pad 1) on the NCHW 3-channel input, NHWC output with `cstore` channels
@@ -68,7 +70,7 @@ template <typename TIn, typename TOut, typename TAcc>
 __global__ void __launch_bounds__(128) k_head_conv(const TIn* __restrict__ in, TOut* __restrict__ out,
                                                    const float* __restrict__ w, const float* __restrict__ bias,
                                                    int B, int H, int W, int out_stride, int cstore) {
-  __shared__ float ws[27 * 64];
+  __shared__ __align__(16) float ws[27 * 64];
   __shared__ float bs[64];
   for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) ws[i] = w[i];
   if (threadIdx.x < 64) bs[threadIdx.x] = bias[threadIdx.x];
@@ -98,8 +100,12 @@ __global__ void __launch_bounds__(128) k_head_conv(const TIn* __restrict__ in, T
 #pragma unroll
     for (int t = 0; t < 27; ++t) {
       const TAcc xv = (TAcc)xin[t];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = fma(xv, (TAcc)ws[t * 64 + c0 + j], acc[j]);
+      const float4 wa = *reinterpret_cast<const float4*>(ws + t * 64 + c0);
+      const float4 wb = *reinterpret_cast<const float4*>(ws + t * 64 + c0 + 4);
+      acc[0] = fma(xv, (TAcc)wa.x, acc[0]); acc[1] = fma(xv, (TAcc)wa.y, acc[1]);
+      acc[2] = fma(xv, (TAcc)wa.z, acc[2]); acc[3] = fma(xv, (TAcc)wa.w, acc[3]);
+      acc[4] = fma(xv, (TAcc)wb.x, acc[4]); acc[5] = fma(xv, (TAcc)wb.y, acc[5]);
+      acc[6] = fma(xv, (TAcc)wb.z, acc[6]); acc[7] = fma(xv, (TAcc)wb.w, acc[7]);
     }
     float f[8];
 #pragma unroll
@@ -284,6 +290,71 @@ __global__ void __launch_bounds__(128) k_conv_generic(const ConvGenericParams p)
 }
 
 // ---------------------------------------------------------------------------------------------
+// Small dense conv for the ESA branch: <= 16 input and output channels (tables with cin8 = cout16 = 16),
+// k = 1 or 3, stride 1 or 2.  thread = one output pixel x 4 output channels (4 consecutive threads
+// share a pixel), weights read as broadcast LDS.128.  Same parameter block as k_conv_generic.
+// ---------------------------------------------------------------------------------------------
+template <typename TIn, typename TOut, typename TAcc>
+__global__ void __launch_bounds__(128) k_conv16(const ConvGenericParams p) {
+  __shared__ __align__(16) float wsm[9 * 16 * 16];
+  const int taps = p.ksize * p.ksize;
+  for (int i = threadIdx.x; i < taps * 256; i += blockDim.x) wsm[i] = p.w[i];
+  __syncthreads();
+  const long long total = (long long)p.B * p.Hout * p.Wout * 4;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int g4 = (int)(idx & 3);
+  const long long pix = idx >> 2;
+  const int x = (int)(pix % p.Wout);
+  const int y = (int)((pix / p.Wout) % p.Hout);
+  const int b = (int)(pix / ((long long)p.Wout * p.Hout));
+  TAcc acc[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) acc[j] = (TAcc)p.bias[g4 * 4 + j];
+  const TIn* in = reinterpret_cast<const TIn*>(p.in);
+#pragma unroll 1
+  for (int ky = 0; ky < p.ksize; ++ky) {
+    const int yy = y * p.stride + ky - p.pad;
+    if (yy < 0 || yy >= p.Hin) continue;
+#pragma unroll 1
+    for (int kx = 0; kx < p.ksize; ++kx) {
+      const int xx = x * p.stride + kx - p.pad;
+      if (xx < 0 || xx >= p.Win) continue;
+      const TIn* ip = in + (((long long)b * p.Hin + yy) * p.Win + xx) * p.in_stride + p.in_coff;
+      float xv[16];
+      {
+        float a[8], c[8];
+        load8(ip, a);
+        load8(ip + 8, c);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { xv[j] = a[j]; xv[8 + j] = c[j]; }
+      }
+      const float* wt = wsm + (ky * p.ksize + kx) * 256 + g4 * 4;
+#pragma unroll
+      for (int ci = 0; ci < 16; ++ci) {
+        const float4 ww = *reinterpret_cast<const float4*>(wt + ci * 16);
+        const TAcc xa = (TAcc)xv[ci];
+        acc[0] = fma(xa, (TAcc)ww.x, acc[0]);
+        acc[1] = fma(xa, (TAcc)ww.y, acc[1]);
+        acc[2] = fma(xa, (TAcc)ww.z, acc[2]);
+        acc[3] = fma(xa, (TAcc)ww.w, acc[3]);
+      }
+    }
+  }
+  TOut* o = reinterpret_cast<TOut*>(p.out) + pix * p.out_stride + p.out_coff + g4 * 4;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    TAcc v = acc[j];
+    if (p.res != nullptr && !p.res_after)
+      v += (TAcc)ldf(reinterpret_cast<const TOut*>(p.res) + pix * p.res_stride + p.res_coff + g4 * 4 + j);
+    v = apply_act(v, p.act, p.slope);
+    if (p.res != nullptr && p.res_after)
+      v += (TAcc)ldf(reinterpret_cast<const TOut*>(p.res) + pix * p.res_stride + p.res_coff + g4 * 4 + j);
+    stf(o + j, (float)v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Depthwise 3x3 (pad 1) + bias (+ residual) + activation; thread = pixel x 8 channels.
 // w: [9][c8] fp32, bias [c8]
 // ---------------------------------------------------------------------------------------------
@@ -350,7 +421,9 @@ __global__ void __launch_bounds__(128) k_maxpool7s3(const float* __restrict__ in
   const int y = (int)((pix / Wout) % Hout);
   const int b = (int)(pix / ((long long)Wout * Hout));
   float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
   for (int i = 0; i < 7; ++i)
+#pragma unroll
     for (int j = 0; j < 7; ++j) {
       const float4 v = *reinterpret_cast<const float4*>(
           in + (((long long)b * Hin + 3 * y + i) * Win + 3 * x + j) * 16 + q * 4);
@@ -378,7 +451,7 @@ struct EsaApplyParams {
 };
 template <typename T, typename TAcc>
 __global__ void __launch_bounds__(128) k_esa_apply(const EsaApplyParams p) {
-  __shared__ float s_wf[16 * 16], s_bf[16], s_w4[16 * 64], s_b4[64];
+  __shared__ __align__(16) float s_wf[16 * 16], s_bf[16], s_w4[16 * 64], s_b4[64];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) s_wf[i] = p.wf[i];
   for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_w4[i] = p.w4[i];
   if (threadIdx.x < 16) s_bf[threadIdx.x] = p.bf[threadIdx.x];
@@ -399,10 +472,10 @@ __global__ void __launch_bounds__(128) k_esa_apply(const EsaApplyParams p) {
   const int y1 = min(y0 + 1, p.H3 - 1), x1 = min(x0 + 1, p.W3 - 1);
   const float ly = sy - (float)y0, lx = sx - (float)x0;
   const float* c3b = p.c3 + (long long)b * p.H3 * p.W3 * 16;
-  const float* p00 = c3b + ((long long)y0 * p.W3 + x0) * 16;
-  const float* p01 = c3b + ((long long)y0 * p.W3 + x1) * 16;
-  const float* p10 = c3b + ((long long)y1 * p.W3 + x0) * 16;
-  const float* p11 = c3b + ((long long)y1 * p.W3 + x1) * 16;
+  const float4* p00 = reinterpret_cast<const float4*>(c3b + ((long long)y0 * p.W3 + x0) * 16);
+  const float4* p01 = reinterpret_cast<const float4*>(c3b + ((long long)y0 * p.W3 + x1) * 16);
+  const float4* p10 = reinterpret_cast<const float4*>(c3b + ((long long)y1 * p.W3 + x0) * 16);
+  const float4* p11 = reinterpret_cast<const float4*>(c3b + ((long long)y1 * p.W3 + x1) * 16);
   float c1v[16];
   {
     const T* cp = reinterpret_cast<const T*>(p.c1) + pix * p.c1_stride + p.c1_coff;
@@ -414,19 +487,27 @@ __global__ void __launch_bounds__(128) k_esa_apply(const EsaApplyParams p) {
   }
   TAcc s[16];
 #pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    const TAcc top = (TAcc)p00[k] * (TAcc)(1.f - lx) + (TAcc)p01[k] * (TAcc)lx;
-    const TAcc bot = (TAcc)p10[k] * (TAcc)(1.f - lx) + (TAcc)p11[k] * (TAcc)lx;
-    const TAcc v = top * (TAcc)(1.f - ly) + bot * (TAcc)ly;
-    TAcc cf;
-    if (p.cf_ready) {
-      cf = (TAcc)c1v[k];
-    } else {
-      cf = (TAcc)s_bf[k];
+  for (int q = 0; q < 4; ++q) {
+    const float4 a00 = p00[q], a01 = p01[q], a10 = p10[q], a11 = p11[q];
+    const float v00[4] = {a00.x, a00.y, a00.z, a00.w}, v01[4] = {a01.x, a01.y, a01.z, a01.w};
+    const float v10[4] = {a10.x, a10.y, a10.z, a10.w}, v11[4] = {a11.x, a11.y, a11.z, a11.w};
 #pragma unroll
-      for (int i = 0; i < 16; ++i) cf = fma((TAcc)c1v[i], (TAcc)s_wf[i * 16 + k], cf);
+    for (int j = 0; j < 4; ++j) {
+      const int k = q * 4 + j;
+      // same association as ATen: blend along x first, then along y
+      const TAcc top = (TAcc)v00[j] * (TAcc)(1.f - lx) + (TAcc)v01[j] * (TAcc)lx;
+      const TAcc bot = (TAcc)v10[j] * (TAcc)(1.f - lx) + (TAcc)v11[j] * (TAcc)lx;
+      const TAcc v = top * (TAcc)(1.f - ly) + bot * (TAcc)ly;
+      TAcc cf;
+      if (p.cf_ready) {
+        cf = (TAcc)c1v[k];
+      } else {
+        cf = (TAcc)s_bf[k];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) cf = fma((TAcc)c1v[i], (TAcc)s_wf[i * 16 + k], cf);
+      }
+      s[k] = (k < p.f) ? (v + cf) : (TAcc)0;
     }
-    s[k] = (k < p.f) ? (v + cf) : (TAcc)0;
   }
   float xv[16];
   {
@@ -437,14 +518,24 @@ __global__ void __launch_bounds__(128) k_esa_apply(const EsaApplyParams p) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) { xv[j] = a[j]; xv[8 + j] = c[j]; }
   }
+  TAcc z[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) z[j] = (TAcc)s_b4[g * 16 + j];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const float4* w4 = reinterpret_cast<const float4*>(s_w4 + k * 64 + g * 16);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 ww = w4[q];
+      z[4 * q + 0] = fma(s[k], (TAcc)ww.x, z[4 * q + 0]);
+      z[4 * q + 1] = fma(s[k], (TAcc)ww.y, z[4 * q + 1]);
+      z[4 * q + 2] = fma(s[k], (TAcc)ww.z, z[4 * q + 2]);
+      z[4 * q + 3] = fma(s[k], (TAcc)ww.w, z[4 * q + 3]);
+    }
+  }
   float o[16];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    TAcc z = (TAcc)s_b4[g * 16 + j];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) z = fma(s[k], (TAcc)s_w4[k * 64 + g * 16 + j], z);
-    o[j] = (float)((TAcc)xv[j] * sigmoid_acc(z));
-  }
+  for (int j = 0; j < 16; ++j) o[j] = (float)((TAcc)xv[j] * sigmoid_acc(z[j]));
   T* op = reinterpret_cast<T*>(p.out) + pix * p.out_stride + p.out_coff + g * 16;
   float a[8], c[8];
 #pragma unroll
