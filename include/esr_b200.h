@@ -83,7 +83,8 @@ int esr_profile_launches(esr_handle* h, const void* in_nchw, void* out_nchw, int
                          void* workspace, size_t workspace_bytes, int reps, float* ms_out, int n, void* stream);
 
 /* Runtime knobs (tuning / A-B measurements): "tc_enable" (fp16: tcgen05 convolutions on/off),
- * "tc_shift_mode", "use_graph", "tc_rows_per_item", "tc_timeline". */
+ * "use_graph", "use_pdl" (programmatic dependent launch between the kernels of a forward),
+ * "tc_rows_per_item", "tc_acc_slots", "tc_timeline", "tc_dbg_flags". */
 int esr_set_option(esr_handle* h, const char* key, int value);
 
 /* Debug aid: with option "tc_timeline" = 1 every tcgen05 launch records clock64 stamps of block 0

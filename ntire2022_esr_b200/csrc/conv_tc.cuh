@@ -19,6 +19,8 @@
 // Measured on B200 (tools/micro/mma_bench.cu): an M=128, K=16 SS-mode MMA costs 32 + N/4 cycles for
 // N <= 128 (A and B are both fetched from shared memory at 128 B/clk), i.e. 48 cycles at N = 64.
 #pragma once
+#include <type_traits>
+
 #include "kernels_generic.cuh"
 #include "tc_common.cuh"
 
@@ -27,7 +29,12 @@ namespace esr {
 constexpr int TC_MAX_ENTRIES = 16;
 constexpr int TC_TILE_PX = 128;
 constexpr int TC_MAX_SLOTS = 8;
-constexpr int TC_THREADS = 192;
+constexpr int TC_MAX_GROUPS = 3;
+constexpr int TC_MAX_CHUNKS = 10;
+constexpr int TC_MAX_UNITS = 5;
+constexpr int TC_PREFETCH_ROWS = 6;  // L2 prefetch distance of the producer, in image rows     // 16-column units per epilogue warp set = ceil(TC_MAX_CHUNKS / 2)
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 
 struct __align__(16) TcEntry {
   uint32_t a_off;   // chunk * chunk_bytes + px_off * 128 (bytes inside a ring slot)
@@ -50,9 +57,14 @@ struct TcOutGroup {
   int32_t swizzle;     // staging layout of the store tensor map (1 = SWIZZLE_128B, 0 = linear)
   int32_t stage_off;   // smem offset of the two staging buffers
   int32_t stage_bytes; // bytes of one staging buffer
-  int32_t bias_off;    // float offset of this group's bias inside the kernel's bias table
   const float* bias;   // [ncols]
   const __half* res;   // nullptr = none
+};
+
+// one unit of epilogue work: 16 accumulator columns of one output group
+struct __align__(8) TcChunk {
+  uint16_t tcol;    // accumulator column
+  uint8_t group, c0, width, pad_[3];
 };
 
 struct TcParams {
@@ -65,9 +77,10 @@ struct TcParams {
   int32_t nslots;        // strip ring depth
   int32_t rows_per_item;
   int32_t strips_x, segs_y, n_items;
-  int32_t n_entries, ngroups;
+  int32_t n_entries, ngroups, n_epi_chunks;
   int32_t tmem_cols;     // TMEM allocation (power of two >= 2*acc_cols)
   int32_t acc_cols;      // columns of one accumulator slot
+  int32_t acc_slots;     // accumulator slots in TMEM (2 or 4): how far the MMA warp may run ahead of the epilogue
   int32_t w_off, w_bytes, ring_off;
   int32_t ps_fp32;
   int32_t dbg_flags;     // experiments: 1 = issue no MMA, 2 = epilogue does no work
@@ -76,7 +89,8 @@ struct TcParams {
   void* ps_out;
   long long* dbg;        // optional timeline buffer (block 0 only): [role][event] clock64 stamps
   TcEntry e[TC_MAX_ENTRIES];
-  TcOutGroup g[2];
+  TcOutGroup g[TC_MAX_GROUPS];
+  TcChunk ck[TC_MAX_CHUNKS];
 };
 
 #define TC_STAMP(role, idx)                                                                        \
@@ -114,66 +128,101 @@ __device__ __forceinline__ void umma_f16_ss_nc(uint32_t tmem_d, uint32_t adesc_l
       ::"r"(tmem_d), "r"(adesc_lo), "r"(bdesc_lo), "r"(idesc), "r"(accumulate), "r"(0x40004040u));
 }
 
-// One output group of one tile: 16 or 32 accumulator columns at a time.
-template <int NC>
-__device__ __forceinline__ void tc_epi_chunk(uint32_t taddr, const float* __restrict__ bias_s, int act, float slope,
-                                             const uint4* res_v, bool has_res, int res_after, float (&f)[NC]) {
-  uint32_t v[NC];
-  if constexpr (NC == 32) {
-    tmem_ld32(taddr, *reinterpret_cast<uint32_t(*)[32]>(v));
-  } else {
-    tmem_ld16_nc(taddr, v);
-  }
-  tmem_ld_wait();
+// out of line on purpose: erff is ~40 instructions and would be replicated 16x in the epilogue otherwise
+__device__ __noinline__ float tc_gelu(float v) { return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f)); }
+
+// bias + residual + activation on 16 accumulator columns of one pixel.  NONE / RELU / LRELU are all
+// max(v, v * slope) with slope 1 / 0 / s (set by the host), so the common path has no activation branch.
+__device__ __forceinline__ void tc_epi_math16(const uint32_t (&v)[16], const float* __restrict__ bias_s, bool gelu, float slope,
+                                              bool has_res, const uint4& u0, const uint4& u1, int res_after, float (&f)[16]) {
 #pragma unroll
-  for (int j = 0; j < NC; j += 4) {
+  for (int j = 0; j < 16; j += 4) {
     const float4 b4 = *reinterpret_cast<const float4*>(bias_s + j);
     f[j] = __uint_as_float(v[j]) + b4.x;
     f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
     f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
     f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
   }
-  float rv[NC];
+  if (!has_res && !gelu) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], f[j] * slope);
+    return;
+  }
+  float rv[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) rv[j] = 0.f;
   if (has_res) {
+    const __half2* h0 = reinterpret_cast<const __half2*>(&u0);
+    const __half2* h1 = reinterpret_cast<const __half2*>(&u1);
 #pragma unroll
-    for (int q = 0; q < NC / 8; ++q) {
-      const __half2* h = reinterpret_cast<const __half2*>(&res_v[q]);
+    for (int j = 0; j < 4; ++j) {
+      const float2 a = __half22float2(h0[j]), c = __half22float2(h1[j]);
+      rv[2 * j] = a.x; rv[2 * j + 1] = a.y; rv[8 + 2 * j] = c.x; rv[8 + 2 * j + 1] = c.y;
+    }
+  }
+  if (!res_after) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 a = __half22float2(h[j]);
-        rv[q * 8 + 2 * j] = a.x;
-        rv[q * 8 + 2 * j + 1] = a.y;
+    for (int j = 0; j < 16; ++j) f[j] += rv[j];
+  }
+  if (gelu) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] = tc_gelu(f[j]);   // (a dynamically indexed loop would push f[] to local memory)
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], f[j] * slope);
+  }
+  if (res_after) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] += rv[j];
+  }
+}
+
+// fp16 pack + store of 16 columns: swizzled staging row (mode 0) or fused PixelShuffle(4) (mode 1)
+__device__ __forceinline__ void tc_epi_store16(const float (&f)[16], int mode, uint8_t* stage_row, int c0, int swz_row,
+                                               bool valid, void* ps_out, int ps_fp32, int b, int y, int x, int H, int W) {
+  if (mode == 0) {
+#pragma unroll
+    for (int hseg = 0; hseg < 2; ++hseg) {
+      uint4 u;
+      __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(f[hseg * 8 + 2 * j], f[hseg * 8 + 2 * j + 1]);
+      const int chunk = (c0 >> 3) + hseg;
+      *reinterpret_cast<uint4*>(stage_row + ((chunk ^ swz_row) << 4)) = u;
+    }
+  } else if (valid) {
+    // column 16*c + 4*i + j of pixel (y,x) -> out[b, c, 4y+i, 4x+j]
+    const int Ho = 4 * H, Wo = 4 * W;
+    const int ch = c0 >> 4;
+    const long long o0 = (((long long)b * 3 + ch) * Ho + 4 * y) * Wo + 4 * x;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const long long o = o0 + (long long)i * Wo;
+      const float* ff = f + 4 * i;
+      if (ps_fp32) {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(ps_out) + o) = make_float4(ff[0], ff[1], ff[2], ff[3]);
+      } else {
+        uint2 u;
+        __half2* h = reinterpret_cast<__half2*>(&u);
+        h[0] = __floats2half2_rn(ff[0], ff[1]);
+        h[1] = __floats2half2_rn(ff[2], ff[3]);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(ps_out) + o) = u;
       }
     }
-    if (!res_after) {
-#pragma unroll
-      for (int j = 0; j < NC; ++j) f[j] += rv[j];
-    }
-  }
-  if (act == ACT_LRELU) {
-#pragma unroll
-    for (int j = 0; j < NC; ++j) f[j] = fmaxf(f[j], f[j] * slope);   // slope < 1
-  } else if (act == ACT_GELU) {
-#pragma unroll
-    for (int j = 0; j < NC; ++j) f[j] = 0.5f * f[j] * (1.f + erff(f[j] * 0.70710678118654752440f));
-  } else if (act == ACT_RELU) {
-#pragma unroll
-    for (int j = 0; j < NC; ++j) f[j] = fmaxf(f[j], 0.f);
-  }
-  if (has_res && res_after) {
-#pragma unroll
-    for (int j = 0; j < NC; ++j) f[j] += rv[j];
   }
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmO0,
-               const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ TcParams p) {
+               const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ CUtensorMap tmO2,
+               const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t full_bar[TC_MAX_SLOTS], empty_bar[TC_MAX_SLOTS], tfull_bar[2], tempty_bar[2], w_bar;
+  __shared__ uint64_t full_bar[TC_MAX_SLOTS], empty_bar[TC_MAX_SLOTS], tfull_bar[4], tempty_bar[4], w_bar;
   __shared__ uint32_t tmem_base_s;
-  __shared__ __align__(16) float bias_s[2][64];
+  __shared__ __align__(16) float bias_s[TC_MAX_GROUPS][64];
   __shared__ __align__(16) TcEntry ent_s[TC_MAX_ENTRIES];
+  __shared__ TcOutGroup grp_s[TC_MAX_GROUPS];
+  __shared__ TcChunk ck_s[TC_MAX_CHUNKS];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   long long* const dbg = p.dbg;
@@ -184,33 +233,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* const smem = smem_raw + pad;
   const uint32_t smem_base = raw_u32 + pad;
 
-  // hoist every parameter the role loops touch into registers once (the param bank is re-read after
-  // each asm volatile with a memory clobber otherwise)
+  // every parameter the role loops touch lives in a register from here on (the param bank would be
+  // re-read after each asm volatile with a memory clobber otherwise)
   const int S = p.nslots, halo = p.halo, nchunks = p.nchunks, strip_bytes = p.strip_bytes, chunk_bytes = p.chunk_bytes;
   const int n_items = p.n_items, strips_x = p.strips_x, segs_y = p.segs_y, rows_per_item = p.rows_per_item;
   const int H = p.H, W = p.W, ring_off = p.ring_off, acc_cols = p.acc_cols, n_entries = p.n_entries, ngroups = p.ngroups;
   const int dbg_flags = p.dbg_flags;
-
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmO0);
-    tma_prefetch_desc(&tmO1);
-    for (int i = 0; i < S; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
-    mbar_init(&w_bar, 1);
-    fence_mbar_init();
-  }
-  if (warp == 1) tmem_alloc(&tmem_base_s, (uint32_t)p.tmem_cols);
-  for (int i = threadIdx.x; i < 128; i += blockDim.x) {
-    const int g = i >> 6, c = i & 63;
-    bias_s[g][c] = (g < ngroups && c < p.g[g].ncols) ? p.g[g].bias[c] : 0.f;
-  }
-  if (threadIdx.x < TC_MAX_ENTRIES) ent_s[threadIdx.x] = p.e[threadIdx.x];
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem_base = tmem_base_s;
-  if (threadIdx.x == 0) TC_STAMP(0, 1);
+  const uint32_t NS = (uint32_t)p.acc_slots, ns_shift = NS == 4 ? 2u : 1u;
 
   auto decode = [&](int item, int& b, int& y0, int& y1, int& x0) {
     const int per_img = strips_x * segs_y;
@@ -223,29 +252,84 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     x0 = sx * TC_TILE_PX;
   };
 
+  // ---- producer state (warp 0, elected lane): strips are issued in two phases so that the first ring
+  // fill overlaps the rest of the CTA set-up (TMEM allocation, bias / entry tables)
+  const uint32_t strip_tx = (uint32_t)(nchunks * p.strip_px * 128);
+  const int cc0 = p.chunk_c0[0], cc1 = p.chunk_c0[1], cc2 = p.chunk_c0[2], cc3 = p.chunk_c0[3];
+  uint32_t pr_slot = 0, pr_par = 0, pr_seq = 0;
+  int pr_item = blockIdx.x, pr_row = 0, pr_b = 0, pr_y1 = 0, pr_x0 = 0;
+  bool pr_open = false;
+  auto produce = [&](uint32_t limit) {   // issue strips until `limit` have been issued in total
+    while (pr_seq < limit) {
+      if (!pr_open) {
+        if (pr_item >= n_items) return;
+        int y0;
+        decode(pr_item, pr_b, y0, pr_y1, pr_x0);
+        pr_row = y0 - halo;
+        pr_open = true;
+      }
+      mbar_wait(&empty_bar[pr_slot], pr_par ^ 1);
+      mbar_arrive_expect_tx(&full_bar[pr_slot], strip_tx);
+      uint8_t* dst = smem + ring_off + pr_slot * strip_bytes;
+      tma_load_4d(&tmA, &full_bar[pr_slot], dst, cc0, pr_x0 - halo, pr_row, pr_b);
+      if (nchunks > 1) tma_load_4d(&tmA, &full_bar[pr_slot], dst + chunk_bytes, cc1, pr_x0 - halo, pr_row, pr_b);
+      if (nchunks > 2) tma_load_4d(&tmA, &full_bar[pr_slot], dst + 2 * chunk_bytes, cc2, pr_x0 - halo, pr_row, pr_b);
+      if (nchunks > 3) tma_load_4d(&tmA, &full_bar[pr_slot], dst + 3 * chunk_bytes, cc3, pr_x0 - halo, pr_row, pr_b);
+      if (pr_row + TC_PREFETCH_ROWS < pr_y1 + halo) {   // warm L2 for the strip the ring cannot hold yet
+        tma_prefetch_4d(&tmA, cc0, pr_x0 - halo, pr_row + TC_PREFETCH_ROWS, pr_b);
+        if (nchunks > 1) tma_prefetch_4d(&tmA, cc1, pr_x0 - halo, pr_row + TC_PREFETCH_ROWS, pr_b);
+        if (nchunks > 2) tma_prefetch_4d(&tmA, cc2, pr_x0 - halo, pr_row + TC_PREFETCH_ROWS, pr_b);
+        if (nchunks > 3) tma_prefetch_4d(&tmA, cc3, pr_x0 - halo, pr_row + TC_PREFETCH_ROWS, pr_b);
+      }
+      TC_STAMP(1, pr_seq);
+      ++pr_seq;
+      if (++pr_slot == (uint32_t)S) { pr_slot = 0; pr_par ^= 1; }
+      if (++pr_row >= pr_y1 + halo) { pr_open = false; pr_item += gridDim.x; }
+    }
+  };
+
+  if (warp == 0) {
+    if (elect_one()) {
+      tma_prefetch_desc(&tmA);
+      for (int i = 0; i < S; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+      for (int i = 0; i < 4; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], TC_EPI_WARPS); }
+      mbar_init(&w_bar, 1);
+      fence_mbar_init();
+      // weights never depend on the previous kernel: fetch them before the grid dependency is resolved
+      mbar_arrive_expect_tx(&w_bar, (uint32_t)p.w_bytes);
+      bulk_load_1d(smem + p.w_off, p.wblob, (uint32_t)p.w_bytes, &w_bar);
+      griddep_wait();
+      produce((uint32_t)S);
+      tma_prefetch_desc(&tmO0);
+      tma_prefetch_desc(&tmO1);
+      tma_prefetch_desc(&tmO2);
+    }
+    __syncwarp();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_s, (uint32_t)p.tmem_cols);
+  if (warp >= 2) {
+    const int tid = threadIdx.x - 64;
+    for (int i = tid; i < TC_MAX_GROUPS * 64; i += 32 * TC_EPI_WARPS) {
+      const int g = i >> 6, c = i & 63;
+      bias_s[g][c] = (g < ngroups && c < p.g[g].ncols) ? p.g[g].bias[c] : 0.f;
+    }
+    if (tid < TC_MAX_ENTRIES) ent_s[tid] = p.e[tid];
+    if (tid >= 32 && tid < 32 + TC_MAX_GROUPS) grp_s[tid - 32] = p.g[tid - 32];
+    if (tid >= 64 && tid < 64 + TC_MAX_CHUNKS) ck_s[tid - 64] = p.ck[tid - 64];
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_base_s;
+  if (threadIdx.x == 0) {
+    TC_STAMP(0, 1);
+    griddep_launch_dependents();   // this grid is fully resident (<= 1 CTA per SM): let the next kernel set up
+  }
+
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (elect_one()) {
-      mbar_arrive_expect_tx(&w_bar, (uint32_t)p.w_bytes);
-      bulk_load_1d(smem + p.w_off, p.wblob, (uint32_t)p.w_bytes, &w_bar);
-      const uint32_t strip_tx = (uint32_t)(nchunks * p.strip_px * 128);
-      const int c0 = p.chunk_c0[0], c1 = p.chunk_c0[1], c2 = p.chunk_c0[2], c3 = p.chunk_c0[3];
-      uint32_t slot = 0, par = 0, seq = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        int b, y0, y1, x0;
-        decode(item, b, y0, y1, x0);
-        for (int row = y0 - halo; row < y1 + halo; ++row, ++seq) {
-          mbar_wait(&empty_bar[slot], par ^ 1);
-          mbar_arrive_expect_tx(&full_bar[slot], strip_tx);
-          uint8_t* dst = smem + ring_off + slot * strip_bytes;
-          tma_load_4d(&tmA, &full_bar[slot], dst, c0, x0 - halo, row, b);
-          if (nchunks > 1) tma_load_4d(&tmA, &full_bar[slot], dst + chunk_bytes, c1, x0 - halo, row, b);
-          if (nchunks > 2) tma_load_4d(&tmA, &full_bar[slot], dst + 2 * chunk_bytes, c2, x0 - halo, row, b);
-          if (nchunks > 3) tma_load_4d(&tmA, &full_bar[slot], dst + 3 * chunk_bytes, c3, x0 - halo, row, b);
-          TC_STAMP(1, seq);
-          if (++slot == (uint32_t)S) { slot = 0; par ^= 1; }
-        }
-      }
+      produce(0xffffffffu);
       TC_STAMP(0, 2);
     }
     __syncwarp();
@@ -270,9 +354,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (++wslot == (uint32_t)S) { wslot = 0; wpar ^= 1; }
             ++waited;
           }
-          const uint32_t aslot = t & 1;
+          const uint32_t aslot = t & (NS - 1);
           TC_STAMP(2, 2 * t);
-          mbar_wait(&tempty_bar[aslot], ((t >> 1) & 1) ^ 1);
+          mbar_wait(&tempty_bar[aslot], ((t >> ns_shift) & 1) ^ 1);
           tc_fence_after_sync();
           const uint32_t d_base = tmem_base + aslot * acc_cols;
           const int ne = (dbg_flags & 1) ? 0 : n_entries;
@@ -308,15 +392,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncwarp();
   } else {
     // ================================ epilogue ====================================
+    // 8 warps: warp w reads TMEM lanes 32*(w%4).. (hardware rule); the two warps of a lane quadrant split
+    // the epilogue chunks (32 or 16 accumulator columns each) between them by chunk parity
     const int q = warp & 3;           // TMEM lane quadrant this warp may read
+    const int half = (warp - 2) >> 2; // 0: warps 2..5, 1: warps 6..9
     const int m = q * 32 + lane;      // pixel of the tile == TMEM lane
-    const bool store_warp = (warp == 2);
-    // group parameters in registers
-    const TcOutGroup g0 = p.g[0];
-    const TcOutGroup g1 = p.g[ngroups > 1 ? 1 : 0];
+    const bool store_thread = (warp == 2) && (lane == 0);
     const int ps_fp32 = p.ps_fp32;
     void* const ps_out = p.ps_out;
     const int ng = (dbg_flags & 2) ? 0 : ngroups;
+    const int nck = ng;
+    griddep_wait();   // residual reads, staging stores and the fused pixel-shuffle store touch global memory
+    // per-group constants in registers (the group index is a compile-time constant in the unrolled loops)
+    int gcol0[TC_MAX_GROUPS], gncols[TC_MAX_GROUPS], gmode[TC_MAX_GROUPS], gswz[TC_MAX_GROUPS];
+    int gstage[TC_MAX_GROUPS], gstage_bytes[TC_MAX_GROUPS];
+    bool ggelu[TC_MAX_GROUPS];
+    float gslope[TC_MAX_GROUPS];
+#pragma unroll
+    for (int gi = 0; gi < TC_MAX_GROUPS; ++gi) {
+      const TcOutGroup& g = grp_s[gi < ngroups ? gi : 0];
+      gcol0[gi] = g.col0; gncols[gi] = gi < ngroups ? g.ncols : 0; gmode[gi] = g.mode; gswz[gi] = g.swizzle;
+      gstage[gi] = g.stage_off; gstage_bytes[gi] = g.stage_bytes;
+      ggelu[gi] = g.act == ACT_GELU; gslope[gi] = g.slope;
+    }
+    const bool g0_has_res = ng > 0 && grp_s[0].res != nullptr;
+    const __half* const g0_res = g0_has_res ? grp_s[0].res + grp_s[0].res_coff : nullptr;
+    const int g0_res_stride = grp_s[0].res_stride;
     uint32_t t = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       int b, y0, y1, x0;
@@ -325,118 +426,82 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int x = x0 + m;
         const bool valid = x < W;
         const long long pix = ((long long)b * H + y) * W + x;
-        const uint32_t aslot = t & 1, sbuf = t & 1;
-        // residual rows are fetched before the accumulator is ready so their latency hides behind the MMAs
-        // (only group 0 may carry a residual)
-        uint4 res0[8];
-        if (g0.res != nullptr) {
-          const uint4* rp = reinterpret_cast<const uint4*>(g0.res + pix * g0.res_stride + g0.res_coff);
+        const uint32_t aslot = t & (NS - 1), sbuf = t & 1;
+        // residual rows (group 0 only) are fetched before the accumulator is ready: their latency hides
+        // behind the MMAs
+        uint4 rpre[2][2];
+        if (g0_has_res) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) res0[i] = (valid && i * 8 < g0.ncols) ? rp[i] : make_uint4(0, 0, 0, 0);
-        }
-        // staging buffer `sbuf` was last read by the TMA store of tile t-2
-        if (store_warp && lane == 0) tma_store_wait_read<1>();
-        named_bar_sync(1, 128);
-        if (threadIdx.x == 64) TC_STAMP(3, 3 * t);
-        mbar_wait(&tfull_bar[aslot], (t >> 1) & 1);
-        tc_fence_after_sync();
-        if (threadIdx.x == 64) TC_STAMP(3, 3 * t + 1);
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + aslot * acc_cols;
-#pragma unroll
-        for (int gi = 0; gi < 2; ++gi) {
-          if (gi >= ng) break;
-          const TcOutGroup& g = gi == 0 ? g0 : g1;
-          const uint4* resv = res0;
-          const bool has_res = gi == 0 && g.res != nullptr;
-          uint8_t* stage = smem + g.stage_off + sbuf * g.stage_bytes;
-          const int row_bytes = g.ncols * 2;
-          for (int c0 = 0; c0 < g.ncols; c0 += 32) {
-            if (g.ncols - c0 >= 32) {
-              float f[32];
-              tc_epi_chunk<32>(taddr + g.col0 + c0, &bias_s[gi][c0], g.act, g.slope, resv + (c0 >> 3), has_res, g.res_after, f);
-              if (g.mode == 0) {
-#pragma unroll
-                for (int hseg = 0; hseg < 4; ++hseg) {
-                  uint4 u;
-                  __half2* h = reinterpret_cast<__half2*>(&u);
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(f[hseg * 8 + 2 * j], f[hseg * 8 + 2 * j + 1]);
-                  const int chunk = (c0 >> 3) + hseg;
-                  const int pos = g.swizzle ? (chunk ^ (m & 7)) : chunk;
-                  *reinterpret_cast<uint4*>(stage + m * row_bytes + pos * 16) = u;
-                }
-              } else if (valid) {
-                // fused PixelShuffle(4): column 16*c + 4*i + j of pixel (y,x) -> out[b, c, 4y+i, 4x+j]
-                const int Ho = 4 * H, Wo = 4 * W;
-#pragma unroll
-                for (int cc = 0; cc < 2; ++cc) {
-                  const int ch = (c0 >> 4) + cc;
-#pragma unroll
-                  for (int i = 0; i < 4; ++i) {
-                    const long long o = (((long long)b * 3 + ch) * Ho + 4 * y + i) * Wo + 4 * x;
-                    const float* ff = f + cc * 16 + 4 * i;
-                    if (ps_fp32) {
-                      *reinterpret_cast<float4*>(reinterpret_cast<float*>(ps_out) + o) = make_float4(ff[0], ff[1], ff[2], ff[3]);
-                    } else {
-                      uint2 u;
-                      __half2* h = reinterpret_cast<__half2*>(&u);
-                      h[0] = __floats2half2_rn(ff[0], ff[1]);
-                      h[1] = __floats2half2_rn(ff[2], ff[3]);
-                      *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(ps_out) + o) = u;
-                    }
-                  }
-                }
-              }
-            } else {
-              float f[16];
-              tc_epi_chunk<16>(taddr + g.col0 + c0, &bias_s[gi][c0], g.act, g.slope, resv + (c0 >> 3), has_res, g.res_after, f);
-              if (g.mode == 0) {
-#pragma unroll
-                for (int hseg = 0; hseg < 2; ++hseg) {
-                  uint4 u;
-                  __half2* h = reinterpret_cast<__half2*>(&u);
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(f[hseg * 8 + 2 * j], f[hseg * 8 + 2 * j + 1]);
-                  const int chunk = (c0 >> 3) + hseg;
-                  const int pos = g.swizzle ? (chunk ^ (m & 7)) : chunk;
-                  *reinterpret_cast<uint4*>(stage + m * row_bytes + pos * 16) = u;
-                }
-              } else if (valid) {
-                const int Ho = 4 * H, Wo = 4 * W;
-                const int ch = c0 >> 4;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const long long o = (((long long)b * 3 + ch) * Ho + 4 * y + i) * Wo + 4 * x;
-                  const float* ff = f + 4 * i;
-                  if (ps_fp32) {
-                    *reinterpret_cast<float4*>(reinterpret_cast<float*>(ps_out) + o) = make_float4(ff[0], ff[1], ff[2], ff[3]);
-                  } else {
-                    uint2 u;
-                    __half2* h = reinterpret_cast<__half2*>(&u);
-                    h[0] = __floats2half2_rn(ff[0], ff[1]);
-                    h[1] = __floats2half2_rn(ff[2], ff[3]);
-                    *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(ps_out) + o) = u;
-                  }
-                }
-              }
+          for (int k = 0; k < 2; ++k) {
+            rpre[k][0] = make_uint4(0, 0, 0, 0);
+            rpre[k][1] = make_uint4(0, 0, 0, 0);
+            const int c0 = (half + 2 * k) * 16;
+            if (valid && c0 < gncols[0]) {
+              const uint4* rp = reinterpret_cast<const uint4*>(g0_res + pix * g0_res_stride + c0);
+              rpre[k][0] = rp[0];
+              rpre[k][1] = rp[1];
             }
           }
         }
+        // staging buffer `sbuf` was last read by the TMA store of tile t-2
+        if (store_thread) tma_store_wait_read<1>();
+        named_bar_sync(1, 32 * TC_EPI_WARPS);
+        if (threadIdx.x == 64) TC_STAMP(3, 3 * t);
+        mbar_wait(&tfull_bar[aslot], (t >> ns_shift) & 1);
+        tc_fence_after_sync();
+        if (threadIdx.x == 64) TC_STAMP(3, 3 * t + 1);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + aslot * acc_cols;
+        // tcgen05.ld is queued behind the MMAs already issued for the next tiles (in-order tensor pipe), so
+        // this warp issues ALL of its TMEM loads for the tile back to back and waits once.  Within every
+        // output group the two warps of a lane quadrant take alternate 16-column units.
+        // (group, k) slots are compile-time; slot s+1's TMEM load is in flight while slot s is converted and
+        // staged (two register buffers)
+        uint32_t va[16], vb[16];
+        auto slot_valid = [&](int s) { return (s >> 1) < ng && (half + 2 * (s & 1)) * 16 < gncols[s >> 1]; };
+        auto slot_load = [&](int s, uint32_t (&v)[16]) { tmem_ld16_nc(taddr + gcol0[s >> 1] + (half + 2 * (s & 1)) * 16, v); };
+        auto slot_run = [&](int s, const uint32_t (&v)[16]) {
+          const int gi = s >> 1, c0 = (half + 2 * (s & 1)) * 16;
+          const TcOutGroup& g = grp_s[gi];
+          const bool has_res = gi == 0 && g0_has_res;
+          uint8_t* stage_row = smem + gstage[gi] + sbuf * gstage_bytes[gi] + m * (gncols[gi] * 2);
+          const int swz = gswz[gi] ? (m & 7) : 0;
+          float f[16];
+          tc_epi_math16(v, &bias_s[gi][c0], ggelu[gi], gslope[gi], has_res, rpre[s & 1][0], rpre[s & 1][1], g.res_after, f);
+          tc_epi_store16(f, gmode[gi], stage_row, c0, swz, valid, ps_out, ps_fp32, b, y, x, H, W);
+        };
+        if (slot_valid(0)) slot_load(0, va);
+#pragma unroll
+        for (int s = 0; s < 2 * TC_MAX_GROUPS; ++s) {
+          tmem_ld_wait();
+          if (s + 1 < 2 * TC_MAX_GROUPS && slot_valid(s + 1)) {
+            if (s & 1) slot_load(s + 1, va); else slot_load(s + 1, vb);
+          }
+          if (slot_valid(s)) {
+            if (s & 1) slot_run(s, vb); else slot_run(s, va);
+          }
+        }
+        if (threadIdx.x == 64 && t < 8) TC_STAMP(1, 16 + 2 * t);
+        if (threadIdx.x == 64 && t < 8) TC_STAMP(1, 17 + 2 * t);
         // accumulator slot drained: hand it back to the MMA warp
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[aslot]);
         fence_proxy_async_smem();
-        named_bar_sync(2, 128);
-        if (store_warp && lane == 0) {
-          if (ng > 0 && g0.mode == 0) tma_store_4d(&tmO0, smem + g0.stage_off + sbuf * g0.stage_bytes, 0, x0, y, b);
-          if (ng > 1 && g1.mode == 0) tma_store_4d(&tmO1, smem + g1.stage_off + sbuf * g1.stage_bytes, 0, x0, y, b);
+        named_bar_sync(2, 32 * TC_EPI_WARPS);
+        if (store_thread) {
+          if (nck > 0) {
+            if (grp_s[0].mode == 0) tma_store_4d(&tmO0, smem + grp_s[0].stage_off + sbuf * grp_s[0].stage_bytes, 0, x0, y, b);
+            if (ngroups > 1 && grp_s[1].mode == 0)
+              tma_store_4d(&tmO1, smem + grp_s[1].stage_off + sbuf * grp_s[1].stage_bytes, 0, x0, y, b);
+            if (ngroups > 2 && grp_s[2].mode == 0)
+              tma_store_4d(&tmO2, smem + grp_s[2].stage_off + sbuf * grp_s[2].stage_bytes, 0, x0, y, b);
+          }
           tma_store_commit();
           TC_STAMP(3, 3 * t + 2);
         }
       }
     }
-    if (store_warp && lane == 0) {
+    if (store_thread) {
       tma_store_wait_all<0>();
       TC_STAMP(0, 4);
     }

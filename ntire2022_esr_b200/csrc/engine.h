@@ -39,7 +39,7 @@ struct BufDecl {
 };
 enum { BUF_IN = -1, BUF_OUT = -2, BUF_NONE = -3 };
 
-enum OpKind { OP_HEAD = 0, OP_BSRN_HEAD, OP_CONV, OP_DW, OP_POOL, OP_ESA_APPLY, OP_CONV_TC };
+enum OpKind { OP_HEAD = 0, OP_BSRN_HEAD, OP_CONV, OP_DW, OP_POOL, OP_ESA_APPLY, OP_CONV_TC, OP_ESA_APPLY2 };
 
 // ---- tcgen05 convolution, shape independent part ------------------------------------------------
 struct TcPlaneEntry {   // one [n x 64] B block = one (tap, chunk, column segment)

@@ -56,7 +56,7 @@ struct Engine {
   DevGraph graphs[2];  // 0: CUDA-core graph (fp32 mode, and fp16 when tc is off), 1: tcgen05 graph
   std::string err;
   // options
-  int opt_tc = 1, opt_shift_mode = 0, opt_use_graph = 1, opt_rows_per_item = 0, opt_timeline = 0, opt_dbg_flags = 0;
+  int opt_tc = 1, opt_shift_mode = 0, opt_use_graph = 1, opt_rows_per_item = 0, opt_timeline = 0, opt_dbg_flags = 0, opt_acc_slots = 4, opt_pdl = 1;
   long long* d_timeline = nullptr;  // 128 stamps per tcgen05 launch (debug option tc_timeline)
   std::list<Plan> plans;
   // host-buffer path
@@ -159,10 +159,25 @@ static WsLayout ws_layout(const Graph& g, int B, int H, int W, int dtype) {
 }
 
 // ---- generic launches -----------------------------------------------------------------------------
+// Every kernel goes through this helper.  With g_pdl set the launch carries the programmatic stream
+// serialization attribute: the kernel may start while its predecessor drains, and synchronises on it
+// with griddepcontrol.wait (all kernels of the engine call it before touching activations).
+static thread_local bool g_pdl = false;
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 template <typename K, typename P>
 static cudaError_t launch1(K kern, dim3 grid, dim3 block, size_t smem, cudaStream_t s, const P& p) {
-  kern<<<grid, block, smem, s>>>(p);
-  return cudaGetLastError();
+  return launch_k(kern, grid, block, smem, s, p);
 }
 
 static int make_tensor_map(Engine* e, CUtensorMap* m, void* base, int C_stride_elems, int c_extent, int W, int H, int B,
@@ -186,11 +201,11 @@ static double op_flops(const OpDecl& op, int B, int H, int W) {
   return 2.0 * op.macs_pp * px * B;
 }
 
-static const size_t kMaxSmem = 232448 - 1024;  // 227 KB minus the kernel's static shared memory (barriers, bias)
+static const size_t kMaxSmem = 232448 - 2048;  // 227 KB minus the kernel's static shared memory (barriers, bias)
 
 static int plan_tc(Engine* e, const DevGraph& dg, const TcConv& c, const std::string& name, const WsLayout& L, Plan& pl) {
   struct Packed {
-    CUtensorMap tmA, tmO0, tmO1;
+    CUtensorMap tmA, tmO[TC_MAX_GROUPS];
     TcParams p;
   };
   auto pk = std::make_shared<Packed>();
@@ -208,8 +223,9 @@ static int plan_tc(Engine* e, const DevGraph& dg, const TcConv& c, const std::st
   p.ngroups = (int)c.groups.size();
   if (p.n_entries > TC_MAX_ENTRIES) return fail(e, ESR_E_INVALID, name + ": too many MMA entries");
   p.acc_cols = (c.acc_cols + 15) / 16 * 16;
+  p.acc_slots = (e->opt_acc_slots == 4 && 4 * p.acc_cols <= 512) ? 4 : 2;
   int tm = 32;
-  while (tm < 2 * p.acc_cols) tm *= 2;
+  while (tm < p.acc_slots * p.acc_cols) tm *= 2;
   if (tm > 512) return fail(e, ESR_E_INVALID, name + ": accumulator does not fit TMEM");
   p.tmem_cols = tm;
   p.ps_fp32 = 0;
@@ -232,10 +248,13 @@ static int plan_tc(Engine* e, const DevGraph& dg, const TcConv& c, const std::st
   p.w_off = 0;
   p.w_bytes = (int)c.blob.size();
   off += (c.blob.size() + 1023) / 1024 * 1024;
+  if (p.ngroups > TC_MAX_GROUPS) return fail(e, ESR_E_INVALID, name + ": too many output groups");
+  std::vector<TcChunk> chunks;
   for (int gi = 0; gi < p.ngroups; ++gi) {
     const TcGroupDecl& gd = c.groups[gi];
     TcOutGroup& g = p.g[gi];
-    g.col0 = gd.col0; g.ncols = gd.ncols; g.act = gd.act; g.slope = gd.slope;
+    g.col0 = gd.col0; g.ncols = gd.ncols; g.act = gd.act;
+    g.slope = gd.act == ACT_RELU ? 0.f : (gd.act == ACT_LRELU ? gd.slope : 1.f);   // NONE/RELU/LRELU = max(v, v*slope)
     g.res_after = gd.res_after;
     g.mode = gd.mode;
     g.swizzle = gd.ncols == 64 ? 1 : 0;
@@ -247,21 +266,28 @@ static int plan_tc(Engine* e, const DevGraph& dg, const TcConv& c, const std::st
       g.res_stride = dg.g.bufs[gd.res].C;
       g.res_coff = gd.res_coff;
     }
+    for (int c0 = 0; c0 < gd.ncols;) {
+      const int wdt = 16;
+      TcChunk ck;
+      memset(&ck, 0, sizeof(ck));
+      ck.tcol = (uint16_t)(gd.col0 + c0); ck.group = (uint8_t)gi; ck.c0 = (uint8_t)c0; ck.width = (uint8_t)wdt;
+      chunks.push_back(ck);
+      c0 += wdt;
+    }
     if (gd.mode == 0) {
       g.stage_off = (int)off;
       g.stage_bytes = (TC_TILE_PX * gd.ncols * 2 + 1023) / 1024 * 1024;
       off += 2 * (size_t)g.stage_bytes;
       const int Cs = dg.g.bufs[gd.out].C;
       __half* base = reinterpret_cast<__half*>(ws + L.off[gd.out]) + gd.out_coff;
-      int rc = make_tensor_map(e, gi == 0 ? &pk->tmO0 : &pk->tmO1, base, Cs, gd.ncols, W, H, B, gd.ncols, TC_TILE_PX,
-                               g.swizzle != 0);
+      int rc = make_tensor_map(e, &pk->tmO[gi], base, Cs, gd.ncols, W, H, B, gd.ncols, TC_TILE_PX, g.swizzle != 0);
       if (rc) return rc;
     }
   }
-  if (p.ngroups < 2) pk->tmO1 = pk->tmO0;
-  if (c.groups[0].mode != 0) {
-    // no NHWC store at all (network tail): the kernel still prefetches the descriptors, give it A's
-  }
+  // 16-column units alternate between the two epilogue warp sets (unit index parity)
+  if ((int)chunks.size() > TC_MAX_CHUNKS) return fail(e, ESR_E_INVALID, name + ": too many epilogue chunks");
+  p.n_epi_chunks = (int)chunks.size();
+  for (size_t i = 0; i < chunks.size(); ++i) p.ck[i] = chunks[i];
   p.ring_off = (int)off;
   const size_t avail = kMaxSmem - 1024 - off;
   int nslots = (int)std::min<size_t>(TC_MAX_SLOTS, avail / p.strip_bytes);
@@ -274,7 +300,8 @@ static int plan_tc(Engine* e, const DevGraph& dg, const TcConv& c, const std::st
     int rc = make_tensor_map(e, &pk->tmA, ws + L.off[c.in], Cs, Cs, W, H, B, 64, p.strip_px, true);
     if (rc) return rc;
   }
-  if (c.groups[0].mode != 0) { pk->tmO0 = pk->tmA; pk->tmO1 = pk->tmA; }
+  for (int gi = 0; gi < TC_MAX_GROUPS; ++gi)   // unused descriptor slots must still hold a valid map (they are prefetched)
+    if (gi >= p.ngroups || c.groups[gi].mode != 0) pk->tmO[gi] = pk->tmA;
   // work decomposition: items = (image, 128-px column strip, segment of R rows)
   p.strips_x = (W + TC_TILE_PX - 1) / TC_TILE_PX;
   int bestR = 1;
@@ -309,8 +336,8 @@ static int plan_tc(Engine* e, const DevGraph& dg, const TcConv& c, const std::st
     attr_set = kMaxSmem;
   }
   pl.launches.push_back(Launch{"conv_tc:" + name, [pk, grid, smem](cudaStream_t s) {
-                                 conv_tc_kernel<<<grid, TC_THREADS, smem, s>>>(pk->tmA, pk->tmO0, pk->tmO1, pk->p);
-                                 return cudaGetLastError();
+                                 return launch_k(conv_tc_kernel, dim3(grid), dim3(TC_THREADS), smem, s, pk->tmA, pk->tmO[0], pk->tmO[1],
+                                                 pk->tmO[2], pk->p);
                                }});
   return ESR_OK;
 }
@@ -358,7 +385,7 @@ static int build_plan(Engine* e, Plan& pl) {
       case OP_HEAD:
       case OP_BSRN_HEAD: {
         const long long npix = (long long)B * H * W;
-        const dim3 grid((unsigned)((npix + 127) / 128));
+        const dim3 grid(op.kind == OP_HEAD ? (unsigned)((long long)B * H * ((W + 255) / 256)) : (unsigned)((npix + 127) / 128));
         const void* in = pl.in;
         void* out = ptr(op.out);
         const int stride = g.bufs[op.out].C;
@@ -367,20 +394,16 @@ static int build_plan(Engine* e, Plan& pl) {
         if (op.kind == OP_HEAD) {
           pl.launches.push_back(Launch{"head:" + op.name, [=](cudaStream_t s) {
             if (f16)
-              k_head_conv<__half, __half, float><<<grid, 128, 0, s>>>((const __half*)in, (__half*)out, w, b, B, H, W, stride, 64);
-            else
-              k_head_conv<float, float, double><<<grid, 128, 0, s>>>((const float*)in, (float*)out, w, b, B, H, W, stride, 64);
-            return cudaGetLastError();
+              return launch_k(k_head_conv<__half, __half, float>, grid, dim3(256), 0, s, (const __half*)in, (__half*)out, w, b, B, H, W, stride, 64);
+            return launch_k(k_head_conv<float, float, double>, grid, dim3(256), 0, s, (const float*)in, (float*)out, w, b, B, H, W, stride, 64);
           }});
         } else {
           const float* wd = dg.d_params + dg.tables[op.tab2].off_w;
           const float* bd = dg.d_params + dg.tables[op.tab2].off_b;
           pl.launches.push_back(Launch{"bsrn_head:" + op.name, [=](cudaStream_t s) {
             if (f16)
-              k_bsrn_head<__half, __half, float><<<grid, 128, 0, s>>>((const __half*)in, (__half*)out, w, b, wd, bd, B, H, W, stride, 64);
-            else
-              k_bsrn_head<float, float, double><<<grid, 128, 0, s>>>((const float*)in, (float*)out, w, b, wd, bd, B, H, W, stride, 64);
-            return cudaGetLastError();
+              return launch_k(k_bsrn_head<__half, __half, float>, grid, dim3(128), 0, s, (const __half*)in, (__half*)out, w, b, wd, bd, B, H, W, stride, 64);
+            return launch_k(k_bsrn_head<float, float, double>, grid, dim3(128), 0, s, (const float*)in, (float*)out, w, b, wd, bd, B, H, W, stride, 64);
           }});
         }
         break;
@@ -412,7 +435,8 @@ static int build_plan(Engine* e, Plan& pl) {
         const bool in32 = is_f32(op.in), out32 = op.ps ? in32 : is_f32(op.out);
         const bool dbl = !f16;
         if (t.cin8 == 16 && t.cout16 == 16 && !op.ps) {  // ESA branch: small-conv kernel
-          const dim3 grid16((unsigned)((npix * 4 + 127) / 128));
+          const long long pairs = (long long)B * p.Hout * ((p.Wout + 1) / 2);
+          const dim3 grid16((unsigned)((pairs * 2 + 127) / 128));
           pl.launches.push_back(Launch{"conv16:" + op.name, [=](cudaStream_t s) {
             return dbl ? launch_conv16<double>(in32, out32, grid16, s, p) : launch_conv16<float>(in32, out32, grid16, s, p);
           }});
@@ -452,8 +476,7 @@ static int build_plan(Engine* e, Plan& pl) {
         const long long total = (long long)B * Ho * Wo * 4;
         const dim3 grid((unsigned)((total + 127) / 128));
         pl.launches.push_back(Launch{"maxpool:" + op.name, [=](cudaStream_t s) {
-          k_maxpool7s3<<<grid, 128, 0, s>>>(in, out, B, Hin, Win, Ho, Wo);
-          return cudaGetLastError();
+          return launch_k(k_maxpool7s3, grid, dim3(128), 0, s, in, out, B, Hin, Win, Ho, Wo);
         }});
         break;
       }
@@ -470,9 +493,24 @@ static int build_plan(Engine* e, Plan& pl) {
         const long long total = (long long)B * H * W * op.cgroups;
         const dim3 grid((unsigned)((total + 127) / 128));
         pl.launches.push_back(Launch{"esa_apply:" + op.name, [=](cudaStream_t s) {
-          if (f16) k_esa_apply<__half, float><<<grid, 128, 0, s>>>(p);
-          else k_esa_apply<float, double><<<grid, 128, 0, s>>>(p);
-          return cudaGetLastError();
+          if (f16) return launch_k(k_esa_apply<__half, float>, grid, dim3(128), 0, s, p);
+          return launch_k(k_esa_apply<float, double>, grid, dim3(128), 0, s, p);
+        }});
+        break;
+      }
+      case OP_ESA_APPLY2: {
+        if (!f16) return fail(e, ESR_E_INVALID, "commuted ESA tail is fp16 only");
+        EsaApply2Params p;
+        memset(&p, 0, sizeof(p));
+        p.x = ptr(op.in); p.x_stride = g.bufs[op.in].C; p.x_coff = op.in_coff;
+        p.cf = ptr(op.c1); p.cf_stride = g.bufs[op.c1].C; p.cf_coff = op.c1_coff;
+        p.m3 = (const float*)ptr(op.c3); p.H3 = L.H[op.c3]; p.W3 = L.W[op.c3]; p.m3_stride = g.bufs[op.c3].C;
+        p.out = ptr(op.out); p.out_stride = g.bufs[op.out].C; p.out_coff = op.out_coff;
+        p.B = B; p.H = H; p.W = W; p.cg8 = op.cgroups;
+        const long long total = (long long)B * H * W * op.cgroups;
+        const int nblk = (int)std::min<long long>((total + 255) / 256, (long long)e->num_sms * 8);
+        pl.launches.push_back(Launch{"esa_apply2:" + op.name, [=](cudaStream_t s) {
+          return launch_k(k_esa_apply2<__half>, dim3(nblk), dim3(256), 0, s, p);
         }});
         break;
       }
@@ -666,6 +704,7 @@ int esr_forward(esr_handle* h, const void* in_nchw, void* out_nchw, int B, int H
   }
   Plan* pl = get_plan(h, in_nchw, out_nchw, B, H, W, dtype, workspace, rc);
   if (!pl) return rc;
+  struct PdlScope { PdlScope(bool on) { g_pdl = on; } ~PdlScope() { g_pdl = false; } } pdl_scope(h->opt_pdl != 0);
   if (h->opt_use_graph && !pl->graph_failed) {
     if (!pl->gexec) {
       cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
@@ -736,7 +775,7 @@ static Plan* dry_plan(esr_handle* h, int B, int H, int W, int dtype, Plan& tmp) 
   // names only: one launch per op
   tmp.launches.clear();
   for (auto& op : h->graphs[gid].g.ops) {
-    static const char* kn[] = {"head", "bsrn_head", "conv_generic", "dwconv", "maxpool", "esa_apply", "conv_tc"};
+    static const char* kn[] = {"head", "bsrn_head", "conv_generic", "dwconv", "maxpool", "esa_apply", "conv_tc", "esa_apply2"};
     std::string kname = kn[op.kind];
     if (op.kind == OP_CONV && !op.ps && h->graphs[gid].tables[op.tab].cin8 == 16 && h->graphs[gid].tables[op.tab].cout16 == 16)
       kname = "conv16";
@@ -813,6 +852,8 @@ int esr_set_option(esr_handle* h, const char* key, int value) {
   else if (k == "tc_rows_per_item") h->opt_rows_per_item = value;
   else if (k == "tc_timeline") h->opt_timeline = value ? 1 : 0;
   else if (k == "tc_dbg_flags") h->opt_dbg_flags = value;
+  else if (k == "tc_acc_slots") h->opt_acc_slots = value == 4 ? 4 : 2;
+  else if (k == "use_pdl") h->opt_pdl = value ? 1 : 0;
   else return fail(h, ESR_E_INVALID, "unknown option: " + k);
   drop_plans(h);
   return ESR_OK;

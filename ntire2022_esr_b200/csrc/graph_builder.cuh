@@ -8,6 +8,7 @@
 // models/imdn_baseline.py:46-65 + models/basicblock.py:259-265, models/team04_rlfn.py:76-152,
 // models/team18_bsrn.py:82-236.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -265,36 +266,71 @@ struct GraphBuilder {
     c.halo = halo;
     c.acc_cols = b.accP;
     std::vector<int> seg_started(b.segs.size(), 0);
-    // order: plane-major so that consecutive MMAs walk different accumulator columns as little as
-    // possible; all entries of one segment accumulate into the same columns
+    // An SS-mode MMA costs 32 + N/4 cycles (measured), so adjacent column segments that are both
+    // non-zero in a (plane, chunk) are issued as ONE wider MMA.  Planes touching more segments go first
+    // so that the merged entry can be the one that initialises all of its segments.
+    auto seg_nz = [&](const TcPlane& p, int ch, size_t si, int* last_k) {
+      const int col0 = b.segs[si].first, n = b.segs[si].second;
+      int lk = -1;
+      for (int k = 0; k < 64; ++k)
+        for (int j = 0; j < n; ++j)
+          if (p.w[(size_t)(ch * 64 + k) * b.accP + col0 + j] != 0.f) lk = k;
+      if (last_k) *last_k = lk;
+      return lk >= 0;
+    };
+    std::vector<size_t> order(b.planes.size());
+    std::vector<int> nseg(b.planes.size(), 0);
     for (size_t pi = 0; pi < b.planes.size(); ++pi) {
-      const TcPlane& p = b.planes[pi];
-      for (int ch = 0; ch < c.nchunks; ++ch)
-        for (size_t si = 0; si < b.segs.size(); ++si) {
-          const int col0 = b.segs[si].first, n = b.segs[si].second;
-          int last_k = -1;
-          for (int k = 0; k < 64; ++k)
-            for (int j = 0; j < n; ++j)
-              if (p.w[(size_t)(ch * 64 + k) * b.accP + col0 + j] != 0.f) last_k = k;
-          const bool last_chance = (pi + 1 == b.planes.size() && ch + 1 == c.nchunks);
-          if (last_k < 0 && !(last_chance && !seg_started[si])) continue;
-          TcPlaneEntry e;
-          e.dy = p.dy; e.dx = p.dx; e.chunk = ch;
-          e.nsteps = last_k < 0 ? 1 : (last_k / 16 + 1);
-          e.n = n; e.dcol = col0;
-          e.first = seg_started[si] ? 0 : 1;
-          seg_started[si] = 1;
-          e.b_off = c.blob.size();
-          c.blob.resize(c.blob.size() + (size_t)n * 128, 0);
-          uint8_t* blk = c.blob.data() + e.b_off;
-          for (int j = 0; j < n; ++j)
-            for (int k = 0; k < 64; ++k) {
-              const __half h = __float2half_rn(p.w[(size_t)(ch * 64 + k) * b.accP + col0 + j]);
-              memcpy(blk + sw128_offset((uint32_t)j, (uint32_t)k), &h, 2);
-            }
-          c.entries.push_back(e);
-        }
+      order[pi] = pi;
+      for (size_t si = 0; si < b.segs.size(); ++si)
+        for (int ch = 0; ch < c.nchunks; ++ch)
+          if (seg_nz(b.planes[pi], ch, si, nullptr)) { ++nseg[pi]; break; }
     }
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t bb) { return nseg[a] > nseg[bb]; });
+    auto emit = [&](const TcPlane& p, int ch, size_t s0, size_t s1, int last_k) {   // segments [s0, s1)
+      const int col0 = b.segs[s0].first;
+      int n = 0;
+      for (size_t si = s0; si < s1; ++si) n += b.segs[si].second;
+      TcPlaneEntry e;
+      e.dy = p.dy; e.dx = p.dx; e.chunk = ch;
+      e.nsteps = last_k < 0 ? 1 : (last_k / 16 + 1);
+      e.n = n; e.dcol = col0;
+      e.first = seg_started[s0] ? 0 : 1;
+      for (size_t si = s0; si < s1; ++si) seg_started[si] = 1;
+      e.b_off = c.blob.size();
+      c.blob.resize(c.blob.size() + (size_t)n * 128, 0);
+      uint8_t* blk = c.blob.data() + e.b_off;
+      for (int j = 0; j < n; ++j)
+        for (int k = 0; k < 64; ++k) {
+          const __half h = __float2half_rn(p.w[(size_t)(ch * 64 + k) * b.accP + col0 + j]);
+          memcpy(blk + sw128_offset((uint32_t)j, (uint32_t)k), &h, 2);
+        }
+      c.entries.push_back(e);
+    };
+    for (size_t oi = 0; oi < order.size(); ++oi) {
+      const TcPlane& p = b.planes[order[oi]];
+      for (int ch = 0; ch < c.nchunks; ++ch) {
+        size_t si = 0;
+        while (si < b.segs.size()) {
+          int lk;
+          if (!seg_nz(p, ch, si, &lk)) { ++si; continue; }
+          size_t sj = si + 1;
+          int n = b.segs[si].second, run_lk = lk;
+          while (sj < b.segs.size() && b.segs[sj - 1].first + b.segs[sj - 1].second == b.segs[sj].first &&
+                 seg_started[sj] == seg_started[si] && n + b.segs[sj].second <= 256) {
+            int lk2;
+            if (!seg_nz(p, ch, sj, &lk2)) break;
+            run_lk = std::max(run_lk, lk2);
+            n += b.segs[sj].second;
+            ++sj;
+          }
+          emit(p, ch, si, sj, run_lk);
+          si = sj;
+        }
+      }
+    }
+    for (size_t si = 0; si < b.segs.size(); ++si)   // all-zero segment: still has to be initialised
+      if (!seg_started[si]) emit(b.planes[0], 0, si, si + 1, -1);
     c.groups = std::move(groups);
     if (group_bias_out) {
       group_bias_out->clear();
@@ -389,6 +425,48 @@ struct GraphBuilder {
     g.ops.push_back(ap);
   }
 
+  // fp16 / tcgen05 flavour of the ESA tail (RFDN, RLFN): conv4 is commuted through the bilinear
+  // interpolation, M3 = (conv4 o last 3x3)(pooled map) at low resolution, cf' arrives from the c5 GEMM.
+  void esa_tail_commuted(const std::string& p, int arch, const EsaBufs& eb, int m3buf, int f, int nf, int x, int x_coff,
+                         int cfp, int dst, int dst_coff, int cg8, const Mat& conv4) {
+    {
+      const Mat m = conv_mat(p + "conv2", f, f, 3);
+      conv_op(p + "conv2", dense_table(m, 16, 16, pos_id(), pos_id()), eb.esa, 0, eb.s2, 0, ACT_NONE, 0.f, 2, 0);
+    }
+    OpDecl pool;
+    pool.kind = OP_POOL;
+    pool.name = p + "max_pool";
+    pool.in = eb.s2; pool.out = eb.s3a;
+    g.ops.push_back(pool);
+    Mat c4nb = conv4;
+    std::fill(c4nb.b.begin(), c4nb.b.end(), 0.0);   // b4 travels with cf'
+    int last_in = eb.s3a;
+    std::string last_name = "conv3";
+    if (arch == ESR_ARCH_RFDN) {
+      const Mat m1 = conv_mat(p + "conv_max", f, f, 3), m2 = conv_mat(p + "conv3", f, f, 3);
+      conv_op(p + "conv_max", dense_table(m1, 16, 16, pos_id(), pos_id()), eb.s3a, 0, eb.s3b, 0, ACT_RELU);
+      conv_op(p + "conv3", dense_table(m2, 16, 16, pos_id(), pos_id()), eb.s3b, 0, eb.s3a, 0, ACT_RELU);
+      last_in = eb.s3a;
+      last_name = "conv3_";
+    }
+    const Mat ml = conv_mat(p + last_name, f, f, 3);
+    const Mat comp = compose(c4nb, ml);   // 3x3 f -> nf
+    const int ti = dense_table(comp, 16, 64, pos_id(), pos_id());
+    pend_macs = (double)f * f * 9;        // algorithmic count: the reference's 3x3 f->f (conv4 is counted with cf')
+    conv_op(p + last_name + "+conv4", ti, last_in, 0, m3buf, 0, ACT_NONE);
+    OpDecl ap;
+    ap.kind = OP_ESA_APPLY2;
+    ap.name = p + "apply";
+    ap.in = x; ap.in_coff = x_coff;
+    ap.c1 = cfp; ap.c1_coff = 0;
+    ap.c3 = m3buf;
+    ap.out = dst; ap.out_coff = dst_coff;
+    ap.cgroups = cg8;
+    ap.f = f;
+    (void)nf;
+    g.ops.push_back(ap);
+  }
+
   // =============================================================================================
   // RFDN
   // =============================================================================================
@@ -396,8 +474,9 @@ struct GraphBuilder {
     const int dc = nf / 2, f = nf / 4;
     const float sl = 0.05f;
     const int fea = buf(BK_FULL, 64), cat = buf(BK_FULL, 64 * nblocks), t0 = buf(BK_FULL, 64), t1 = buf(BK_FULL, 64),
-              dist = buf(BK_FULL, 128), c5o = buf(BK_FULL, 64), esa = buf(BK_FULL, 32);
+              dist = buf(BK_FULL, 128), c5o = buf(BK_FULL, 64), esa = buf(BK_FULL, tc ? 16 : 32);
     EsaBufs eb{esa, buf(BK_S2, 16, true), buf(BK_S3, 16, true), buf(BK_S3, 16, true)};
+    const int cfpb = tc ? buf(BK_FULL, 64) : BUF_NONE, m3b = tc ? buf(BK_S3, 64, true) : BUF_NONE;
     {
       OpDecl op;
       op.kind = OP_HEAD;
@@ -450,15 +529,17 @@ struct GraphBuilder {
         TcBuild b4 = tc_begin(1, 32, {{0, 32}});
         tc_add(b4, m4, pos_id(), pos_id());
         tc_emit(p + "c4", b4, cur, curc, 1, {tc_group(0, 32, ACT_LRELU, sl, dist, 96)});
-        // c5 with the ESA entry folded in: c1_ = conv1(c5(.)), cf = conv_f(c1_) are 1x1s of a 1x1
-        const Mat c1c = compose(e1, m5), cfc = compose(ef, c1c);
-        TcBuild b5 = tc_begin(2, 96, {{0, 64}, {64, 32}});
+        // c5 with the ESA entry folded in: c1_ = conv1(c5(.)) and cf' = conv4(conv_f(c1_)) + b4 are 1x1s of
+        // a 1x1, so they are extra output columns of the same GEMM
+        const Mat c1c = compose(e1, m5), cfc = compose(ef, c1c), cfp = compose(e4, cfc);
+        TcBuild b5 = tc_begin(2, 144, {{0, 64}, {64, 16}, {80, 64}});
         tc_add(b5, m5, pos_slots(dc, 32), pos_id());
         tc_add(b5, c1c, pos_slots(dc, 32), pos_id(64), (double)e1.O * e1.I);
-        tc_add(b5, cfc, pos_slots(dc, 32), pos_id(80), (double)ef.O * ef.I);
-        tc_emit(p + "c5+esa.conv1+esa.conv_f", b5, dist, 0, 0,
-                {tc_group(0, 64, ACT_NONE, 0.f, c5o, 0), tc_group(64, 32, ACT_NONE, 0.f, esa, 0)});
-        esa_tail(p + "esa.", ESR_ARCH_RFDN, eb, f, nf, c5o, 0, cat, 64 * bi, 4, 1, ef, e4);
+        tc_add(b5, cfp, pos_slots(dc, 32), pos_id(80), (double)ef.O * ef.I + (double)e4.O * e4.I);
+        tc_emit(p + "c5+esa.conv1+esa.conv_f+esa.conv4", b5, dist, 0, 0,
+                {tc_group(0, 64, ACT_NONE, 0.f, c5o, 0), tc_group(64, 16, ACT_NONE, 0.f, esa, 0),
+                 tc_group(80, 64, ACT_NONE, 0.f, cfpb, 0)});
+        esa_tail_commuted(p + "esa.", ESR_ARCH_RFDN, eb, m3b, f, nf, c5o, 0, cfpb, cat, 64 * bi, 8, e4);
       }
       x = cat; xc = 64 * bi;
     }
@@ -490,8 +571,9 @@ struct GraphBuilder {
     const int mf = 48, f = 16;
     const float sl = 0.05f;
     const int fea = buf(BK_FULL, 64), xa = buf(BK_FULL, 64), xb = buf(BK_FULL, 64), t0 = buf(BK_FULL, 64),
-              t1 = buf(BK_FULL, 64), esa = buf(BK_FULL, 32);
+              t1 = buf(BK_FULL, 64), esa = buf(BK_FULL, tc ? 16 : 32);
     EsaBufs eb{esa, buf(BK_S2, 16, true), buf(BK_S3, 16, true), buf(BK_S3, 16, true)};
+    const int cfpb = tc ? buf(BK_FULL, 64) : BUF_NONE, m3b = tc ? buf(BK_S3, 64, true) : BUF_NONE;
     {
       OpDecl op;
       op.kind = OP_HEAD;
@@ -534,14 +616,15 @@ struct GraphBuilder {
         TcBuild b3 = tc_begin(1, 48, {{0, 48}});
         tc_add(b3, m3, pos_id(), pos_id());
         tc_emit(p + "c3_r", b3, t1, 0, 1, {tc_group(0, 48, ACT_LRELU, sl, t0, 0, x, 0, 1)});
-        const Mat c1c = compose(e1, m5), cfc = compose(ef, c1c);
-        TcBuild b5 = tc_begin(1, 80, {{0, 48}, {48, 32}});
+        const Mat c1c = compose(e1, m5), cfc = compose(ef, c1c), cfp = compose(e4, cfc);
+        TcBuild b5 = tc_begin(1, 112, {{0, 48}, {48, 16}, {64, 48}});
         tc_add(b5, m5, pos_id(), pos_id());
         tc_add(b5, c1c, pos_id(), pos_id(48), (double)e1.O * e1.I);
-        tc_add(b5, cfc, pos_id(), pos_id(64), (double)ef.O * ef.I);
-        tc_emit(p + "c5+esa.conv1+esa.conv_f", b5, t0, 0, 0,
-                {tc_group(0, 48, ACT_NONE, 0.f, t1, 0), tc_group(48, 32, ACT_NONE, 0.f, esa, 0)});
-        esa_tail(p + "esa.", ESR_ARCH_RLFN, eb, f, nf, t1, 0, xn, 0, 3, 1, ef, e4);
+        tc_add(b5, cfp, pos_id(), pos_id(64), (double)ef.O * ef.I + (double)e4.O * e4.I);
+        tc_emit(p + "c5+esa.conv1+esa.conv_f+esa.conv4", b5, t0, 0, 0,
+                {tc_group(0, 48, ACT_NONE, 0.f, t1, 0), tc_group(48, 16, ACT_NONE, 0.f, esa, 0),
+                 tc_group(64, 48, ACT_NONE, 0.f, cfpb, 0)});
+        esa_tail_commuted(p + "esa.", ESR_ARCH_RLFN, eb, m3b, f, nf, t1, 0, cfpb, xn, 0, 6, e4);
       }
       x = xn;
     }

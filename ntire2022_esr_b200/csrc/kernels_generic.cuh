@@ -9,6 +9,8 @@
 
 namespace esr {
 
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 enum Act : int { ACT_NONE = 0, ACT_LRELU = 1, ACT_RELU = 2, ACT_GELU = 3 };
 
 __device__ __forceinline__ float apply_act(float v, int act, float slope) {
@@ -67,50 +69,76 @@ __device__ __forceinline__ void stf(__half* p, float v) { *p = __float2half_rn(v
 // w: [27][64] fp32, index (ky*3+kx)*3+ci; bias [64].
 // ---------------------------------------------------------------------------------------------
 template <typename TIn, typename TOut, typename TAcc>
-__global__ void __launch_bounds__(128) k_head_conv(const TIn* __restrict__ in, TOut* __restrict__ out,
+__global__ void __launch_bounds__(256) k_head_conv(const TIn* __restrict__ in, TOut* __restrict__ out,
                                                    const float* __restrict__ w, const float* __restrict__ bias,
                                                    int B, int H, int W, int out_stride, int cstore) {
+  // block = up to 256 consecutive pixels of one image row; thread = 4 consecutive pixels x 16 output
+  // channels (64 accumulators): every weight fetched from shared memory (broadcast LDS.128) feeds 4 FMAs
+  // per lane, which is what keeps a CUDA-core convolution off the shared-memory bandwidth limit.
   __shared__ __align__(16) float ws[27 * 64];
-  __shared__ float bs[64];
-  for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) ws[i] = w[i];
-  if (threadIdx.x < 64) bs[threadIdx.x] = bias[threadIdx.x];
+  __shared__ __align__(16) float bs[64];
+  __shared__ float xs[3][3][260];
+  const int segs = (W + 255) / 256;
+  const int seg = blockIdx.x % segs;
+  const int y = (blockIdx.x / segs) % H;
+  const int b = blockIdx.x / (segs * H);
+  const int x0 = seg * 256;
+  {
+    const float4* src = reinterpret_cast<const float4*>(w);
+    float4* dst = reinterpret_cast<float4*>(ws);
+    for (int i = threadIdx.x; i < 27 * 16; i += 256) dst[i] = __ldg(src + i);
+    if (threadIdx.x < 64) bs[threadIdx.x] = __ldg(bias + threadIdx.x);
+    pdl_wait();
+    for (int i = threadIdx.x; i < 3 * 3 * 258; i += 256) {
+      const int xx = i % 258, r = (i / 258) % 3, ci = i / 774;
+      const int gy = y + r - 1, gx = x0 + xx - 1;
+      const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
+      xs[ci][r][xx] = ok ? ldf(in + (((long long)b * 3 + ci) * H + gy) * W + gx) : 0.f;
+    }
+  }
   __syncthreads();
-  const long long npix = (long long)B * H * W;
-  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (pix >= npix) return;
-  const int x = (int)(pix % W);
-  const int y = (int)((pix / W) % H);
-  const int b = (int)(pix / ((long long)W * H));
-  float xin[27];
+  const int quad = threadIdx.x >> 2, g = threadIdx.x & 3;
+  const int xq = x0 + quad * 4;
+  if (xq >= W || g * 16 >= cstore) return;
+  TAcc acc[4][16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const TAcc bv = (TAcc)bs[g * 16 + j];
+    acc[0][j] = bv; acc[1][j] = bv; acc[2][j] = bv; acc[3][j] = bv;
+  }
 #pragma unroll
   for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-    for (int kx = 0; kx < 3; ++kx) {
-      const int yy = y + ky - 1, xx = x + kx - 1;
-      const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+    for (int ci = 0; ci < 3; ++ci) {
+      float xv[6];
 #pragma unroll
-      for (int ci = 0; ci < 3; ++ci)
-        xin[(ky * 3 + kx) * 3 + ci] = ok ? ldf(in + (((long long)b * 3 + ci) * H + yy) * W + xx) : 0.f;
+      for (int j = 0; j < 6; ++j) xv[j] = xs[ci][ky][quad * 4 + j];
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const float4* w4 = reinterpret_cast<const float4*>(ws + ((ky * 3 + kx) * 3 + ci) * 64 + g * 16);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 ww = w4[q];
+          const float wv[4] = {ww.x, ww.y, ww.z, ww.w};
+#pragma unroll
+          for (int px = 0; px < 4; ++px) {
+            const TAcc xa = (TAcc)xv[px + kx];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[px][4 * q + j] = fma(xa, (TAcc)wv[j], acc[px][4 * q + j]);
+          }
+        }
+      }
     }
-  TOut* o = out + pix * out_stride;
-  for (int c0 = 0; c0 < cstore; c0 += 8) {
-    TAcc acc[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = (TAcc)bs[c0 + j];
+  for (int px = 0; px < 4; ++px) {
+    if (xq + px >= W) break;
+    const long long pix = ((long long)b * H + y) * W + xq + px;
+    TOut* o = out + pix * out_stride + g * 16;
+    float f0[8], f1[8];
 #pragma unroll
-    for (int t = 0; t < 27; ++t) {
-      const TAcc xv = (TAcc)xin[t];
-      const float4 wa = *reinterpret_cast<const float4*>(ws + t * 64 + c0);
-      const float4 wb = *reinterpret_cast<const float4*>(ws + t * 64 + c0 + 4);
-      acc[0] = fma(xv, (TAcc)wa.x, acc[0]); acc[1] = fma(xv, (TAcc)wa.y, acc[1]);
-      acc[2] = fma(xv, (TAcc)wa.z, acc[2]); acc[3] = fma(xv, (TAcc)wa.w, acc[3]);
-      acc[4] = fma(xv, (TAcc)wb.x, acc[4]); acc[5] = fma(xv, (TAcc)wb.y, acc[5]);
-      acc[6] = fma(xv, (TAcc)wb.z, acc[6]); acc[7] = fma(xv, (TAcc)wb.w, acc[7]);
-    }
-    float f[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = (float)acc[j];
-    store8(o + c0, f);
+    for (int j = 0; j < 8; ++j) { f0[j] = (float)acc[px][j]; f1[j] = (float)acc[px][8 + j]; }
+    store8(o, f0);
+    store8(o + 8, f1);
   }
 }
 
@@ -128,6 +156,7 @@ __global__ void __launch_bounds__(128) k_bsrn_head(const TIn* __restrict__ in, T
   for (int i = threadIdx.x; i < 3 * 64; i += blockDim.x) s_wpw[i] = wpw[i];
   for (int i = threadIdx.x; i < 9 * 64; i += blockDim.x) s_wdw[i] = wdw[i];
   if (threadIdx.x < 64) { s_bpw[threadIdx.x] = bpw[threadIdx.x]; s_bdw[threadIdx.x] = bdw[threadIdx.x]; }
+  pdl_wait();
   __syncthreads();
   const long long npix = (long long)B * H * W;
   const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -200,10 +229,15 @@ __global__ void __launch_bounds__(128) k_conv_generic(const ConvGenericParams p)
   const int taps = p.ksize * p.ksize;
   const int g = blockIdx.y;
   const int nw = taps * p.cin8 * 16;
-  for (int i = threadIdx.x; i < nw; i += blockDim.x) {
-    const int r = i >> 4, c = i & 15;
-    wsm[i] = p.w[(long long)r * p.cout16 + g * 16 + c];
+  {
+    float4* dst = reinterpret_cast<float4*>(wsm);
+#pragma unroll 4
+    for (int i = threadIdx.x; i < (nw >> 2); i += 128) {
+      const int r = i >> 2, c4 = i & 3;
+      dst[i] = __ldg(reinterpret_cast<const float4*>(p.w + (long long)r * p.cout16 + g * 16) + c4);
+    }
   }
+  pdl_wait();
   __syncthreads();
   const long long npix = (long long)p.B * p.Hout * p.Wout;
   const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -296,21 +330,32 @@ __global__ void __launch_bounds__(128) k_conv_generic(const ConvGenericParams p)
 // ---------------------------------------------------------------------------------------------
 template <typename TIn, typename TOut, typename TAcc>
 __global__ void __launch_bounds__(128) k_conv16(const ConvGenericParams p) {
+  // thread = 2 horizontally adjacent output pixels x 8 output channels (16 accumulators against
+  // 2 broadcast LDS.128 of weights per input channel); 2 consecutive threads share a pixel pair
   __shared__ __align__(16) float wsm[9 * 16 * 16];
   const int taps = p.ksize * p.ksize;
-  for (int i = threadIdx.x; i < taps * 256; i += blockDim.x) wsm[i] = p.w[i];
+  {
+    const float4* src = reinterpret_cast<const float4*>(p.w);
+    float4* dst = reinterpret_cast<float4*>(wsm);
+#pragma unroll 5
+    for (int i = threadIdx.x; i < taps * 64; i += 128) dst[i] = __ldg(src + i);
+  }
+  pdl_wait();
   __syncthreads();
-  const long long total = (long long)p.B * p.Hout * p.Wout * 4;
+  const int Wp = (p.Wout + 1) >> 1;   // pixel pairs per row
+  const long long total = (long long)p.B * p.Hout * Wp * 2;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  const int g4 = (int)(idx & 3);
-  const long long pix = idx >> 2;
-  const int x = (int)(pix % p.Wout);
-  const int y = (int)((pix / p.Wout) % p.Hout);
-  const int b = (int)(pix / ((long long)p.Wout * p.Hout));
-  TAcc acc[4];
+  const int g8 = (int)(idx & 1);
+  const long long pp = idx >> 1;
+  const int xp = (int)(pp % Wp);
+  const int y = (int)((pp / Wp) % p.Hout);
+  const int b = (int)(pp / ((long long)Wp * p.Hout));
+  const int xa = 2 * xp, xb = 2 * xp + 1;
+  const bool has_b = xb < p.Wout;
+  TAcc acc[2][8];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) acc[j] = (TAcc)p.bias[g4 * 4 + j];
+  for (int j = 0; j < 8; ++j) { acc[0][j] = (TAcc)p.bias[g8 * 8 + j]; acc[1][j] = acc[0][j]; }
   const TIn* in = reinterpret_cast<const TIn*>(p.in);
 #pragma unroll 1
   for (int ky = 0; ky < p.ksize; ++ky) {
@@ -318,39 +363,57 @@ __global__ void __launch_bounds__(128) k_conv16(const ConvGenericParams p) {
     if (yy < 0 || yy >= p.Hin) continue;
 #pragma unroll 1
     for (int kx = 0; kx < p.ksize; ++kx) {
-      const int xx = x * p.stride + kx - p.pad;
-      if (xx < 0 || xx >= p.Win) continue;
-      const TIn* ip = in + (((long long)b * p.Hin + yy) * p.Win + xx) * p.in_stride + p.in_coff;
-      float xv[16];
-      {
-        float a[8], c[8];
-        load8(ip, a);
-        load8(ip + 8, c);
+      const int xxa = xa * p.stride + kx - p.pad, xxb = xb * p.stride + kx - p.pad;
+      const bool oka = xxa >= 0 && xxa < p.Win, okb = has_b && xxb >= 0 && xxb < p.Win;
+      float va[16], vb[16];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { xv[j] = a[j]; xv[8 + j] = c[j]; }
+      for (int j = 0; j < 16; ++j) { va[j] = 0.f; vb[j] = 0.f; }
+      const TIn* row = in + ((long long)b * p.Hin + yy) * p.Win * p.in_stride + p.in_coff;
+      if (oka) {
+        float a[8], c[8];
+        load8(row + (long long)xxa * p.in_stride, a);
+        load8(row + (long long)xxa * p.in_stride + 8, c);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { va[j] = a[j]; va[8 + j] = c[j]; }
       }
-      const float* wt = wsm + (ky * p.ksize + kx) * 256 + g4 * 4;
+      if (okb) {
+        float a[8], c[8];
+        load8(row + (long long)xxb * p.in_stride, a);
+        load8(row + (long long)xxb * p.in_stride + 8, c);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { vb[j] = a[j]; vb[8 + j] = c[j]; }
+      }
+      const float* wt = wsm + (ky * p.ksize + kx) * 256 + g8 * 8;
 #pragma unroll
       for (int ci = 0; ci < 16; ++ci) {
-        const float4 ww = *reinterpret_cast<const float4*>(wt + ci * 16);
-        const TAcc xa = (TAcc)xv[ci];
-        acc[0] = fma(xa, (TAcc)ww.x, acc[0]);
-        acc[1] = fma(xa, (TAcc)ww.y, acc[1]);
-        acc[2] = fma(xa, (TAcc)ww.z, acc[2]);
-        acc[3] = fma(xa, (TAcc)ww.w, acc[3]);
+        const float4 w0 = *reinterpret_cast<const float4*>(wt + ci * 16);
+        const float4 w1 = *reinterpret_cast<const float4*>(wt + ci * 16 + 4);
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        const TAcc xa_ = (TAcc)va[ci], xb_ = (TAcc)vb[ci];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[0][j] = fma(xa_, (TAcc)wv[j], acc[0][j]);
+          acc[1][j] = fma(xb_, (TAcc)wv[j], acc[1][j]);
+        }
       }
     }
   }
-  TOut* o = reinterpret_cast<TOut*>(p.out) + pix * p.out_stride + p.out_coff + g4 * 4;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    TAcc v = acc[j];
-    if (p.res != nullptr && !p.res_after)
-      v += (TAcc)ldf(reinterpret_cast<const TOut*>(p.res) + pix * p.res_stride + p.res_coff + g4 * 4 + j);
-    v = apply_act(v, p.act, p.slope);
-    if (p.res != nullptr && p.res_after)
-      v += (TAcc)ldf(reinterpret_cast<const TOut*>(p.res) + pix * p.res_stride + p.res_coff + g4 * 4 + j);
-    stf(o + j, (float)v);
+  for (int h = 0; h < 2; ++h) {
+    if (h == 1 && !has_b) break;
+    const long long pix = ((long long)b * p.Hout + y) * p.Wout + (h ? xb : xa);
+    float o8[8];
+    float rv[8];
+    if (p.res != nullptr) load8(reinterpret_cast<const TOut*>(p.res) + pix * p.res_stride + p.res_coff + g8 * 8, rv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      TAcc v = acc[h][j];
+      if (p.res != nullptr && !p.res_after) v += (TAcc)rv[j];
+      v = apply_act(v, p.act, p.slope);
+      if (p.res != nullptr && p.res_after) v += (TAcc)rv[j];
+      o8[j] = (float)v;
+    }
+    store8(reinterpret_cast<TOut*>(p.out) + pix * p.out_stride + p.out_coff + g8 * 8, o8);
   }
 }
 
@@ -367,6 +430,7 @@ struct DwParams {
 };
 template <typename TIn, typename TOut, typename TAcc>
 __global__ void __launch_bounds__(128) k_dwconv3x3(const DwParams p) {
+  pdl_wait();
   const int groups = p.c8 >> 3;
   const long long total = (long long)p.B * p.H * p.W * groups;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -412,6 +476,7 @@ __global__ void __launch_bounds__(128) k_dwconv3x3(const DwParams p) {
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_maxpool7s3(const float* __restrict__ in, float* __restrict__ out, int B,
                                                     int Hin, int Win, int Hout, int Wout) {
+  pdl_wait();
   const long long total = (long long)B * Hout * Wout * 4;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
@@ -452,10 +517,14 @@ struct EsaApplyParams {
 template <typename T, typename TAcc>
 __global__ void __launch_bounds__(128) k_esa_apply(const EsaApplyParams p) {
   __shared__ __align__(16) float s_wf[16 * 16], s_bf[16], s_w4[16 * 64], s_b4[64];
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_wf[i] = p.wf[i];
-  for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_w4[i] = p.w4[i];
-  if (threadIdx.x < 16) s_bf[threadIdx.x] = p.bf[threadIdx.x];
-  if (threadIdx.x < 64) s_b4[threadIdx.x] = p.b4[threadIdx.x];
+  {
+    if (threadIdx.x < 64) reinterpret_cast<float4*>(s_wf)[threadIdx.x] = __ldg(reinterpret_cast<const float4*>(p.wf) + threadIdx.x);
+    reinterpret_cast<float4*>(s_w4)[threadIdx.x] = __ldg(reinterpret_cast<const float4*>(p.w4) + threadIdx.x);
+    reinterpret_cast<float4*>(s_w4)[threadIdx.x + 128] = __ldg(reinterpret_cast<const float4*>(p.w4) + threadIdx.x + 128);
+    if (threadIdx.x < 16) s_bf[threadIdx.x] = __ldg(p.bf + threadIdx.x);
+    if (threadIdx.x < 64) s_b4[threadIdx.x] = __ldg(p.b4 + threadIdx.x);
+  }
+  pdl_wait();
   __syncthreads();
   const long long total = (long long)p.B * p.H * p.W * p.cgroups;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -542,6 +611,53 @@ __global__ void __launch_bounds__(128) k_esa_apply(const EsaApplyParams p) {
   for (int j = 0; j < 8; ++j) { a[j] = o[j]; c[j] = o[8 + j]; }
   store8(op, a);
   store8(op + 8, c);
+}
+
+// ---------------------------------------------------------------------------------------------
+// ESA tail, commuted form used by the fp16 path:  y = x * sigmoid(bilinear(M3) + cf')
+// where M3 = conv4 o conv3_ evaluated on the pooled map (bilinear interpolation commutes with a 1x1 conv)
+// and cf' = conv4(conv_f(conv1(.))) + b4 comes out of the c5 tensor-core GEMM.  Pure elementwise:
+// 8 threads per pixel x 8 channels, 16-byte accesses.
+// ---------------------------------------------------------------------------------------------
+struct EsaApply2Params {
+  const void* x; int x_stride, x_coff;
+  const void* cf; int cf_stride, cf_coff;
+  const float* m3; int H3, W3, m3_stride;
+  void* out; int out_stride, out_coff;
+  int B, H, W, cg8;   // cg8: 8-channel groups per pixel
+};
+template <typename T>
+__global__ void __launch_bounds__(256) k_esa_apply2(const EsaApply2Params p) {
+  pdl_wait();
+  const long long total = (long long)p.B * p.H * p.W * p.cg8;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % p.cg8);
+    const long long pix = idx / p.cg8;
+    const int x = (int)(pix % p.W);
+    const int y = (int)((pix / p.W) % p.H);
+    const int b = (int)(pix / ((long long)p.W * p.H));
+    const float sy = fmaxf(((float)y + 0.5f) * ((float)p.H3 / (float)p.H) - 0.5f, 0.f);
+    const float sx = fmaxf(((float)x + 0.5f) * ((float)p.W3 / (float)p.W) - 0.5f, 0.f);
+    const int y0 = min((int)sy, p.H3 - 1), x0 = min((int)sx, p.W3 - 1);
+    const int y1 = min(y0 + 1, p.H3 - 1), x1 = min(x0 + 1, p.W3 - 1);
+    const float ly = sy - (float)y0, lx = sx - (float)x0;
+    const float* mb = p.m3 + (long long)b * p.H3 * p.W3 * p.m3_stride + g * 8;
+    float a00[8], a01[8], a10[8], a11[8], xv[8], cf[8], o[8];
+    load8(mb + ((long long)y0 * p.W3 + x0) * p.m3_stride, a00);
+    load8(mb + ((long long)y0 * p.W3 + x1) * p.m3_stride, a01);
+    load8(mb + ((long long)y1 * p.W3 + x0) * p.m3_stride, a10);
+    load8(mb + ((long long)y1 * p.W3 + x1) * p.m3_stride, a11);
+    load8(reinterpret_cast<const T*>(p.x) + pix * p.x_stride + p.x_coff + g * 8, xv);
+    load8(reinterpret_cast<const T*>(p.cf) + pix * p.cf_stride + p.cf_coff + g * 8, cf);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float top = a00[j] * (1.f - lx) + a01[j] * lx;
+      const float bot = a10[j] * (1.f - lx) + a11[j] * lx;
+      const float z = top * (1.f - ly) + bot * ly + cf[j];
+      o[j] = __fdividef(xv[j], 1.f + __expf(-z));
+    }
+    store8(reinterpret_cast<T*>(p.out) + pix * p.out_stride + p.out_coff + g * 8, o);
+  }
 }
 
 }  // namespace esr
