@@ -67,6 +67,15 @@ int esr_forward(esr_handle* h, const void* in_nchw, void* out_nchw, int B, int H
  * caller binds; bench.py times it as the end-to-end number. */
 int esr_forward_host(esr_handle* h, const void* in_host, void* out_host, int B, int H, int W, int dtype);
 
+/* Pipelined form of the same path for serving loops (run() of the reference, test_demo.py:416-434, one
+ * image after another): returns once the request is queued on the engine's streams; up to 3 requests are
+ * in flight, so the H2D copy, the forward and the D2H copy of consecutive requests overlap.  Host buffers
+ * should be pinned.  *ticket identifies the request; esr_host_wait(h, ticket) blocks until its output (and
+ * every earlier one) is in out_host; ticket < 0 waits for all. */
+int esr_forward_host_async(esr_handle* h, const void* in_host, void* out_host, int B, int H, int W, int dtype,
+                           long long* ticket);
+int esr_host_wait(esr_handle* h, long long ticket);
+
 /* Number of kernels one esr_forward of this shape launches (0 on error); used by bench.py. */
 int esr_launch_count(esr_handle* h, int B, int H, int W, int dtype);
 /* Name of the i-th launch of that plan ("conv_tc", "conv_generic", ...), or NULL. */
@@ -76,7 +85,8 @@ const char* esr_launch_name(esr_handle* h, int B, int H, int W, int dtype, int i
 double esr_launch_flops(esr_handle* h, int B, int H, int W, int dtype, int i);
 
 /* Measurement aid for bench.py's roofline: runs the plan of one forward launch by launch, each launch
- * repeated `reps` times between two CUDA events on `stream`, and writes the mean milliseconds of
+ * repeated `reps` times (captured into a CUDA graph, so the CPU launch rate does not mask short kernels)
+ * between two CUDA events on `stream`, and writes the mean milliseconds of
  * every launch to ms_out[0..n).  Returns the number of launches (>0) or a negative ESR_E_* code.
  * Same arguments as esr_forward; synchronises the stream. */
 int esr_profile_launches(esr_handle* h, const void* in_nchw, void* out_nchw, int B, int H, int W, int dtype,

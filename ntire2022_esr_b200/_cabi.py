@@ -25,6 +25,9 @@ SYMBOLS = [
     ("esr_forward", _c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
                                _c.c_void_p, _c.c_size_t, _c.c_void_p]),
     ("esr_forward_host", _c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int]),
+    ("esr_forward_host_async", _c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
+                                          _c.POINTER(_c.c_longlong)]),
+    ("esr_host_wait", _c.c_int, [_c.c_void_p, _c.c_longlong]),
     ("esr_launch_count", _c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int]),
     ("esr_launch_name", _c.c_char_p, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int]),
     ("esr_launch_flops", _c.c_double, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int]),

@@ -36,13 +36,13 @@ constexpr int TC_PREFETCH_ROWS = 6;  // L2 prefetch distance of the producer, in
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 
+// One MMA group = one (tap, K-chunk, column segment), pre-digested on the host so that the issuing thread
+// spends a handful of instructions per tcgen05.mma (the issue loop, not the tensor pipe, was the limiter).
 struct __align__(16) TcEntry {
-  uint32_t a_off;   // chunk * chunk_bytes + px_off * 128 (bytes inside a ring slot)
-  uint32_t b_off;   // byte offset of the [n x 64] pre-swizzled weight block inside the blob
+  uint32_t a_row;   // bits 0-27: (chunk * chunk_bytes + px_off * 128) >> 4, bits 28-31: strip of the row window
+  uint32_t b_off16; // (byte offset of the [n x 64] pre-swizzled weight block inside the blob) >> 4
   uint32_t idesc;   // instruction descriptor (M = 128, N = n)
-  uint16_t dcol;    // first accumulator column
-  uint8_t row;      // strip of the tile's row window (0 .. 2*halo)
-  uint8_t steps_first;  // bits 0-3: K=16 steps issued, bit 7: first MMA overwrites the accumulator
+  uint32_t misc;    // bits 0-15: first accumulator column, 16-19: K=16 steps, bit 31: first MMA overwrites
 };
 
 struct TcOutGroup {
@@ -360,18 +360,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc_fence_after_sync();
           const uint32_t d_base = tmem_base + aslot * acc_cols;
           const int ne = (dbg_flags & 1) ? 0 : n_entries;
+          // descriptor low words of the (up to three) strips of this tile's row window
+          uint32_t s1 = tslot + 1, s2 = tslot + 2;
+          if (s1 >= (uint32_t)S) s1 -= S;
+          if (s2 >= (uint32_t)S) s2 -= S;
+          const uint32_t rb0 = 0x10000u | ((ring_base + tslot * strip_bytes) >> 4);
+          const uint32_t rb1 = 0x10000u | ((ring_base + s1 * strip_bytes) >> 4);
+          const uint32_t rb2 = 0x10000u | ((ring_base + s2 * strip_bytes) >> 4);
+          uint4 en = *reinterpret_cast<const uint4*>(&ent_s[0]);
           for (int ei = 0; ei < ne; ++ei) {
-            const TcEntry e = ent_s[ei];
-            uint32_t sl = tslot + e.row;
-            if (sl >= (uint32_t)S) sl -= S;
-            const uint32_t a_lo = 0x10000u | ((ring_base + sl * strip_bytes + e.a_off) >> 4);
-            const uint32_t b_lo = w_lo + (e.b_off >> 4);
-            const uint32_t steps = e.steps_first & 15u;
-            const uint32_t d = d_base + e.dcol;
-            umma_f16_ss_nc(d, a_lo, b_lo, e.idesc, (e.steps_first & 0x80u) ? 0u : 1u);
-            if (steps > 1) umma_f16_ss_nc(d, a_lo + 2, b_lo + 2, e.idesc, 1u);
-            if (steps > 2) umma_f16_ss_nc(d, a_lo + 4, b_lo + 4, e.idesc, 1u);
-            if (steps > 3) umma_f16_ss_nc(d, a_lo + 6, b_lo + 6, e.idesc, 1u);
+            const uint4 e = en;
+            if (ei + 1 < ne) en = *reinterpret_cast<const uint4*>(&ent_s[ei + 1]);   // next entry in flight
+            const uint32_t row = e.x >> 28;
+            const uint32_t a_lo = (row == 0 ? rb0 : (row == 1 ? rb1 : rb2)) + (e.x & 0x0fffffffu);
+            const uint32_t b_lo = w_lo + e.y;
+            const uint32_t steps = (e.w >> 16) & 15u;
+            const uint32_t d = d_base + (e.w & 0xffffu);
+            umma_f16_ss_nc(d, a_lo, b_lo, e.z, (e.w >> 31) ? 0u : 1u);
+            if (steps > 1) umma_f16_ss_nc(d, a_lo + 2, b_lo + 2, e.z, 1u);
+            if (steps > 2) umma_f16_ss_nc(d, a_lo + 4, b_lo + 4, e.z, 1u);
+            if (steps > 3) umma_f16_ss_nc(d, a_lo + 6, b_lo + 6, e.z, 1u);
           }
           umma_commit(&tfull_bar[aslot]);
           TC_STAMP(2, 2 * t + 1);

@@ -39,7 +39,7 @@ struct BufDecl {
 };
 enum { BUF_IN = -1, BUF_OUT = -2, BUF_NONE = -3 };
 
-enum OpKind { OP_HEAD = 0, OP_BSRN_HEAD, OP_CONV, OP_DW, OP_POOL, OP_ESA_APPLY, OP_CONV_TC, OP_ESA_APPLY2 };
+enum OpKind { OP_HEAD = 0, OP_BSRN_HEAD, OP_CONV, OP_DW, OP_POOL, OP_ESA_APPLY, OP_CONV_TC, OP_ESA_APPLY2, OP_ESA_FRONT, OP_ESA_CHAIN };
 
 // ---- tcgen05 convolution, shape independent part ------------------------------------------------
 struct TcPlaneEntry {   // one [n x 64] B block = one (tap, chunk, column segment)
@@ -80,6 +80,7 @@ struct OpDecl {
   // ESA apply
   int c1 = BUF_NONE, c1_coff = 0, c3 = BUF_NONE, f = 0, cgroups = 0, cf_ready = 0;
   int tc = -1;  // OP_CONV_TC: index into Graph::tc
+  int tab3 = -1, npre = 0;  // OP_ESA_CHAIN: tab/tab2 = the 16->16 layers, tab3 = last layer (16->64)
   double macs_pp = 0;  // algorithmic (unpadded) multiply-accumulates per output pixel
   int macs_res = BK_FULL;  // spatial class the MAC count applies to
 };

@@ -59,10 +59,19 @@ struct Engine {
   int opt_tc = 1, opt_shift_mode = 0, opt_use_graph = 1, opt_rows_per_item = 0, opt_timeline = 0, opt_dbg_flags = 0, opt_acc_slots = 4, opt_pdl = 1;
   long long* d_timeline = nullptr;  // 128 stamps per tcgen05 launch (debug option tc_timeline)
   std::list<Plan> plans;
-  // host-buffer path
-  void* h_in = nullptr; void* h_out = nullptr; void* h_ws = nullptr;
-  size_t h_in_sz = 0, h_out_sz = 0, h_ws_sz = 0;
-  cudaStream_t h_stream = nullptr;
+  // host-buffer path: kHostSlots requests in flight (H2D, forward and D2H of consecutive requests overlap)
+  static const int kHostSlots = 3;
+  struct HostSlot {
+    void* d_in = nullptr; void* d_out = nullptr;
+    size_t in_sz = 0, out_sz = 0;
+    cudaEvent_t ev_in = nullptr, ev_fwd = nullptr, ev_done = nullptr;
+    bool busy = false;
+    long long ticket = -1;
+  } hslot[kHostSlots];
+  void* h_ws = nullptr;
+  size_t h_ws_sz = 0;
+  cudaStream_t s_h2d = nullptr, s_cmp = nullptr, s_d2h = nullptr;
+  long long next_ticket = 0;
   void* ws_zeroed = nullptr; size_t ws_zeroed_sz = 0;
   PFN_encodeTiled encode = nullptr;
 };
@@ -322,12 +331,10 @@ static int plan_tc(Engine* e, const DevGraph& dg, const TcConv& c, const std::st
   for (int i = 0; i < p.n_entries; ++i) {
     const TcPlaneEntry& s = c.entries[i];
     TcEntry& d = p.e[i];
-    d.a_off = (uint32_t)(s.chunk * p.chunk_bytes + (s.dx + c.halo) * 128);
-    d.b_off = (uint32_t)s.b_off;
+    d.a_row = (uint32_t)((s.chunk * p.chunk_bytes + (s.dx + c.halo) * 128) >> 4) | ((uint32_t)(s.dy + c.halo) << 28);
+    d.b_off16 = (uint32_t)(s.b_off >> 4);
     d.idesc = umma_idesc_f16((uint32_t)s.n);
-    d.dcol = (uint16_t)s.dcol;
-    d.row = (uint8_t)(s.dy + c.halo);
-    d.steps_first = (uint8_t)((s.nsteps & 15) | (s.first ? 0x80 : 0));
+    d.misc = (uint32_t)s.dcol | ((uint32_t)(s.nsteps & 15) << 16) | (s.first ? 0x80000000u : 0u);
   }
   const int grid = std::min(p.n_items, e->num_sms);
   static size_t attr_set = 0;
@@ -495,6 +502,44 @@ static int build_plan(Engine* e, Plan& pl) {
         pl.launches.push_back(Launch{"esa_apply:" + op.name, [=](cudaStream_t s) {
           if (f16) return launch_k(k_esa_apply<__half, float>, grid, dim3(128), 0, s, p);
           return launch_k(k_esa_apply<float, double>, grid, dim3(128), 0, s, p);
+        }});
+        break;
+      }
+      case OP_ESA_FRONT: {
+        if (!f16) return fail(e, ESR_E_INVALID, "fused ESA front is fp16 only");
+        EsaFrontParams p;
+        memset(&p, 0, sizeof(p));
+        const Table& t = dg.tables[op.tab];
+        p.in = ptr(op.in); p.in_stride = g.bufs[op.in].C; p.in_coff = op.in_coff;
+        p.w = dg.d_params + t.off_w; p.bias = dg.d_params + t.off_b;
+        p.out = (float*)ptr(op.out);
+        p.B = B; p.H = H; p.W = W;
+        esa_dims(H, W, p.H2, p.W2, p.H3, p.W3);
+        const int nblk = B * ((p.H3 + 3) / 4) * ((p.W3 + 3) / 4);
+        pl.launches.push_back(Launch{"esa_conv2_pool:" + op.name, [=](cudaStream_t s) {
+          return launch_k(k_esa_conv2_pool<__half>, dim3(nblk), dim3(128), 0, s, p);
+        }});
+        break;
+      }
+      case OP_ESA_CHAIN: {
+        if (!f16) return fail(e, ESR_E_INVALID, "fused ESA chain is fp16 only");
+        EsaChainParams p;
+        memset(&p, 0, sizeof(p));
+        p.in = (const float*)ptr(op.in); p.out = (float*)ptr(op.out);
+        p.npre = op.npre;
+        if (op.npre > 0) { p.wpre0 = dg.d_params + dg.tables[op.tab].off_w; p.bpre0 = dg.d_params + dg.tables[op.tab].off_b; }
+        if (op.npre > 1) { p.wpre1 = dg.d_params + dg.tables[op.tab2].off_w; p.bpre1 = dg.d_params + dg.tables[op.tab2].off_b; }
+        p.wl = dg.d_params + dg.tables[op.tab3].off_w; p.bl = dg.d_params + dg.tables[op.tab3].off_b;
+        p.B = B; p.H3 = L.H[op.in]; p.W3 = L.W[op.in];
+        const int nblk = B * ((p.H3 + 5) / 6) * ((p.W3 + 5) / 6);
+        const size_t smem = (size_t)(9 * 16 * 64 + 2 * 9 * 256 + 144 * 16 + 100 * 16) * sizeof(float);
+        static bool attr_done = false;
+        if (!attr_done) {
+          CUDA_TRY(e, cudaFuncSetAttribute(k_esa_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          attr_done = true;
+        }
+        pl.launches.push_back(Launch{"esa_chain:" + op.name, [=](cudaStream_t s) {
+          return launch_k(k_esa_chain, dim3(nblk), dim3(256), smem, s, p);
         }});
         break;
       }
@@ -737,7 +782,20 @@ int esr_forward(esr_handle* h, const void* in_nchw, void* out_nchw, int B, int H
   return ESR_OK;
 }
 
-int esr_forward_host(esr_handle* h, const void* in_host, void* out_host, int B, int H, int W, int dtype) {
+int esr_host_wait(esr_handle* h, long long ticket) {
+  if (!h) return ESR_E_INVALID;
+  if (!h->has_gpu) return fail(h, ESR_E_NOGPU, "no sm_100 device bound to this handle (the engine has no CPU fallback)");
+  for (auto& sl : h->hslot) {
+    if (!sl.busy) continue;
+    if (ticket >= 0 && sl.ticket > ticket) continue;   // requests complete in order: wait for everything up to `ticket`
+    CUDA_TRY(h, cudaEventSynchronize(sl.ev_done));
+    sl.busy = false;
+  }
+  return ESR_OK;
+}
+
+int esr_forward_host_async(esr_handle* h, const void* in_host, void* out_host, int B, int H, int W, int dtype,
+                           long long* ticket_out) {
   if (!h) return ESR_E_INVALID;
   if (!h->finalized) return fail(h, ESR_E_STATE, "esr_forward_host before esr_finalize");
   if (!h->has_gpu) return fail(h, ESR_E_NOGPU, "no sm_100 device bound to this handle (the engine has no CPU fallback)");
@@ -747,24 +805,55 @@ int esr_forward_host(esr_handle* h, const void* in_host, void* out_host, int B, 
   CUDA_TRY(h, cudaSetDevice(h->device));
   const size_t elt = dtype == ESR_DTYPE_F16 ? 2 : 4;
   const size_t in_b = (size_t)B * 3 * H * W * elt, out_b = in_b * 16, ws_b = esr_workspace_bytes(h, B, H, W, dtype);
-  if (!h->h_stream) CUDA_TRY(h, cudaStreamCreateWithFlags(&h->h_stream, cudaStreamNonBlocking));
+  if (!h->s_cmp) {
+    CUDA_TRY(h, cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
+    CUDA_TRY(h, cudaStreamCreateWithFlags(&h->s_cmp, cudaStreamNonBlocking));
+    CUDA_TRY(h, cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
+    for (auto& sl : h->hslot) {
+      CUDA_TRY(h, cudaEventCreateWithFlags(&sl.ev_in, cudaEventDisableTiming));
+      CUDA_TRY(h, cudaEventCreateWithFlags(&sl.ev_fwd, cudaEventDisableTiming));
+      CUDA_TRY(h, cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
+    }
+  }
+  const long long ticket = h->next_ticket++;
+  esr::Engine::HostSlot& sl = h->hslot[ticket % esr::Engine::kHostSlots];
+  if (sl.busy) {   // the slot's previous request must have left the device buffers
+    CUDA_TRY(h, cudaEventSynchronize(sl.ev_done));
+    sl.busy = false;
+  }
   auto grow = [&](void*& p, size_t& have, size_t need) -> cudaError_t {
     if (have >= need) return cudaSuccess;
+    cudaError_t err = cudaDeviceSynchronize();   // nothing may still use the old buffer
+    if (err != cudaSuccess) return err;
     if (p) cudaFree(p);
     p = nullptr; have = 0;
-    cudaError_t err = cudaMalloc(&p, need);
+    err = cudaMalloc(&p, need);
     if (err == cudaSuccess) have = need;
     return err;
   };
-  CUDA_TRY(h, grow(h->h_in, h->h_in_sz, in_b));
-  CUDA_TRY(h, grow(h->h_out, h->h_out_sz, out_b));
+  CUDA_TRY(h, grow(sl.d_in, sl.in_sz, in_b));
+  CUDA_TRY(h, grow(sl.d_out, sl.out_sz, out_b));
   CUDA_TRY(h, grow(h->h_ws, h->h_ws_sz, ws_b));
-  CUDA_TRY(h, cudaMemcpyAsync(h->h_in, in_host, in_b, cudaMemcpyHostToDevice, h->h_stream));
-  rc = esr_forward(h, h->h_in, h->h_out, B, H, W, dtype, h->h_ws, h->h_ws_sz, h->h_stream);
+  CUDA_TRY(h, cudaMemcpyAsync(sl.d_in, in_host, in_b, cudaMemcpyHostToDevice, h->s_h2d));
+  CUDA_TRY(h, cudaEventRecord(sl.ev_in, h->s_h2d));
+  CUDA_TRY(h, cudaStreamWaitEvent(h->s_cmp, sl.ev_in, 0));
+  rc = esr_forward(h, sl.d_in, sl.d_out, B, H, W, dtype, h->h_ws, h->h_ws_sz, h->s_cmp);
   if (rc) return rc;
-  CUDA_TRY(h, cudaMemcpyAsync(out_host, h->h_out, out_b, cudaMemcpyDeviceToHost, h->h_stream));
-  CUDA_TRY(h, cudaStreamSynchronize(h->h_stream));
+  CUDA_TRY(h, cudaEventRecord(sl.ev_fwd, h->s_cmp));
+  CUDA_TRY(h, cudaStreamWaitEvent(h->s_d2h, sl.ev_fwd, 0));
+  CUDA_TRY(h, cudaMemcpyAsync(out_host, sl.d_out, out_b, cudaMemcpyDeviceToHost, h->s_d2h));
+  CUDA_TRY(h, cudaEventRecord(sl.ev_done, h->s_d2h));
+  sl.busy = true;
+  sl.ticket = ticket;
+  if (ticket_out) *ticket_out = ticket;
   return ESR_OK;
+}
+
+int esr_forward_host(esr_handle* h, const void* in_host, void* out_host, int B, int H, int W, int dtype) {
+  long long ticket = -1;
+  int rc = esr_forward_host_async(h, in_host, out_host, B, H, W, dtype, &ticket);
+  if (rc) return rc;
+  return esr_host_wait(h, ticket);
 }
 
 static Plan* dry_plan(esr_handle* h, int B, int H, int W, int dtype, Plan& tmp) {
@@ -775,7 +864,8 @@ static Plan* dry_plan(esr_handle* h, int B, int H, int W, int dtype, Plan& tmp) 
   // names only: one launch per op
   tmp.launches.clear();
   for (auto& op : h->graphs[gid].g.ops) {
-    static const char* kn[] = {"head", "bsrn_head", "conv_generic", "dwconv", "maxpool", "esa_apply", "conv_tc", "esa_apply2"};
+    static const char* kn[] = {"head", "bsrn_head", "conv_generic", "dwconv", "maxpool", "esa_apply", "conv_tc", "esa_apply2",
+                               "esa_conv2_pool", "esa_chain"};
     std::string kname = kn[op.kind];
     if (op.kind == OP_CONV && !op.ps && h->graphs[gid].tables[op.tab].cin8 == 16 && h->graphs[gid].tables[op.tab].cout16 == 16)
       kname = "conv16";
@@ -823,24 +913,39 @@ int esr_profile_launches(esr_handle* h, const void* in_nchw, void* out_nchw, int
   cudaEvent_t e0, e1;
   CUDA_TRY(h, cudaEventCreate(&e0));
   CUDA_TRY(h, cudaEventCreate(&e1));
+  cudaStream_t cs;
+  CUDA_TRY(h, cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+  int rc_out = (int)pl->launches.size();
   for (size_t i = 0; i < pl->launches.size(); ++i) {
-    // every launch is idempotent (no op writes a buffer it reads), so repeating it in place is safe
-    cudaError_t err = pl->launches[i].fn(s);  // warm
-    cudaEventRecord(e0, s);
-    for (int r = 0; r < reps && err == cudaSuccess; ++r) err = pl->launches[i].fn(s);
-    cudaEventRecord(e1, s);
+    // every launch is idempotent (no op writes a buffer it reads), so repeating it in place is safe.  The
+    // repeats are captured into a CUDA graph so that the CPU launch rate (~10 us per cudaLaunchKernelEx with
+    // tensor-map arguments) does not hide the GPU time of short kernels.
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    cudaError_t err = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+    for (int r = 0; r < reps && err == cudaSuccess; ++r) err = pl->launches[i].fn(cs);
+    cudaError_t err2 = cudaStreamEndCapture(cs, &graph);
+    if (err == cudaSuccess) err = err2;
+    if (err == cudaSuccess) err = cudaGraphInstantiate(&gexec, graph, 0);
+    if (err == cudaSuccess) err = cudaGraphLaunch(gexec, s);   // warm
+    if (err == cudaSuccess) err = cudaEventRecord(e0, s);
+    if (err == cudaSuccess) err = cudaGraphLaunch(gexec, s);
+    if (err == cudaSuccess) err = cudaEventRecord(e1, s);
     if (err == cudaSuccess) err = cudaEventSynchronize(e1);
+    if (gexec) cudaGraphExecDestroy(gexec);
+    if (graph) cudaGraphDestroy(graph);
     if (err != cudaSuccess) {
-      cudaEventDestroy(e0); cudaEventDestroy(e1);
-      return fail(h, ESR_E_CUDA, pl->launches[i].name + ": " + cudaGetErrorString(err));
+      rc_out = fail(h, ESR_E_CUDA, pl->launches[i].name + ": " + cudaGetErrorString(err));
+      break;
     }
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
     ms_out[i] = ms / reps;
   }
+  cudaStreamDestroy(cs);
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
-  return (int)pl->launches.size();
+  return rc_out;
 }
 
 int esr_set_option(esr_handle* h, const char* key, int value) {
@@ -879,10 +984,18 @@ void esr_destroy(esr_handle* h) {
       if (dg.d_params) cudaFree(dg.d_params);
       if (dg.d_blobs) cudaFree(dg.d_blobs);
     }
-    if (h->h_in) cudaFree(h->h_in);
-    if (h->h_out) cudaFree(h->h_out);
+    cudaDeviceSynchronize();
+    for (auto& sl : h->hslot) {
+      if (sl.d_in) cudaFree(sl.d_in);
+      if (sl.d_out) cudaFree(sl.d_out);
+      if (sl.ev_in) cudaEventDestroy(sl.ev_in);
+      if (sl.ev_fwd) cudaEventDestroy(sl.ev_fwd);
+      if (sl.ev_done) cudaEventDestroy(sl.ev_done);
+    }
     if (h->h_ws) cudaFree(h->h_ws);
-    if (h->h_stream) cudaStreamDestroy(h->h_stream);
+    if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
+    if (h->s_cmp) cudaStreamDestroy(h->s_cmp);
+    if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
     if (h->d_timeline) cudaFree(h->d_timeline);
   }
   delete h;

@@ -429,31 +429,42 @@ struct GraphBuilder {
   // interpolation, M3 = (conv4 o last 3x3)(pooled map) at low resolution, cf' arrives from the c5 GEMM.
   void esa_tail_commuted(const std::string& p, int arch, const EsaBufs& eb, int m3buf, int f, int nf, int x, int x_coff,
                          int cfp, int dst, int dst_coff, int cg8, const Mat& conv4) {
-    {
+    {   // conv2 (3x3 stride 2) + max_pool2d(7,3) in one launch
       const Mat m = conv_mat(p + "conv2", f, f, 3);
-      conv_op(p + "conv2", dense_table(m, 16, 16, pos_id(), pos_id()), eb.esa, 0, eb.s2, 0, ACT_NONE, 0.f, 2, 0);
+      OpDecl op;
+      op.kind = OP_ESA_FRONT;
+      op.name = p + "conv2+max_pool";
+      op.tab = dense_table(m, 16, 16, pos_id(), pos_id());
+      op.in = eb.esa; op.in_coff = 0; op.out = eb.s3a;
+      op.macs_pp = take_macs();
+      op.macs_res = BK_S2;
+      g.ops.push_back(op);
     }
-    OpDecl pool;
-    pool.kind = OP_POOL;
-    pool.name = p + "max_pool";
-    pool.in = eb.s2; pool.out = eb.s3a;
-    g.ops.push_back(pool);
     Mat c4nb = conv4;
     std::fill(c4nb.b.begin(), c4nb.b.end(), 0.0);   // b4 travels with cf'
-    int last_in = eb.s3a;
+    OpDecl ch;
+    ch.kind = OP_ESA_CHAIN;
+    ch.in = eb.s3a; ch.out = m3buf;
+    ch.macs_res = BK_S3;
     std::string last_name = "conv3";
+    double macs = 0;
     if (arch == ESR_ARCH_RFDN) {
       const Mat m1 = conv_mat(p + "conv_max", f, f, 3), m2 = conv_mat(p + "conv3", f, f, 3);
-      conv_op(p + "conv_max", dense_table(m1, 16, 16, pos_id(), pos_id()), eb.s3a, 0, eb.s3b, 0, ACT_RELU);
-      conv_op(p + "conv3", dense_table(m2, 16, 16, pos_id(), pos_id()), eb.s3b, 0, eb.s3a, 0, ACT_RELU);
-      last_in = eb.s3a;
+      ch.tab = dense_table(m1, 16, 16, pos_id(), pos_id());
+      ch.tab2 = dense_table(m2, 16, 16, pos_id(), pos_id());
+      ch.npre = 2;
+      macs += take_macs();
       last_name = "conv3_";
+      ch.name = p + "conv_max+conv3+conv3_+conv4";
+    } else {
+      ch.name = p + "conv3+conv4";
     }
     const Mat ml = conv_mat(p + last_name, f, f, 3);
     const Mat comp = compose(c4nb, ml);   // 3x3 f -> nf
-    const int ti = dense_table(comp, 16, 64, pos_id(), pos_id());
-    pend_macs = (double)f * f * 9;        // algorithmic count: the reference's 3x3 f->f (conv4 is counted with cf')
-    conv_op(p + last_name + "+conv4", ti, last_in, 0, m3buf, 0, ACT_NONE);
+    ch.tab3 = dense_table(comp, 16, 64, pos_id(), pos_id());
+    take_macs();
+    ch.macs_pp = macs + (double)f * f * 9;   // algorithmic count: the reference's 3x3 f->f layers (conv4 is counted with cf')
+    g.ops.push_back(ch);
     OpDecl ap;
     ap.kind = OP_ESA_APPLY2;
     ap.name = p + "apply";

@@ -660,4 +660,258 @@ __global__ void __launch_bounds__(256) k_esa_apply2(const EsaApply2Params p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused ESA front (fp16 path): conv2 (3x3, stride 2, pad 0, f->f) + max_pool2d(7, 3) in one kernel.
+// block = 4x4 pooled outputs = a 16x16 tile of conv2 outputs kept in shared memory; 128 threads, each
+// 4 horizontally adjacent conv2 pixels x 8 channels (register tile: every broadcast LDS.128 of weights
+// feeds 16 FMAs).  Tiles overlap by 4 conv2 pixels (recompute 1.78x on a 37 MMAC layer) - the price
+// for never writing / re-reading the 127x127 map and for one launch instead of two.
+//   in : NHWC T (c1_), 16 channels used;  w: [9][16][16] fp32 (tap, cin, cout), bias[16]
+//   out: pooled map NHWC fp32, 16 channels
+// ---------------------------------------------------------------------------------------------
+struct EsaFrontParams {
+  const void* in; int in_stride, in_coff;
+  const float* w; const float* bias;
+  float* out;
+  int B, H, W, H2, W2, H3, W3;
+};
+template <typename T>
+__global__ void __launch_bounds__(128) k_esa_conv2_pool(const EsaFrontParams p) {
+  __shared__ __align__(16) float wsm[9 * 256];
+  __shared__ __align__(16) float tile[16][16][16];   // conv2 outputs [y][x][c]
+  {
+    const float4* src = reinterpret_cast<const float4*>(p.w);
+    float4* dst = reinterpret_cast<float4*>(wsm);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const int j = threadIdx.x + i * 128;
+      if (j < 9 * 64) dst[j] = __ldg(src + j);
+    }
+  }
+  pdl_wait();
+  __syncthreads();
+  const int tx3 = (p.W3 + 3) >> 2, ty3 = (p.H3 + 3) >> 2;
+  const int bx = blockIdx.x % tx3, by = (blockIdx.x / tx3) % ty3, b = blockIdx.x / (tx3 * ty3);
+  const int cy0 = by * 12, cx0 = bx * 12;   // conv2 origin of this tile (pooled origin * 3)
+  {
+    const int g8 = threadIdx.x & 1, quad = (threadIdx.x >> 1) & 3, ty = threadIdx.x >> 3;
+    const int cy = cy0 + ty, cx = cx0 + quad * 4;
+    float acc[4][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float bv = __ldg(p.bias + g8 * 8 + j);
+      acc[0][j] = bv; acc[1][j] = bv; acc[2][j] = bv; acc[3][j] = bv;
+    }
+    const T* in = reinterpret_cast<const T*>(p.in);
+    if (cy < p.H2) {
+#pragma unroll 1
+      for (int ky = 0; ky < 3; ++ky) {
+        const T* row = in + ((long long)b * p.H + 2 * cy + ky) * p.W * p.in_stride + p.in_coff;
+#pragma unroll 1
+        for (int kx = 0; kx < 3; ++kx) {
+          float xv[4][16];
+#pragma unroll
+          for (int px = 0; px < 4; ++px) {
+            const int ix = 2 * (cx + px) + kx;
+            if (cx + px < p.W2) {
+              float a[8], c[8];
+              load8(row + (long long)ix * p.in_stride, a);
+              load8(row + (long long)ix * p.in_stride + 8, c);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { xv[px][j] = a[j]; xv[px][8 + j] = c[j]; }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) xv[px][j] = 0.f;
+            }
+          }
+          const float* wt = wsm + (ky * 3 + kx) * 256 + g8 * 8;
+#pragma unroll
+          for (int ci = 0; ci < 16; ++ci) {
+            const float4 w0 = *reinterpret_cast<const float4*>(wt + ci * 16);
+            const float4 w1 = *reinterpret_cast<const float4*>(wt + ci * 16 + 4);
+            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+            for (int px = 0; px < 4; ++px)
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc[px][j] = fmaf(xv[px][ci], wv[j], acc[px][j]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int px = 0; px < 4; ++px) {
+      // positions outside the conv2 map never win a max
+      const bool ok = cy < p.H2 && cx + px < p.W2;
+      float4* d = reinterpret_cast<float4*>(&tile[ty][quad * 4 + px][g8 * 8]);
+      d[0] = ok ? make_float4(acc[px][0], acc[px][1], acc[px][2], acc[px][3]) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      d[1] = ok ? make_float4(acc[px][4], acc[px][5], acc[px][6], acc[px][7]) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    }
+  }
+  __syncthreads();
+  // 4x4 pooled outputs x 16 channels = 256 values, 2 per thread
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int o = threadIdx.x + it * 128;
+    const int c = o & 15, pxl = (o >> 4) & 3, pyl = o >> 6;
+    const int py = by * 4 + pyl, pxg = bx * 4 + pxl;
+    if (py < p.H3 && pxg < p.W3) {
+      float m = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 7; ++i)
+#pragma unroll
+        for (int j = 0; j < 7; ++j) m = fmaxf(m, tile[3 * pyl + i][3 * pxl + j][c]);
+      p.out[(((long long)b * p.H3 + py) * p.W3 + pxg) * 16 + c] = m;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused ESA low-resolution chain (fp16 path) on the pooled map: [conv_max + ReLU, conv3 + ReLU] (RFDN;
+// none for RLFN) followed by the last 3x3 composed with conv4 (f -> nf, no activation) - one launch,
+// intermediates in shared memory.  block = 6x6 outputs; halo = number of 3x3 layers.
+//   in : pooled map NHWC fp32 16 ch;  wpre: npre x [9][16][16], bpre: npre x [16];  wl: [9][16][64], bl[64]
+//   out: M3 NHWC fp32 64 ch.   Zero padding applies to every layer's input: intermediate values at positions
+//   outside the map are forced to 0.
+// ---------------------------------------------------------------------------------------------
+struct EsaChainParams {
+  const float* in; float* out;
+  const float* wpre0; const float* bpre0; const float* wpre1; const float* bpre1; const float* wl; const float* bl;
+  int npre, B, H3, W3;
+};
+__global__ void __launch_bounds__(256) k_esa_chain(const EsaChainParams p) {
+  extern __shared__ __align__(16) float sm[];
+  const int npre = p.npre;
+  const int halo = npre + 1;
+  const int T0 = 6 + 2 * halo;                 // input tile extent
+  float* wl = sm;                              // [9][16][64]
+  float* wpre = wl + 9 * 16 * 64;              // npre x [9][16][16]
+  float* buf0 = wpre + 2 * 9 * 256;            // [16][12*12]  (channel-major: conflict-free window reads)
+  float* buf1 = buf0 + 12 * 12 * 16;           // [16][10*10]
+  {
+    const float4* s1 = reinterpret_cast<const float4*>(p.wl);
+    float4* d1 = reinterpret_cast<float4*>(wl);
+    for (int i = threadIdx.x; i < 9 * 16 * 16; i += 256) d1[i] = __ldg(s1 + i);
+    float4* d2 = reinterpret_cast<float4*>(wpre);
+    if (npre > 0)
+      for (int i = threadIdx.x; i < 9 * 64; i += 256) d2[i] = __ldg(reinterpret_cast<const float4*>(p.wpre0) + i);
+    if (npre > 1)
+      for (int i = threadIdx.x; i < 9 * 64; i += 256) d2[9 * 64 + i] = __ldg(reinterpret_cast<const float4*>(p.wpre1) + i);
+  }
+  pdl_wait();
+  const int tx = (p.W3 + 5) / 6, ty = (p.H3 + 5) / 6;
+  const int bx = blockIdx.x % tx, by = (blockIdx.x / tx) % ty, b = blockIdx.x / (tx * ty);
+  const int oy0 = by * 6, ox0 = bx * 6;
+  // input tile with zero padding outside the map
+  for (int i = threadIdx.x; i < T0 * T0 * 4; i += 256) {
+    const int q = i & 3, pos = i >> 2;
+    const int yy = oy0 - halo + pos / T0, xx = ox0 - halo + pos % T0;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (yy >= 0 && yy < p.H3 && xx >= 0 && xx < p.W3)
+      v = *reinterpret_cast<const float4*>(p.in + (((long long)b * p.H3 + yy) * p.W3 + xx) * 16 + q * 4);
+    const int TP0 = T0 * T0;
+    buf0[(q * 4 + 0) * TP0 + pos] = v.x;
+    buf0[(q * 4 + 1) * TP0 + pos] = v.y;
+    buf0[(q * 4 + 2) * TP0 + pos] = v.z;
+    buf0[(q * 4 + 3) * TP0 + pos] = v.w;
+  }
+  __syncthreads();
+  float* cur = buf0;
+  float* nxt = buf1;
+  int Tin = T0;
+  // ---- the 16 -> 16 layers with ReLU: item = (2x2 outputs, 4 channels)
+  for (int l = 0; l < npre; ++l) {
+    const int Tout = Tin - 2;
+    const int q2 = Tout >> 1;                  // 2x2 blocks per row (Tout is even)
+    const float* wt = wpre + l * 9 * 256;
+    const int oy_base = oy0 - halo + (l + 1), ox_base = ox0 - halo + (l + 1);
+    for (int item = threadIdx.x; item < q2 * q2 * 4; item += 256) {
+      const int g4 = item & 3, blk = item >> 2;
+      const int y2 = (blk / q2) * 2, x2 = (blk % q2) * 2;
+      float acc[4][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float bv = __ldg((l == 0 ? p.bpre0 : p.bpre1) + g4 * 4 + j);
+        acc[0][j] = bv; acc[1][j] = bv; acc[2][j] = bv; acc[3][j] = bv;
+      }
+#pragma unroll 2
+      for (int ci = 0; ci < 16; ++ci) {
+        float win[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) win[a][c] = cur[ci * (Tin * Tin) + (y2 + a) * Tin + x2 + c];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const float4 w4 = *reinterpret_cast<const float4*>(wt + ((ky * 3 + kx) * 16 + ci) * 16 + g4 * 4);
+            const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+            for (int py = 0; py < 2; ++py)
+#pragma unroll
+              for (int px = 0; px < 2; ++px)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[py * 2 + px][j] = fmaf(win[py + ky][px + kx], wv[j], acc[py * 2 + px][j]);
+          }
+      }
+#pragma unroll
+      for (int py = 0; py < 2; ++py)
+#pragma unroll
+        for (int px = 0; px < 2; ++px) {
+          const int gy = oy_base + y2 + py, gx = ox_base + x2 + px;
+          const bool inside = gy >= 0 && gy < p.H3 && gx >= 0 && gx < p.W3;
+          const int pos = (y2 + py) * Tout + x2 + px;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) nxt[(g4 * 4 + j) * (Tout * Tout) + pos] = inside ? fmaxf(acc[py * 2 + px][j], 0.f) : 0.f;
+        }
+    }
+    __syncthreads();
+    float* t = cur; cur = nxt; nxt = t;
+    Tin = Tout;
+  }
+  // ---- last layer 16 -> 64 (composed with conv4), 6x6 outputs: item = (2x2 outputs, 4 channels)
+  {
+    for (int item = threadIdx.x; item < 9 * 16; item += 256) {
+      const int g4 = item & 15, blk = item >> 4;
+      const int y2 = (blk / 3) * 2, x2 = (blk % 3) * 2;
+      float acc[4][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float bv = __ldg(p.bl + g4 * 4 + j);
+        acc[0][j] = bv; acc[1][j] = bv; acc[2][j] = bv; acc[3][j] = bv;
+      }
+#pragma unroll 2
+      for (int ci = 0; ci < 16; ++ci) {
+        float win[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) win[a][c] = cur[ci * (Tin * Tin) + (y2 + a) * Tin + x2 + c];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const float4 w4 = *reinterpret_cast<const float4*>(wl + ((ky * 3 + kx) * 16 + ci) * 64 + g4 * 4);
+            const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+            for (int py = 0; py < 2; ++py)
+#pragma unroll
+              for (int px = 0; px < 2; ++px)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[py * 2 + px][j] = fmaf(win[py + ky][px + kx], wv[j], acc[py * 2 + px][j]);
+          }
+      }
+#pragma unroll
+      for (int py = 0; py < 2; ++py)
+#pragma unroll
+        for (int px = 0; px < 2; ++px) {
+          const int gy = oy0 + y2 + py, gx = ox0 + x2 + px;
+          if (gy < p.H3 && gx < p.W3)
+            *reinterpret_cast<float4*>(p.out + (((long long)b * p.H3 + gy) * p.W3 + gx) * 64 + g4 * 4) =
+                make_float4(acc[py * 2 + px][0], acc[py * 2 + px][1], acc[py * 2 + px][2], acc[py * 2 + px][3]);
+        }
+    }
+  }
+}
+
 }  // namespace esr

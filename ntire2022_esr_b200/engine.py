@@ -159,6 +159,15 @@ class Engine:
                                          out.ctypes.data_as(ctypes.c_void_p), B, H, W, dt))
         return out
 
+    def forward_host_async_ptr(self, in_ptr: int, out_ptr: int, B: int, H: int, W: int, dt: int) -> int:
+        """Queue one request on pinned host buffers; returns its ticket (see esr_forward_host_async)."""
+        t = ctypes.c_longlong(-1)
+        self._check(lib.esr_forward_host_async(self._h, in_ptr, out_ptr, B, H, W, dt, ctypes.byref(t)))
+        return t.value
+
+    def host_wait(self, ticket: int = -1):
+        self._check(lib.esr_host_wait(self._h, ticket))
+
     def forward_host_ptr(self, in_ptr: int, out_ptr: int, B: int, H: int, W: int, dt: int):
         """Raw-pointer variant (pinned torch tensors): no numpy wrapping on the timed path."""
         self._check(lib.esr_forward_host(self._h, in_ptr, out_ptr, B, H, W, dt))
