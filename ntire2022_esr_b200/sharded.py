@@ -66,3 +66,20 @@ def forward_sharded(model: Callable[[torch.Tensor], torch.Tensor], images: Optio
     if e > s:
         dist.send(y.contiguous(), dst=root, group=group)
     return None
+
+
+def forward_bucketed(model: Callable[[torch.Tensor], torch.Tensor], images: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+    """Mixed-size batch (BASELINE.json configs[2]: DIV2K-shaped LR images): images of equal (H, W) are stacked
+    and run as one batch, results come back in the original order.  No padding - padding an image changes
+    its output (zero-padded convolutions, ESA pooling), so shapes are never mixed inside a launch."""
+    buckets = {}
+    for i, im in enumerate(images):
+        if im.dim() != 3:
+            raise ValueError("forward_bucketed expects (3, H, W) tensors")
+        buckets.setdefault((im.shape[1], im.shape[2], im.dtype, im.device), []).append(i)
+    out: List[Optional[torch.Tensor]] = [None] * len(images)
+    for idxs in buckets.values():
+        y = model(torch.stack([images[i] for i in idxs]))
+        for k, i in enumerate(idxs):
+            out[i] = y[k]
+    return out  # type: ignore[return-value]

@@ -65,3 +65,21 @@ def test_shard_bounds():
     for n, w in [(128, 8), (7, 3), (0, 2)]:
         b = shard_bounds(n, w)
         assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+
+
+def test_forward_bucketed_groups_equal_shapes_and_keeps_order():
+    from ntire2022_esr_b200.sharded import forward_bucketed
+
+    calls = []
+
+    def model(x):
+        calls.append(tuple(x.shape))
+        return _stand_in(x)
+
+    g = torch.Generator().manual_seed(5)
+    shapes = [(9, 7), (6, 8), (9, 7), (5, 5), (6, 8), (9, 7)]
+    imgs = [torch.rand(3, h, w, generator=g) for h, w in shapes]
+    outs = forward_bucketed(model, imgs)
+    assert sorted(calls) == sorted([(3, 3, 9, 7), (2, 3, 6, 8), (1, 3, 5, 5)])
+    for im, o in zip(imgs, outs):
+        torch.testing.assert_close(o, _stand_in(im[None])[0])
