@@ -84,6 +84,7 @@ struct TcParams {
   int32_t w_off, w_bytes, ring_off;
   int32_t ps_fp32;
   int32_t dbg_flags;     // experiments: 1 = issue no MMA, 2 = epilogue does no work
+  int32_t pdl;           // launched with programmatic stream serialization
   int32_t chunk_c0[4];   // channel coordinate of each chunk in the A tensor
   const uint8_t* wblob;
   void* ps_out;
@@ -295,11 +296,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int i = 0; i < 4; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], TC_EPI_WARPS); }
       mbar_init(&w_bar, 1);
       fence_mbar_init();
-      // weights never depend on the previous kernel: fetch them before the grid dependency is resolved
-      mbar_arrive_expect_tx(&w_bar, (uint32_t)p.w_bytes);
-      bulk_load_1d(smem + p.w_off, p.wblob, (uint32_t)p.w_bytes, &w_bar);
-      griddep_wait();
-      produce((uint32_t)S);
+      // With programmatic dependent launch the weights (which never depend on the previous kernel) go before
+      // the grid dependency is resolved; otherwise the strips the first tile needs are requested first (the TMA
+      // queue is served in order and the 77 KB weight copy would delay them).
+      if (p.pdl) {
+        mbar_arrive_expect_tx(&w_bar, (uint32_t)p.w_bytes);
+        bulk_load_1d(smem + p.w_off, p.wblob, (uint32_t)p.w_bytes, &w_bar);
+        griddep_wait();
+        produce((uint32_t)S);
+      } else {
+        produce((uint32_t)(1 + 2 * halo));
+        mbar_arrive_expect_tx(&w_bar, (uint32_t)p.w_bytes);
+        bulk_load_1d(smem + p.w_off, p.wblob, (uint32_t)p.w_bytes, &w_bar);
+        produce((uint32_t)S);
+      }
       tma_prefetch_desc(&tmO0);
       tma_prefetch_desc(&tmO1);
       tma_prefetch_desc(&tmO2);

@@ -56,7 +56,7 @@ struct Engine {
   DevGraph graphs[2];  // 0: CUDA-core graph (fp32 mode, and fp16 when tc is off), 1: tcgen05 graph
   std::string err;
   // options
-  int opt_tc = 1, opt_shift_mode = 0, opt_use_graph = 1, opt_rows_per_item = 0, opt_timeline = 0, opt_dbg_flags = 0, opt_acc_slots = 4, opt_pdl = 1;
+  int opt_tc = 1, opt_shift_mode = 0, opt_use_graph = 1, opt_rows_per_item = 0, opt_timeline = 0, opt_dbg_flags = 0, opt_acc_slots = 4, opt_pdl = 0;
   long long* d_timeline = nullptr;  // 128 stamps per tcgen05 launch (debug option tc_timeline)
   std::list<Plan> plans;
   // host-buffer path: kHostSlots requests in flight (H2D, forward and D2H of consecutive requests overlap)
@@ -243,6 +243,7 @@ static int plan_tc(Engine* e, const DevGraph& dg, const TcConv& c, const std::st
   p.wblob = dg.d_blobs + c.off_blob;
   p.dbg = nullptr;
   p.dbg_flags = e->opt_dbg_flags;
+  p.pdl = e->opt_pdl;
   if (e->opt_timeline) {
     if (!e->d_timeline) {
       CUDA_TRY(e, cudaMalloc(&e->d_timeline, 256 * 128 * sizeof(long long)));

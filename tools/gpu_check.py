@@ -34,7 +34,7 @@ def main():
     ap.add_argument("--dbg", type=int, default=0)
     ap.add_argument("--slots", type=int, default=4)
     ap.add_argument("--nocheck", type=int, default=0)
-    ap.add_argument("--pdl", type=int, default=1)
+    ap.add_argument("--pdl", type=int, default=0)
     a = ap.parse_args()
     import torch
     from ntire2022_esr_b200 import Engine
