@@ -34,7 +34,8 @@ constexpr int TC_MAX_CHUNKS = 10;
 constexpr int TC_MAX_UNITS = 5;
 constexpr int TC_PREFETCH_ROWS = 6;  // L2 prefetch distance of the producer, in image rows     // 16-column units per epilogue warp set = ceil(TC_MAX_CHUNKS / 2)
 constexpr int TC_EPI_WARPS = 8;
-constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int TC_THREADS = 96 + 32 * TC_EPI_WARPS;  // warp 0 TMA, warp 1 + warp 10 MMA issuers, warps 2..9 epilogue
+constexpr int TC_DONE_BARS = 8;
 
 // One MMA group = one (tap, K-chunk, column segment), pre-digested on the host so that the issuing thread
 // spends a handful of instructions per tcgen05.mma (the issue loop, not the tensor pipe, was the limiter).
@@ -218,7 +219,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ CUtensorMap tmO2,
                const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t full_bar[TC_MAX_SLOTS], empty_bar[TC_MAX_SLOTS], tfull_bar[4], tempty_bar[4], w_bar;
+  __shared__ uint64_t full_bar[TC_MAX_SLOTS], tdone_bar[TC_DONE_BARS], tfull_bar[4], tempty_bar[4], w_bar;
+  __shared__ int need_a_s[TC_MAX_SLOTS], need_b_s[TC_MAX_SLOTS];   // producer-private: last reader tiles of the strip in each slot
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float bias_s[TC_MAX_GROUPS][64];
   __shared__ __align__(16) TcEntry ent_s[TC_MAX_ENTRIES];
@@ -257,19 +259,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // fill overlaps the rest of the CTA set-up (TMEM allocation, bias / entry tables)
   const uint32_t strip_tx = (uint32_t)(nchunks * p.strip_px * 128);
   const int cc0 = p.chunk_c0[0], cc1 = p.chunk_c0[1], cc2 = p.chunk_c0[2], cc3 = p.chunk_c0[3];
-  uint32_t pr_slot = 0, pr_par = 0, pr_seq = 0;
-  int pr_item = blockIdx.x, pr_row = 0, pr_b = 0, pr_y1 = 0, pr_x0 = 0;
+  uint32_t pr_slot = 0, pr_seq = 0;
+  int pr_item = blockIdx.x, pr_row = 0, pr_b = 0, pr_y0 = 0, pr_y1 = 0, pr_x0 = 0, pr_tile_base = 0;
   bool pr_open = false;
   auto produce = [&](uint32_t limit) {   // issue strips until `limit` have been issued in total
     while (pr_seq < limit) {
       if (!pr_open) {
         if (pr_item >= n_items) return;
-        int y0;
-        decode(pr_item, pr_b, y0, pr_y1, pr_x0);
-        pr_row = y0 - halo;
+        decode(pr_item, pr_b, pr_y0, pr_y1, pr_x0);
+        pr_row = pr_y0 - halo;
         pr_open = true;
       }
-      mbar_wait(&empty_bar[pr_slot], pr_par ^ 1);
+      if (pr_seq >= (uint32_t)S) {
+        // the slot still holds an older strip: every tile that reads it must have completed.  Its readers are
+        // up to 1 + 2*halo consecutive tiles, issued alternately by the two MMA warps, so the last reader of
+        // each warp is waited for (tile-done barriers, committed by the issuers after each tile).
+        const int ua = need_a_s[pr_slot], ub = need_b_s[pr_slot];
+        mbar_wait(&tdone_bar[ua & (TC_DONE_BARS - 1)], (uint32_t)(ua >> 3) & 1u);
+        if (ub >= 0) mbar_wait(&tdone_bar[ub & (TC_DONE_BARS - 1)], (uint32_t)(ub >> 3) & 1u);
+      }
+      {
+        const int nrows = pr_y1 - pr_y0, j = pr_row - (pr_y0 - halo);
+        const int last = min(j, nrows - 1), first = max(0, j - 2 * halo);
+        need_a_s[pr_slot] = pr_tile_base + last;
+        need_b_s[pr_slot] = (last - 1 >= first) ? pr_tile_base + last - 1 : -1;
+      }
       mbar_arrive_expect_tx(&full_bar[pr_slot], strip_tx);
       uint8_t* dst = smem + ring_off + pr_slot * strip_bytes;
       tma_load_4d(&tmA, &full_bar[pr_slot], dst, cc0, pr_x0 - halo, pr_row, pr_b);
@@ -284,15 +298,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       TC_STAMP(1, pr_seq);
       ++pr_seq;
-      if (++pr_slot == (uint32_t)S) { pr_slot = 0; pr_par ^= 1; }
-      if (++pr_row >= pr_y1 + halo) { pr_open = false; pr_item += gridDim.x; }
+      if (++pr_slot == (uint32_t)S) pr_slot = 0;
+      if (++pr_row >= pr_y1 + halo) { pr_open = false; pr_tile_base += pr_y1 - pr_y0; pr_item += gridDim.x; }
     }
   };
 
   if (warp == 0) {
     if (elect_one()) {
       tma_prefetch_desc(&tmA);
-      for (int i = 0; i < S; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+      for (int i = 0; i < S; ++i) mbar_init(&full_bar[i], 1);
+      for (int i = 0; i < TC_DONE_BARS; ++i) mbar_init(&tdone_bar[i], 1);
       for (int i = 0; i < 4; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], TC_EPI_WARPS); }
       mbar_init(&w_bar, 1);
       fence_mbar_init();
@@ -343,68 +358,72 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       TC_STAMP(0, 2);
     }
     __syncwarp();
-  } else if (warp == 1) {
-    // ================================ MMA issuer ==================================
+  } else if (warp == 1 || warp == 2 + TC_EPI_WARPS) {
+    // ================================ MMA issuers =================================
+    // Two issuing threads (warp 1: even tiles, warp 10: odd tiles).  One thread cannot keep the tensor pipe
+    // busy: between two tiles it spends ~0.8k cycles on barrier traffic (commits, strip / accumulator waits)
+    // while the short MMA queue drains; with two threads that bookkeeping hides behind the other one's MMAs.
     if (elect_one()) {
+      const uint32_t me = warp == 1 ? 0u : 1u;
       mbar_wait(&w_bar, 0);
-      TC_STAMP(0, 3);
+      if (me == 0) TC_STAMP(0, 3);
       const uint32_t ring_base = smem_base + ring_off;
       const uint32_t w_lo = 0x10000u | ((smem_base + p.w_off) >> 4);   // descriptor low word: LBO = 1, start >> 4
-      // strips are consumed in order: `wslot/wpar` = next strip to wait for, `rslot` = next to release,
-      // `tslot` = ring slot of the top row of the current tile's window
-      uint32_t wslot = 0, wpar = 0, waited = 0, rslot = 0, released = 0, tslot = 0, seq_base = 0, t = 0;
+      // strips are numbered q = 0, 1, ... in the order the producer issues them: slot = q % S, phase = (q / S) & 1.
+      // `tslot/tpar` follow the top strip of the current tile; `seen` = strips this thread has already waited for
+      uint32_t tslot = 0, tpar = 0, q_top = 0, seen = 0, t = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         int b, y0, y1, x0;
         decode(item, b, y0, y1, x0);
         const int nrows = y1 - y0;
         for (int r = 0; r < nrows; ++r, ++t) {
-          const uint32_t need_hi = seq_base + r + 2 * halo;
-          while (waited <= need_hi) {
-            mbar_wait(&full_bar[wslot], wpar);
-            if (++wslot == (uint32_t)S) { wslot = 0; wpar ^= 1; }
-            ++waited;
+          if ((t & 1u) == me) {
+            // wait for the strips of this tile's row window that this thread has not seen yet
+            uint32_t sl = tslot, pa = tpar;
+            for (uint32_t q = q_top; q <= q_top + 2 * halo; ++q) {
+              if (q >= seen) mbar_wait(&full_bar[sl], pa);
+              if (++sl == (uint32_t)S) { sl = 0; pa ^= 1; }
+            }
+            seen = q_top + 2 * halo + 1;
+            const uint32_t aslot = t & (NS - 1);
+            if (t < 16) TC_STAMP(2, 2 * t);
+            mbar_wait(&tempty_bar[aslot], ((t >> ns_shift) & 1) ^ 1);
+            tc_fence_after_sync();
+            const uint32_t d_base = tmem_base + aslot * acc_cols;
+            const int ne = (dbg_flags & 1) ? 0 : n_entries;
+            // descriptor low words of the (up to three) strips of this tile's row window
+            uint32_t s1 = tslot + 1, s2 = tslot + 2;
+            if (s1 >= (uint32_t)S) s1 -= S;
+            if (s2 >= (uint32_t)S) s2 -= S;
+            const uint32_t rb0 = 0x10000u | ((ring_base + tslot * strip_bytes) >> 4);
+            const uint32_t rb1 = 0x10000u | ((ring_base + s1 * strip_bytes) >> 4);
+            const uint32_t rb2 = 0x10000u | ((ring_base + s2 * strip_bytes) >> 4);
+            uint4 en = *reinterpret_cast<const uint4*>(&ent_s[0]);
+            for (int ei = 0; ei < ne; ++ei) {
+              const uint4 e = en;
+              if (ei + 1 < ne) en = *reinterpret_cast<const uint4*>(&ent_s[ei + 1]);   // next entry in flight
+              const uint32_t row = e.x >> 28;
+              const uint32_t a_lo = (row == 0 ? rb0 : (row == 1 ? rb1 : rb2)) + (e.x & 0x0fffffffu);
+              const uint32_t b_lo = w_lo + e.y;
+              const uint32_t steps = (e.w >> 16) & 15u;
+              const uint32_t d = d_base + (e.w & 0xffffu);
+              umma_f16_ss_nc(d, a_lo, b_lo, e.z, (e.w >> 31) ? 0u : 1u);
+              if (steps > 1) umma_f16_ss_nc(d, a_lo + 2, b_lo + 2, e.z, 1u);
+              if (steps > 2) umma_f16_ss_nc(d, a_lo + 4, b_lo + 4, e.z, 1u);
+              if (steps > 3) umma_f16_ss_nc(d, a_lo + 6, b_lo + 6, e.z, 1u);
+            }
+            umma_commit(&tfull_bar[aslot]);
+            umma_commit(&tdone_bar[t & (TC_DONE_BARS - 1)]);
+            if (t < 16) TC_STAMP(2, 2 * t + 1);
           }
-          const uint32_t aslot = t & (NS - 1);
-          TC_STAMP(2, 2 * t);
-          mbar_wait(&tempty_bar[aslot], ((t >> ns_shift) & 1) ^ 1);
-          tc_fence_after_sync();
-          const uint32_t d_base = tmem_base + aslot * acc_cols;
-          const int ne = (dbg_flags & 1) ? 0 : n_entries;
-          // descriptor low words of the (up to three) strips of this tile's row window
-          uint32_t s1 = tslot + 1, s2 = tslot + 2;
-          if (s1 >= (uint32_t)S) s1 -= S;
-          if (s2 >= (uint32_t)S) s2 -= S;
-          const uint32_t rb0 = 0x10000u | ((ring_base + tslot * strip_bytes) >> 4);
-          const uint32_t rb1 = 0x10000u | ((ring_base + s1 * strip_bytes) >> 4);
-          const uint32_t rb2 = 0x10000u | ((ring_base + s2 * strip_bytes) >> 4);
-          uint4 en = *reinterpret_cast<const uint4*>(&ent_s[0]);
-          for (int ei = 0; ei < ne; ++ei) {
-            const uint4 e = en;
-            if (ei + 1 < ne) en = *reinterpret_cast<const uint4*>(&ent_s[ei + 1]);   // next entry in flight
-            const uint32_t row = e.x >> 28;
-            const uint32_t a_lo = (row == 0 ? rb0 : (row == 1 ? rb1 : rb2)) + (e.x & 0x0fffffffu);
-            const uint32_t b_lo = w_lo + e.y;
-            const uint32_t steps = (e.w >> 16) & 15u;
-            const uint32_t d = d_base + (e.w & 0xffffu);
-            umma_f16_ss_nc(d, a_lo, b_lo, e.z, (e.w >> 31) ? 0u : 1u);
-            if (steps > 1) umma_f16_ss_nc(d, a_lo + 2, b_lo + 2, e.z, 1u);
-            if (steps > 2) umma_f16_ss_nc(d, a_lo + 4, b_lo + 4, e.z, 1u);
-            if (steps > 3) umma_f16_ss_nc(d, a_lo + 6, b_lo + 6, e.z, 1u);
-          }
-          umma_commit(&tfull_bar[aslot]);
-          TC_STAMP(2, 2 * t + 1);
-          const uint32_t limit = (r == nrows - 1) ? need_hi + 1 : seq_base + r + 1;
-          while (released < limit) {
-            umma_commit(&empty_bar[rslot]);
-            if (++rslot == (uint32_t)S) rslot = 0;
-            ++released;
-          }
-          if (++tslot == (uint32_t)S) tslot = 0;
+          ++q_top;
+          if (++tslot == (uint32_t)S) { tslot = 0; tpar ^= 1; }
         }
         // the next item starts 2*halo strips further down the ring
-        seq_base += nrows + 2 * halo;
-        tslot += 2 * halo;
-        if (tslot >= (uint32_t)S) tslot -= S;
+        for (int k = 0; k < 2 * halo; ++k) {
+          ++q_top;
+          if (++tslot == (uint32_t)S) { tslot = 0; tpar ^= 1; }
+        }
       }
     }
     __syncwarp();
