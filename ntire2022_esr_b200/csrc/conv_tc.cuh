@@ -506,16 +506,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc_epi_math16(v, &bias_s[gi][c0], ggelu[gi], gslope[gi], has_res, rpre[s & 1][0], rpre[s & 1][1], g.res_after, f);
           tc_epi_store16(f, gmode[gi], stage_row, c0, swz, valid, ps_out, ps_fp32, b, y, x, H, W);
         };
-        if (slot_valid(0)) slot_load(0, va);
+        // With both MMA warps keeping the tensor pipe busy a tcgen05.ld takes ~0.7k cycles to come back, so
+        // the loads of three slots are issued back to back and waited for once (two rounds cover all six)
+        uint32_t vc[16];
 #pragma unroll
-        for (int s = 0; s < 2 * TC_MAX_GROUPS; ++s) {
+        for (int s0 = 0; s0 < 2 * TC_MAX_GROUPS; s0 += 3) {
+          if (!(slot_valid(s0) || slot_valid(s0 + 1) || slot_valid(s0 + 2))) continue;
+          if (slot_valid(s0)) slot_load(s0, va);
+          if (slot_valid(s0 + 1)) slot_load(s0 + 1, vb);
+          if (slot_valid(s0 + 2)) slot_load(s0 + 2, vc);
           tmem_ld_wait();
-          if (s + 1 < 2 * TC_MAX_GROUPS && slot_valid(s + 1)) {
-            if (s & 1) slot_load(s + 1, va); else slot_load(s + 1, vb);
-          }
-          if (slot_valid(s)) {
-            if (s & 1) slot_run(s, vb); else slot_run(s, va);
-          }
+          if (slot_valid(s0)) slot_run(s0, va);
+          if (slot_valid(s0 + 1)) slot_run(s0 + 1, vb);
+          if (slot_valid(s0 + 2)) slot_run(s0 + 2, vc);
         }
         if (threadIdx.x == 64 && t < 8) TC_STAMP(1, 16 + 2 * t);
         if (threadIdx.x == 64 && t < 8) TC_STAMP(1, 17 + 2 * t);
