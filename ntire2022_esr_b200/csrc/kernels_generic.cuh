@@ -704,36 +704,49 @@ __global__ void __launch_bounds__(128) k_esa_conv2_pool(const EsaFrontParams p) 
     }
     const T* in = reinterpret_cast<const T*>(p.in);
     if (cy < p.H2) {
+      // per kernel row: the 9 input pixels (2*cx .. 2*cx+8) the 4 outputs x 3 taps touch are fetched once, raw,
+      // in one batch of 18 x 16-byte loads (3 latency rounds per thread instead of 9, 25 % fewer loads)
 #pragma unroll 1
       for (int ky = 0; ky < 3; ++ky) {
         const T* row = in + ((long long)b * p.H + 2 * cy + ky) * p.W * p.in_stride + p.in_coff;
-#pragma unroll 1
-        for (int kx = 0; kx < 3; ++kx) {
-          float xv[4][16];
+        uint4 raw[9][2];
 #pragma unroll
-          for (int px = 0; px < 4; ++px) {
-            const int ix = 2 * (cx + px) + kx;
-            if (cx + px < p.W2) {
-              float a[8], c[8];
-              load8(row + (long long)ix * p.in_stride, a);
-              load8(row + (long long)ix * p.in_stride + 8, c);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) { xv[px][j] = a[j]; xv[px][8 + j] = c[j]; }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) xv[px][j] = 0.f;
-            }
+        for (int ip = 0; ip < 9; ++ip) {
+          const int ix = 2 * cx + ip;
+          if (ix < p.W) {
+            const uint4* src = reinterpret_cast<const uint4*>(row + (long long)ix * p.in_stride);
+            raw[ip][0] = src[0];
+            raw[ip][1] = src[1];
+          } else {
+            raw[ip][0] = make_uint4(0, 0, 0, 0);
+            raw[ip][1] = make_uint4(0, 0, 0, 0);
           }
+        }
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
           const float* wt = wsm + (ky * 3 + kx) * 256 + g8 * 8;
 #pragma unroll
-          for (int ci = 0; ci < 16; ++ci) {
-            const float4 w0 = *reinterpret_cast<const float4*>(wt + ci * 16);
-            const float4 w1 = *reinterpret_cast<const float4*>(wt + ci * 16 + 4);
-            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+          for (int hh = 0; hh < 2; ++hh) {          // input channels 0-7 / 8-15
+            float xv[4][8];
 #pragma unroll
-            for (int px = 0; px < 4; ++px)
+            for (int px = 0; px < 4; ++px) {
+              const __half2* h2 = reinterpret_cast<const __half2*>(&raw[2 * px + kx][hh]);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) acc[px][j] = fmaf(xv[px][ci], wv[j], acc[px][j]);
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = __half22float2(h2[j]);
+                xv[px][2 * j] = f.x; xv[px][2 * j + 1] = f.y;
+              }
+            }
+#pragma unroll
+            for (int ci = 0; ci < 8; ++ci) {
+              const float4 w0 = *reinterpret_cast<const float4*>(wt + (hh * 8 + ci) * 16);
+              const float4 w1 = *reinterpret_cast<const float4*>(wt + (hh * 8 + ci) * 16 + 4);
+              const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+              for (int px = 0; px < 4; ++px)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[px][j] = fmaf(xv[px][ci], wv[j], acc[px][j]);
+            }
           }
         }
       }
@@ -788,14 +801,27 @@ __global__ void __launch_bounds__(256) k_esa_chain(const EsaChainParams p) {
   float* buf0 = wpre + 2 * 9 * 256;            // [16][12*12]  (channel-major: conflict-free window reads)
   float* buf1 = buf0 + 12 * 12 * 16;           // [16][10*10]
   {
+    // all weight loads of a thread are issued before the first shared-memory store (one L2 round trip, not nine)
     const float4* s1 = reinterpret_cast<const float4*>(p.wl);
     float4* d1 = reinterpret_cast<float4*>(wl);
-    for (int i = threadIdx.x; i < 9 * 16 * 16; i += 256) d1[i] = __ldg(s1 + i);
+    float4 t1[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) t1[i] = __ldg(s1 + threadIdx.x + i * 256);
+    float4 t2[3], t3[3];
     float4* d2 = reinterpret_cast<float4*>(wpre);
-    if (npre > 0)
-      for (int i = threadIdx.x; i < 9 * 64; i += 256) d2[i] = __ldg(reinterpret_cast<const float4*>(p.wpre0) + i);
-    if (npre > 1)
-      for (int i = threadIdx.x; i < 9 * 64; i += 256) d2[9 * 64 + i] = __ldg(reinterpret_cast<const float4*>(p.wpre1) + i);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int j = threadIdx.x + i * 256;
+      t2[i] = (npre > 0 && j < 9 * 64) ? __ldg(reinterpret_cast<const float4*>(p.wpre0) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      t3[i] = (npre > 1 && j < 9 * 64) ? __ldg(reinterpret_cast<const float4*>(p.wpre1) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) d1[threadIdx.x + i * 256] = t1[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int j = threadIdx.x + i * 256;
+      if (j < 9 * 64) { d2[j] = t2[i]; d2[9 * 64 + j] = t3[i]; }
+    }
   }
   pdl_wait();
   const int tx = (p.W3 + 5) / 6, ty = (p.H3 + 5) / 6;
