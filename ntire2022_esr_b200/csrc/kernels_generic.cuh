@@ -844,22 +844,23 @@ __global__ void __launch_bounds__(256) k_esa_chain(const EsaChainParams p) {
   float* cur = buf0;
   float* nxt = buf1;
   int Tin = T0;
-  // ---- the 16 -> 16 layers with ReLU: item = (2x2 outputs, 4 channels)
+  // ---- the 16 -> 16 layers with ReLU: item = (2x2 outputs, 2 channels) so that all 256 threads have work on a
+  // 10x10 / 8x8 tile (the chain is latency bound at batch 1)
   for (int l = 0; l < npre; ++l) {
     const int Tout = Tin - 2;
     const int q2 = Tout >> 1;                  // 2x2 blocks per row (Tout is even)
     const float* wt = wpre + l * 9 * 256;
     const int oy_base = oy0 - halo + (l + 1), ox_base = ox0 - halo + (l + 1);
-    for (int item = threadIdx.x; item < q2 * q2 * 4; item += 256) {
-      const int g4 = item & 3, blk = item >> 2;
+    for (int item = threadIdx.x; item < q2 * q2 * 8; item += 256) {
+      const int g2 = item & 7, blk = item >> 3;
       const int y2 = (blk / q2) * 2, x2 = (blk % q2) * 2;
-      float acc[4][4];
+      float acc[4][2];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float bv = __ldg((l == 0 ? p.bpre0 : p.bpre1) + g4 * 4 + j);
+      for (int j = 0; j < 2; ++j) {
+        const float bv = __ldg((l == 0 ? p.bpre0 : p.bpre1) + g2 * 2 + j);
         acc[0][j] = bv; acc[1][j] = bv; acc[2][j] = bv; acc[3][j] = bv;
       }
-#pragma unroll 2
+#pragma unroll 4
       for (int ci = 0; ci < 16; ++ci) {
         float win[4][4];
 #pragma unroll
@@ -870,14 +871,14 @@ __global__ void __launch_bounds__(256) k_esa_chain(const EsaChainParams p) {
         for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
           for (int kx = 0; kx < 3; ++kx) {
-            const float4 w4 = *reinterpret_cast<const float4*>(wt + ((ky * 3 + kx) * 16 + ci) * 16 + g4 * 4);
-            const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+            const float2 w2 = *reinterpret_cast<const float2*>(wt + ((ky * 3 + kx) * 16 + ci) * 16 + g2 * 2);
 #pragma unroll
             for (int py = 0; py < 2; ++py)
 #pragma unroll
-              for (int px = 0; px < 2; ++px)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[py * 2 + px][j] = fmaf(win[py + ky][px + kx], wv[j], acc[py * 2 + px][j]);
+              for (int px = 0; px < 2; ++px) {
+                acc[py * 2 + px][0] = fmaf(win[py + ky][px + kx], w2.x, acc[py * 2 + px][0]);
+                acc[py * 2 + px][1] = fmaf(win[py + ky][px + kx], w2.y, acc[py * 2 + px][1]);
+              }
           }
       }
 #pragma unroll
@@ -888,25 +889,25 @@ __global__ void __launch_bounds__(256) k_esa_chain(const EsaChainParams p) {
           const bool inside = gy >= 0 && gy < p.H3 && gx >= 0 && gx < p.W3;
           const int pos = (y2 + py) * Tout + x2 + px;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) nxt[(g4 * 4 + j) * (Tout * Tout) + pos] = inside ? fmaxf(acc[py * 2 + px][j], 0.f) : 0.f;
+          for (int j = 0; j < 2; ++j) nxt[(g2 * 2 + j) * (Tout * Tout) + pos] = inside ? fmaxf(acc[py * 2 + px][j], 0.f) : 0.f;
         }
     }
     __syncthreads();
     float* t = cur; cur = nxt; nxt = t;
     Tin = Tout;
   }
-  // ---- last layer 16 -> 64 (composed with conv4), 6x6 outputs: item = (2x2 outputs, 4 channels)
+  // ---- last layer 16 -> 64 (composed with conv4), 6x6 outputs: item = (2x2 outputs, 2 channels): 288 items
   {
-    for (int item = threadIdx.x; item < 9 * 16; item += 256) {
-      const int g4 = item & 15, blk = item >> 4;
+    for (int item = threadIdx.x; item < 9 * 32; item += 256) {
+      const int g2 = item & 31, blk = item >> 5;
       const int y2 = (blk / 3) * 2, x2 = (blk % 3) * 2;
-      float acc[4][4];
+      float acc[4][2];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float bv = __ldg(p.bl + g4 * 4 + j);
+      for (int j = 0; j < 2; ++j) {
+        const float bv = __ldg(p.bl + g2 * 2 + j);
         acc[0][j] = bv; acc[1][j] = bv; acc[2][j] = bv; acc[3][j] = bv;
       }
-#pragma unroll 2
+#pragma unroll 4
       for (int ci = 0; ci < 16; ++ci) {
         float win[4][4];
 #pragma unroll
@@ -917,14 +918,14 @@ __global__ void __launch_bounds__(256) k_esa_chain(const EsaChainParams p) {
         for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
           for (int kx = 0; kx < 3; ++kx) {
-            const float4 w4 = *reinterpret_cast<const float4*>(wl + ((ky * 3 + kx) * 16 + ci) * 64 + g4 * 4);
-            const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+            const float2 w2 = *reinterpret_cast<const float2*>(wl + ((ky * 3 + kx) * 16 + ci) * 64 + g2 * 2);
 #pragma unroll
             for (int py = 0; py < 2; ++py)
 #pragma unroll
-              for (int px = 0; px < 2; ++px)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[py * 2 + px][j] = fmaf(win[py + ky][px + kx], wv[j], acc[py * 2 + px][j]);
+              for (int px = 0; px < 2; ++px) {
+                acc[py * 2 + px][0] = fmaf(win[py + ky][px + kx], w2.x, acc[py * 2 + px][0]);
+                acc[py * 2 + px][1] = fmaf(win[py + ky][px + kx], w2.y, acc[py * 2 + px][1]);
+              }
           }
       }
 #pragma unroll
@@ -933,8 +934,8 @@ __global__ void __launch_bounds__(256) k_esa_chain(const EsaChainParams p) {
         for (int px = 0; px < 2; ++px) {
           const int gy = oy0 + y2 + py, gx = ox0 + x2 + px;
           if (gy < p.H3 && gx < p.W3)
-            *reinterpret_cast<float4*>(p.out + (((long long)b * p.H3 + gy) * p.W3 + gx) * 64 + g4 * 4) =
-                make_float4(acc[py * 2 + px][0], acc[py * 2 + px][1], acc[py * 2 + px][2], acc[py * 2 + px][3]);
+            *reinterpret_cast<float2*>(p.out + (((long long)b * p.H3 + gy) * p.W3 + gx) * 64 + g2 * 2) =
+                make_float2(acc[py * 2 + px][0], acc[py * 2 + px][1]);
         }
     }
   }
