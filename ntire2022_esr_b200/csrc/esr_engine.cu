@@ -37,6 +37,17 @@ struct Plan {
   std::vector<Launch> launches;
   cudaGraphExec_t gexec = nullptr;
   bool graph_failed = false;
+  int n_tc_layers = 0;
+  std::vector<void*> dev_allocs;   // layer descriptors of the tcgen05 chains (freed with the plan)
+};
+
+// consecutive tcgen05 convolutions waiting to be emitted as ONE launch (a chain, conv_tc.cuh)
+struct TcPending {
+  std::vector<TcLayerDesc> layers;
+  std::vector<std::string> names;
+  double flops = 0;
+  size_t smem = 0;
+  int tmem_cols = 32, max_items = 0;
 };
 
 struct DevGraph {            // a Graph plus its device-side parameters
@@ -57,6 +68,8 @@ struct Engine {
   std::string err;
   // options
   int opt_tc = 1, opt_shift_mode = 0, opt_use_graph = 1, opt_rows_per_item = 0, opt_timeline = 0, opt_dbg_flags = 0, opt_acc_slots = 4, opt_pdl = 0;
+  int opt_chain = 1;               // consecutive tcgen05 layers share one launch (grid barrier between them)
+  uint32_t* d_gbar = nullptr;      // grid barrier state of the chain kernel
   long long* d_timeline = nullptr;  // 128 stamps per tcgen05 launch (debug option tc_timeline)
   std::list<Plan> plans;
   // host-buffer path: kHostSlots requests in flight (H2D, forward and D2H of consecutive requests overlap)
@@ -212,13 +225,45 @@ static double op_flops(const OpDecl& op, int B, int H, int W) {
 
 static const size_t kMaxSmem = 232448 - 2048;  // 227 KB minus the kernel's static shared memory (barriers, bias)
 
-static int plan_tc(Engine* e, const DevGraph& dg, const TcConv& c, const std::string& name, const WsLayout& L, Plan& pl) {
-  struct Packed {
-    CUtensorMap tmA, tmO[TC_MAX_GROUPS];
-    TcParams p;
-  };
-  auto pk = std::make_shared<Packed>();
-  memset(pk.get(), 0, sizeof(Packed));
+// Emits the pending chain as one launch of conv_tc_kernel.
+static int flush_tc(Engine* e, Plan& pl, TcPending& pend) {
+  if (pend.layers.empty()) return ESR_OK;
+  const int n = (int)pend.layers.size();
+  TcLayerDesc* d_layers = nullptr;
+  CUDA_TRY(e, cudaMalloc(&d_layers, sizeof(TcLayerDesc) * n));
+  pl.dev_allocs.push_back(d_layers);
+  CUDA_TRY(e, cudaMemcpy(d_layers, pend.layers.data(), sizeof(TcLayerDesc) * n, cudaMemcpyHostToDevice));
+  if (!e->d_gbar) {
+    CUDA_TRY(e, cudaMalloc(&e->d_gbar, 64));
+    CUDA_TRY(e, cudaMemset(e->d_gbar, 0, 64));
+  }
+  TcChainParams cp;
+  cp.layers = d_layers;
+  cp.nlayers = n;
+  cp.tmem_cols = pend.tmem_cols;
+  cp.gbar = e->d_gbar;
+  // every CTA of a chain must be resident for the grid barrier: at most one per SM
+  const int grid = std::min(pend.max_items, e->num_sms);
+  const size_t smem = pend.smem;
+  static size_t attr_set = 0;
+  if (smem > attr_set) {
+    CUDA_TRY(e, cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+    attr_set = kMaxSmem;
+  }
+  std::string name = "conv_tc:";
+  for (int i = 0; i < n; ++i) name += (i ? " | " : "") + pend.names[i];
+  Launch l{name, [cp, grid, smem](cudaStream_t s) { return launch_k(conv_tc_kernel, dim3(grid), dim3(TC_THREADS), smem, s, cp); }};
+  l.flops = pend.flops;
+  pl.launches.push_back(std::move(l));
+  pend = TcPending();
+  return ESR_OK;
+}
+
+static int plan_tc(Engine* e, const DevGraph& dg, const TcConv& c, const std::string& name, const WsLayout& L, Plan& pl,
+                   TcPending& pend, double flops) {
+  pend.layers.emplace_back();
+  TcLayerDesc* pk = &pend.layers.back();
+  memset(pk, 0, sizeof(TcLayerDesc));
   TcParams& p = pk->p;
   const int B = pl.B, H = pl.H, W = pl.W;
   uint8_t* ws = reinterpret_cast<uint8_t*>(pl.ws);
@@ -249,8 +294,7 @@ static int plan_tc(Engine* e, const DevGraph& dg, const TcConv& c, const std::st
       CUDA_TRY(e, cudaMalloc(&e->d_timeline, 256 * 128 * sizeof(long long)));
       CUDA_TRY(e, cudaMemset(e->d_timeline, 0, 256 * 128 * sizeof(long long)));
     }
-    int idx = 0;
-    for (auto& l : pl.launches) idx += l.name.rfind("conv_tc", 0) == 0 ? 1 : 0;
+    const int idx = pl.n_tc_layers;
     if (idx < 256) p.dbg = e->d_timeline + (size_t)idx * 128;
   }
   // shared memory carve-up
@@ -259,7 +303,6 @@ static int plan_tc(Engine* e, const DevGraph& dg, const TcConv& c, const std::st
   p.w_bytes = (int)c.blob.size();
   off += (c.blob.size() + 1023) / 1024 * 1024;
   if (p.ngroups > TC_MAX_GROUPS) return fail(e, ESR_E_INVALID, name + ": too many output groups");
-  std::vector<TcChunk> chunks;
   for (int gi = 0; gi < p.ngroups; ++gi) {
     const TcGroupDecl& gd = c.groups[gi];
     TcOutGroup& g = p.g[gi];
@@ -276,14 +319,6 @@ static int plan_tc(Engine* e, const DevGraph& dg, const TcConv& c, const std::st
       g.res_stride = dg.g.bufs[gd.res].C;
       g.res_coff = gd.res_coff;
     }
-    for (int c0 = 0; c0 < gd.ncols;) {
-      const int wdt = 16;
-      TcChunk ck;
-      memset(&ck, 0, sizeof(ck));
-      ck.tcol = (uint16_t)(gd.col0 + c0); ck.group = (uint8_t)gi; ck.c0 = (uint8_t)c0; ck.width = (uint8_t)wdt;
-      chunks.push_back(ck);
-      c0 += wdt;
-    }
     if (gd.mode == 0) {
       g.stage_off = (int)off;
       g.stage_bytes = (TC_TILE_PX * gd.ncols * 2 + 1023) / 1024 * 1024;
@@ -294,10 +329,6 @@ static int plan_tc(Engine* e, const DevGraph& dg, const TcConv& c, const std::st
       if (rc) return rc;
     }
   }
-  // 16-column units alternate between the two epilogue warp sets (unit index parity)
-  if ((int)chunks.size() > TC_MAX_CHUNKS) return fail(e, ESR_E_INVALID, name + ": too many epilogue chunks");
-  p.n_epi_chunks = (int)chunks.size();
-  for (size_t i = 0; i < chunks.size(); ++i) p.ck[i] = chunks[i];
   p.ring_off = (int)off;
   const size_t avail = kMaxSmem - 1024 - off;
   int nslots = (int)std::min<size_t>(TC_MAX_SLOTS, avail / p.strip_bytes);
@@ -337,16 +368,13 @@ static int plan_tc(Engine* e, const DevGraph& dg, const TcConv& c, const std::st
     d.idesc = umma_idesc_f16((uint32_t)s.n);
     d.misc = (uint32_t)s.dcol | ((uint32_t)(s.nsteps & 15) << 16) | (s.first ? 0x80000000u : 0u);
   }
-  const int grid = std::min(p.n_items, e->num_sms);
-  static size_t attr_set = 0;
-  if (smem > attr_set) {
-    CUDA_TRY(e, cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-    attr_set = kMaxSmem;
-  }
-  pl.launches.push_back(Launch{"conv_tc:" + name, [pk, grid, smem](cudaStream_t s) {
-                                 return launch_k(conv_tc_kernel, dim3(grid), dim3(TC_THREADS), smem, s, pk->tmA, pk->tmO[0], pk->tmO[1],
-                                                 pk->tmO[2], pk->p);
-                               }});
+  ++pl.n_tc_layers;
+  pend.names.push_back(name);
+  pend.flops += flops;
+  pend.smem = std::max(pend.smem, smem);
+  pend.tmem_cols = std::max(pend.tmem_cols, p.tmem_cols);
+  pend.max_items = std::max(pend.max_items, p.n_items);
+  if (!e->opt_chain) return flush_tc(e, pl, pend);
   return ESR_OK;
 }
 
@@ -388,7 +416,12 @@ static int build_plan(Engine* e, Plan& pl) {
     return ws + L.off[b];
   };
   (void)elt;
+  TcPending pend;
   for (const OpDecl& op : g.ops) {
+    if (op.kind != OP_CONV_TC) {
+      int rc = flush_tc(e, pl, pend);
+      if (rc) return rc;
+    }
     switch (op.kind) {
       case OP_HEAD:
       case OP_BSRN_HEAD: {
@@ -562,15 +595,15 @@ static int build_plan(Engine* e, Plan& pl) {
       }
       case OP_CONV_TC: {
         if (!f16) return fail(e, ESR_E_INVALID, "tcgen05 path is fp16 only");
-        int rc = plan_tc(e, dg, g.tc[op.tc], op.name, L, pl);
+        int rc = plan_tc(e, dg, g.tc[op.tc], op.name, L, pl, pend, op_flops(op, B, H, W));
         if (rc) return rc;
-        break;
+        continue;   // emitted (with its FLOPs) when the chain is flushed
       }
       default: return fail(e, ESR_E_INVALID, "unknown op");
     }
     pl.launches.back().flops = op_flops(op, B, H, W);
   }
-  return ESR_OK;
+  return flush_tc(e, pl, pend);
 }
 
 static int check_shape(Engine* e, int B, int H, int W, int dtype) {
@@ -596,6 +629,14 @@ static int ensure_graph(Engine* e, int gid) {
   return ESR_OK;
 }
 
+static void free_plan(Plan& p) {
+  if (p.gexec) cudaGraphExecDestroy(p.gexec);
+  p.gexec = nullptr;
+  if (!p.dev_allocs.empty()) cudaDeviceSynchronize();   // a replay may still read the descriptors
+  for (void* d : p.dev_allocs) cudaFree(d);
+  p.dev_allocs.clear();
+}
+
 static Plan* get_plan(Engine* e, const void* in, void* out, int B, int H, int W, int dtype, void* ws, int& rc) {
   const int gid = graph_id(e, dtype);
   for (auto it = e->plans.begin(); it != e->plans.end(); ++it)
@@ -610,18 +651,17 @@ static Plan* get_plan(Engine* e, const void* in, void* out, int B, int H, int W,
   Plan pl;
   pl.B = B; pl.H = H; pl.W = W; pl.dtype = dtype; pl.gid = gid; pl.in = in; pl.out = out; pl.ws = ws;
   rc = build_plan(e, pl);
-  if (rc) return nullptr;
+  if (rc) { free_plan(pl); return nullptr; }
   e->plans.push_front(std::move(pl));
   while (e->plans.size() > 16) {
-    if (e->plans.back().gexec) cudaGraphExecDestroy(e->plans.back().gexec);
+    free_plan(e->plans.back());
     e->plans.pop_back();
   }
   return &e->plans.front();
 }
 
 static void drop_plans(Engine* e) {
-  for (auto& p : e->plans)
-    if (p.gexec) cudaGraphExecDestroy(p.gexec);
+  for (auto& p : e->plans) free_plan(p);
   e->plans.clear();
 }
 
@@ -864,12 +904,20 @@ static Plan* dry_plan(esr_handle* h, int B, int H, int W, int dtype, Plan& tmp) 
     if (p.B == B && p.H == H && p.W == W && p.dtype == dtype && p.gid == gid) return &p;
   // names only: one launch per op
   tmp.launches.clear();
+  bool prev_tc = false;
   for (auto& op : h->graphs[gid].g.ops) {
     static const char* kn[] = {"head", "bsrn_head", "conv_generic", "dwconv", "maxpool", "esa_apply", "conv_tc", "esa_apply2",
                                "esa_conv2_pool", "esa_chain"};
     std::string kname = kn[op.kind];
     if (op.kind == OP_CONV && !op.ps && h->graphs[gid].tables[op.tab].cin8 == 16 && h->graphs[gid].tables[op.tab].cout16 == 16)
       kname = "conv16";
+    const bool merge = op.kind == OP_CONV_TC && h->opt_chain && prev_tc;
+    prev_tc = op.kind == OP_CONV_TC;
+    if (merge) {
+      tmp.launches.back().name += " | " + op.name;
+      tmp.launches.back().flops += op_flops(op, B, H, W);
+      continue;
+    }
     tmp.launches.push_back(Launch{kname + ":" + op.name, nullptr, op_flops(op, B, H, W)});
   }
   return &tmp;
@@ -960,6 +1008,7 @@ int esr_set_option(esr_handle* h, const char* key, int value) {
   else if (k == "tc_dbg_flags") h->opt_dbg_flags = value;
   else if (k == "tc_acc_slots") h->opt_acc_slots = value == 4 ? 4 : 2;
   else if (k == "use_pdl") h->opt_pdl = value ? 1 : 0;
+  else if (k == "tc_chain") h->opt_chain = value ? 1 : 0;
   else return fail(h, ESR_E_INVALID, "unknown option: " + k);
   drop_plans(h);
   return ESR_OK;
@@ -998,6 +1047,7 @@ void esr_destroy(esr_handle* h) {
     if (h->s_cmp) cudaStreamDestroy(h->s_cmp);
     if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
     if (h->d_timeline) cudaFree(h->d_timeline);
+    if (h->d_gbar) cudaFree(h->d_gbar);
   }
   delete h;
 }
