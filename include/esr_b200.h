@@ -62,6 +62,24 @@ size_t esr_workspace_bytes(esr_handle* h, int B, int H, int W, int dtype);
 int esr_forward(esr_handle* h, const void* in_nchw, void* out_nchw, int B, int H, int W, int dtype,
                 void* workspace, size_t workspace_bytes, void* stream);
 
+/* uint8 image in, uint8 image out: replaces the three calls the reference's run() makes per image,
+ *   img_lr = util.uint2tensor4(img_lr, data_range)   (test_demo.py:423, utils/utils_image.py:190-193)
+ *   img_sr = forward(img_lr, model, tile)            (test_demo.py:430)
+ *   img_sr = util.tensor2uint(img_sr, data_range)    (test_demo.py:434, utils/utils_image.py:204-208)
+ * in = (B,H,W,3) interleaved uint8, out = (B,4H,4W,3) interleaved uint8, both DEVICE pointers.  The scaling
+ * u8 / (255 / data_range) is folded into the first convolution's load; the clamp / * 255 / data_range /
+ * round-half-even / uint8 cast runs on the device on the network's output, so only 1/2 (fp16) or 1/4 (fp32) of
+ * the output bytes ever leave the GPU.  `dtype` selects the engine precision (ESR_DTYPE_F16: result identical to
+ * tensor2uint(model(uint2tensor4(img).half()))).  The workspace needs esr_workspace_bytes_u8() bytes. */
+size_t esr_workspace_bytes_u8(esr_handle* h, int B, int H, int W, int dtype);
+int esr_forward_u8(esr_handle* h, const uint8_t* in_hwc, uint8_t* out_hwc, int B, int H, int W, float data_range,
+                   int dtype, void* workspace, size_t workspace_bytes, void* stream);
+/* the same with HOST buffers (see esr_forward_host / esr_forward_host_async below) */
+int esr_forward_host_u8(esr_handle* h, const uint8_t* in_host_hwc, uint8_t* out_host_hwc, int B, int H, int W,
+                        float data_range, int dtype);
+int esr_forward_host_u8_async(esr_handle* h, const uint8_t* in_host_hwc, uint8_t* out_host_hwc, int B, int H, int W,
+                              float data_range, int dtype, long long* ticket);
+
 /* Same computation with HOST buffers (pageable or pinned): the engine stages them through its own
  * device buffers on `stream` and synchronises before returning.  This is the path a non-PyTorch
  * caller binds; bench.py times it as the end-to-end number. */

@@ -2,6 +2,6 @@
 reference's `select_model` / `forward` API.  Compute lives in csrc/ (sm_100a CUDA, C ABI in
 include/esr_b200.h); this package is the host-side mirror of the reference interface."""
 from .engine import Engine, EsrError  # noqa: F401
-from .demo_api import B200SRModel, build_model, forward, select_model  # noqa: F401
+from .demo_api import B200SRModel, build_model, forward, forward_uint8, select_model  # noqa: F401
 
-__all__ = ["Engine", "EsrError", "B200SRModel", "build_model", "select_model", "forward"]
+__all__ = ["Engine", "EsrError", "B200SRModel", "build_model", "select_model", "forward", "forward_uint8"]

@@ -24,6 +24,13 @@ SYMBOLS = [
     ("esr_workspace_bytes", _c.c_size_t, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int]),
     ("esr_forward", _c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
                                _c.c_void_p, _c.c_size_t, _c.c_void_p]),
+    ("esr_workspace_bytes_u8", _c.c_size_t, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int]),
+    ("esr_forward_u8", _c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_float, _c.c_int,
+                                  _c.c_void_p, _c.c_size_t, _c.c_void_p]),
+    ("esr_forward_host_u8", _c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_float,
+                                       _c.c_int]),
+    ("esr_forward_host_u8_async", _c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_float,
+                                             _c.c_int, _c.POINTER(_c.c_longlong)]),
     ("esr_forward_host", _c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int]),
     ("esr_forward_host_async", _c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
                                           _c.POINTER(_c.c_longlong)]),

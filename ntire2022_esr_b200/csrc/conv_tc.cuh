@@ -11,15 +11,10 @@
 // column strip keeping a ring of row strips in shared memory; weights are staged once per CTA as
 // pre-swizzled blocks.
 //
-// Warp roles (352 threads): warp 0 = TMA producer, warps 1 and 10 = MMA issuers for even / odd tiles (one
-// elected lane each), warps 2..5 and 6..9 = two independent epilogue sets for even / odd tiles (TMEM ->
-// registers -> bias/residual/activation -> fp16 -> swizzled staging -> TMA store, or the fused pixel-shuffle
-// store of the network tail).  Up to four TMEM accumulator slots decouple the MMAs from the epilogues.
-//
-// One launch runs a CHAIN of layers (the five convolutions of a distillation block, or the network tail):
-// the CTAs are persistent across the layers and meet at a grid-wide barrier between two layers (all CTAs
-// are co-resident: one per SM), so a block costs one launch and the weights of layer l+1 are fetched while
-// the barrier of layer l drains.
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (one elected
+// lane each), warps 2..5 = epilogue (TMEM -> registers -> bias/residual/activation -> fp16 ->
+// swizzled staging -> TMA store, or the fused pixel-shuffle store of the network tail).  Two TMEM
+// accumulator slots let the epilogue of tile t overlap the MMAs of tile t+1.
 //
 // Measured on B200 (tools/micro/mma_bench.cu): an M=128, K=16 SS-mode MMA costs 32 + N/4 cycles for
 // N <= 128 (A and B are both fetched from shared memory at 128 B/clk), i.e. 48 cycles at N = 64.
@@ -35,7 +30,9 @@ constexpr int TC_MAX_ENTRIES = 16;
 constexpr int TC_TILE_PX = 128;
 constexpr int TC_MAX_SLOTS = 8;
 constexpr int TC_MAX_GROUPS = 3;
-constexpr int TC_PREFETCH_ROWS = 6;  // L2 prefetch distance of the producer, in image rows
+constexpr int TC_MAX_CHUNKS = 10;
+constexpr int TC_MAX_UNITS = 5;
+constexpr int TC_PREFETCH_ROWS = 6;  // L2 prefetch distance of the producer, in image rows     // 16-column units per epilogue warp set = ceil(TC_MAX_CHUNKS / 2)
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_THREADS = 96 + 32 * TC_EPI_WARPS;  // warp 0 TMA, warp 1 + warp 10 MMA issuers, warps 2..9 epilogue
 constexpr int TC_DONE_BARS = 8;
@@ -58,11 +55,17 @@ struct TcOutGroup {
   int32_t res_stride;  // residual: elements per pixel
   int32_t res_coff;
   int32_t mode;        // 0: TMA store NHWC fp16   1: pixel-shuffle x4 store into NCHW output
-  int32_t swizzle;     // staging layout of the store tensor map (1 = SWIZZLE_128B, 0 = linear)
+  int32_t swizzle;     // staging layout of the store tensor map: 0 linear, 1 SWIZZLE_128B (64 ch), 2 SWIZZLE_64B (32 ch), 3 SWIZZLE_32B (16 ch)
   int32_t stage_off;   // smem offset of the two staging buffers
   int32_t stage_bytes; // bytes of one staging buffer
   const float* bias;   // [ncols]
   const __half* res;   // nullptr = none
+};
+
+// one unit of epilogue work: 16 accumulator columns of one output group
+struct __align__(8) TcChunk {
+  uint16_t tcol;    // accumulator column
+  uint8_t group, c0, width, pad_[3];
 };
 
 struct TcParams {
@@ -75,7 +78,7 @@ struct TcParams {
   int32_t nslots;        // strip ring depth
   int32_t rows_per_item;
   int32_t strips_x, segs_y, n_items;
-  int32_t n_entries, ngroups;
+  int32_t n_entries, ngroups, n_epi_chunks;
   int32_t tmem_cols;     // TMEM allocation (power of two >= 2*acc_cols)
   int32_t acc_cols;      // columns of one accumulator slot
   int32_t acc_slots;     // accumulator slots in TMEM (2 or 4): how far the MMA warp may run ahead of the epilogue
@@ -89,18 +92,7 @@ struct TcParams {
   long long* dbg;        // optional timeline buffer (block 0 only): [role][event] clock64 stamps
   TcEntry e[TC_MAX_ENTRIES];
   TcOutGroup g[TC_MAX_GROUPS];
-};
-
-// One layer of a chain as it lives in device memory (tensor maps may be read from global memory)
-struct __align__(128) TcLayerDesc {
-  CUtensorMap tmA, tmO[TC_MAX_GROUPS];
-  TcParams p;
-};
-struct TcChainParams {
-  const TcLayerDesc* layers;   // device memory, nlayers entries
-  int32_t nlayers;
-  int32_t tmem_cols;           // TMEM allocation of the CTA: the maximum over the layers
-  uint32_t* gbar;              // grid barrier state: [0] arrivals, [1] generation (zero-initialised once)
+  TcChunk ck[TC_MAX_CHUNKS];
 };
 
 #define TC_STAMP(role, idx)                                                                        \
@@ -125,37 +117,6 @@ __device__ __forceinline__ void tmem_ld16_nc(uint32_t taddr, uint32_t* v) {
       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
         "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr));
-}
-__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-// orders this thread's generic-proxy and async-proxy (TMA) accesses, all state spaces
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
-// Grid-wide barrier between two layers of a chain (count + generation, self-resetting).  Called by ONE thread
-// per CTA after a __syncthreads() that follows the completion of every global write of the CTA (TMA stores
-// included); every CTA of the grid must be resident (grid <= number of SMs, one CTA per SM).  Bounded: a
-// scheduling bug must surface as a launch error, never as a hung GPU.
-__device__ __forceinline__ void grid_barrier(uint32_t* gbar, uint32_t nblocks) {
-  const uint32_t gen = ld_acquire_gpu(gbar + 1);   // read before arriving: it cannot advance until this CTA arrives
-  fence_proxy_async_all();
-  __threadfence();
-  if (atomicAdd(gbar, 1u) == nblocks - 1) {
-    atomicExch(gbar, 0u);
-    __threadfence();
-    atomicAdd(gbar + 1, 1u);
-  } else {
-    const long long t0 = clock64();
-    while (ld_acquire_gpu(gbar + 1) == gen) {
-      if (clock64() - t0 > 4000000000LL) {
-        printf("esr: grid barrier timeout block %d\n", blockIdx.x);
-        __trap();
-      }
-    }
-  }
-  __threadfence();
-  fence_proxy_async_all();
 }
 // MMA without a memory clobber: ordering against the barrier waits / commits comes from `volatile`
 __device__ __forceinline__ void umma_f16_ss_nc(uint32_t tmem_d, uint32_t adesc_lo, uint32_t bdesc_lo, uint32_t idesc,
@@ -253,7 +214,10 @@ __device__ __forceinline__ void tc_epi_store16(const float (&f)[16], int mode, u
   }
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcChainParams cp) {
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmO0,
+               const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ CUtensorMap tmO2,
+               const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[TC_MAX_SLOTS], tdone_bar[TC_DONE_BARS], tfull_bar[4], tempty_bar[4], w_bar;
   __shared__ int need_a_s[TC_MAX_SLOTS], need_b_s[TC_MAX_SLOTS];   // producer-private: last reader tiles of the strip in each slot
@@ -261,355 +225,331 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcChainPar
   __shared__ __align__(16) float bias_s[TC_MAX_GROUPS][64];
   __shared__ __align__(16) TcEntry ent_s[TC_MAX_ENTRIES];
   __shared__ TcOutGroup grp_s[TC_MAX_GROUPS];
+  __shared__ TcChunk ck_s[TC_MAX_CHUNKS];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long* const dbg = p.dbg;
+  if (threadIdx.x == 0) TC_STAMP(0, 0);
   // 1024-byte aligned view of dynamic shared memory (SWIZZLE_128B atoms)
   const uint32_t raw_u32 = smem_u32(smem_raw);
   const uint32_t pad = (1024u - (raw_u32 & 1023u)) & 1023u;
   uint8_t* const smem = smem_raw + pad;
   const uint32_t smem_base = raw_u32 + pad;
-  const int nlayers = cp.nlayers;
-  if (warp == 1) tmem_alloc(&tmem_base_s, (uint32_t)cp.tmem_cols);
 
-  for (int layer = 0; layer < nlayers; ++layer) {
-    const TcLayerDesc* const L = cp.layers + layer;
-    const TcParams& p = L->p;   // global memory: everything the role loops touch is copied to registers below
-    const CUtensorMap* const tmA = &L->tmA;
-    const CUtensorMap* const tmO0 = &L->tmO[0];
-    const CUtensorMap* const tmO1 = &L->tmO[1];
-    const CUtensorMap* const tmO2 = &L->tmO[2];
-    long long* const dbg = p.dbg;
-    if (threadIdx.x == 0) TC_STAMP(0, 0);
+  // every parameter the role loops touch lives in a register from here on (the param bank would be
+  // re-read after each asm volatile with a memory clobber otherwise)
+  const int S = p.nslots, halo = p.halo, nchunks = p.nchunks, strip_bytes = p.strip_bytes, chunk_bytes = p.chunk_bytes;
+  const int n_items = p.n_items, strips_x = p.strips_x, segs_y = p.segs_y, rows_per_item = p.rows_per_item;
+  const int H = p.H, W = p.W, ring_off = p.ring_off, acc_cols = p.acc_cols, n_entries = p.n_entries, ngroups = p.ngroups;
+  const int dbg_flags = p.dbg_flags;
+  const uint32_t NS = (uint32_t)p.acc_slots, ns_shift = NS == 4 ? 2u : 1u;
 
-    const int S = p.nslots, halo = p.halo, nchunks = p.nchunks, strip_bytes = p.strip_bytes, chunk_bytes = p.chunk_bytes;
-    const int n_items = p.n_items, strips_x = p.strips_x, segs_y = p.segs_y, rows_per_item = p.rows_per_item;
-    const int H = p.H, W = p.W, ring_off = p.ring_off, acc_cols = p.acc_cols, n_entries = p.n_entries, ngroups = p.ngroups;
-    const int dbg_flags = p.dbg_flags, w_off = p.w_off, w_bytes = p.w_bytes;
-    const uint32_t NS = (uint32_t)p.acc_slots, ns_shift = NS == 4 ? 2u : 1u;
+  auto decode = [&](int item, int& b, int& y0, int& y1, int& x0) {
+    const int per_img = strips_x * segs_y;
+    b = item / per_img;
+    const int rem = item - b * per_img;
+    const int seg = rem / strips_x;
+    const int sx = rem - seg * strips_x;
+    y0 = seg * rows_per_item;
+    y1 = min(y0 + rows_per_item, H);
+    x0 = sx * TC_TILE_PX;
+  };
 
-    auto decode = [&](int item, int& b, int& y0, int& y1, int& x0) {
-      const int per_img = strips_x * segs_y;
-      b = item / per_img;
-      const int rem = item - b * per_img;
-      const int seg = rem / strips_x;
-      const int sx = rem - seg * strips_x;
-      y0 = seg * rows_per_item;
-      y1 = min(y0 + rows_per_item, H);
-      x0 = sx * TC_TILE_PX;
-    };
-
-    // ---- producer state (warp 0, elected lane): strips are issued in two phases so that the first ring
-    // fill overlaps the rest of the layer set-up (bias / entry tables)
-    const uint32_t strip_tx = (uint32_t)(nchunks * p.strip_px * 128);
-    const int cc0 = p.chunk_c0[0], cc1 = p.chunk_c0[1], cc2 = p.chunk_c0[2], cc3 = p.chunk_c0[3];
-    uint32_t pr_slot = 0, pr_seq = 0;
-    int pr_item = blockIdx.x, pr_row = 0, pr_b = 0, pr_y0 = 0, pr_y1 = 0, pr_x0 = 0, pr_tile_base = 0;
-    bool pr_open = false;
-    auto produce = [&](uint32_t limit) {   // issue strips until `limit` have been issued in total
-      while (pr_seq < limit) {
-        if (!pr_open) {
-          if (pr_item >= n_items) return;
-          decode(pr_item, pr_b, pr_y0, pr_y1, pr_x0);
-          pr_row = pr_y0 - halo;
-          pr_open = true;
-        }
-        if (pr_seq >= (uint32_t)S) {
-          // the slot still holds an older strip: every tile that reads it must have completed.  Its readers are
-          // up to 1 + 2*halo consecutive tiles, issued alternately by the two MMA warps, so the last reader of
-          // each warp is waited for (tile-done barriers, committed by the issuers after each tile).
-          const int ua = need_a_s[pr_slot], ub = need_b_s[pr_slot];
-          mbar_wait(&tdone_bar[ua & (TC_DONE_BARS - 1)], (uint32_t)(ua >> 3) & 1u);
-          if (ub >= 0) mbar_wait(&tdone_bar[ub & (TC_DONE_BARS - 1)], (uint32_t)(ub >> 3) & 1u);
-        }
-        {
-          const int nrows = pr_y1 - pr_y0, j = pr_row - (pr_y0 - halo);
-          const int last = min(j, nrows - 1), first = max(0, j - 2 * halo);
-          need_a_s[pr_slot] = pr_tile_base + last;
-          need_b_s[pr_slot] = (last - 1 >= first) ? pr_tile_base + last - 1 : -1;
-        }
-        mbar_arrive_expect_tx(&full_bar[pr_slot], strip_tx);
-        uint8_t* dst = smem + ring_off + pr_slot * strip_bytes;
-        tma_load_4d(tmA, &full_bar[pr_slot], dst, cc0, pr_x0 - halo, pr_row, pr_b);
-        if (nchunks > 1) tma_load_4d(tmA, &full_bar[pr_slot], dst + chunk_bytes, cc1, pr_x0 - halo, pr_row, pr_b);
-        if (nchunks > 2) tma_load_4d(tmA, &full_bar[pr_slot], dst + 2 * chunk_bytes, cc2, pr_x0 - halo, pr_row, pr_b);
-        if (nchunks > 3) tma_load_4d(tmA, &full_bar[pr_slot], dst + 3 * chunk_bytes, cc3, pr_x0 - halo, pr_row, pr_b);
-        if (pr_row + TC_PREFETCH_ROWS < pr_y1 + halo) {   // warm L2 for the strip the ring cannot hold yet
-          tma_prefetch_4d(tmA, cc0, pr_x0 - halo, pr_row + TC_PREFETCH_ROWS, pr_b);
-          if (nchunks > 1) tma_prefetch_4d(tmA, cc1, pr_x0 - halo, pr_row + TC_PREFETCH_ROWS, pr_b);
-          if (nchunks > 2) tma_prefetch_4d(tmA, cc2, pr_x0 - halo, pr_row + TC_PREFETCH_ROWS, pr_b);
-          if (nchunks > 3) tma_prefetch_4d(tmA, cc3, pr_x0 - halo, pr_row + TC_PREFETCH_ROWS, pr_b);
-        }
-        TC_STAMP(1, pr_seq);
-        ++pr_seq;
-        if (++pr_slot == (uint32_t)S) pr_slot = 0;
-        if (++pr_row >= pr_y1 + halo) { pr_open = false; pr_tile_base += pr_y1 - pr_y0; pr_item += gridDim.x; }
+  // ---- producer state (warp 0, elected lane): strips are issued in two phases so that the first ring
+  // fill overlaps the rest of the CTA set-up (TMEM allocation, bias / entry tables)
+  const uint32_t strip_tx = (uint32_t)(nchunks * p.strip_px * 128);
+  const int cc0 = p.chunk_c0[0], cc1 = p.chunk_c0[1], cc2 = p.chunk_c0[2], cc3 = p.chunk_c0[3];
+  uint32_t pr_slot = 0, pr_seq = 0;
+  int pr_item = blockIdx.x, pr_row = 0, pr_b = 0, pr_y0 = 0, pr_y1 = 0, pr_x0 = 0, pr_tile_base = 0;
+  bool pr_open = false;
+  auto produce = [&](uint32_t limit) {   // issue strips until `limit` have been issued in total
+    while (pr_seq < limit) {
+      if (!pr_open) {
+        if (pr_item >= n_items) return;
+        decode(pr_item, pr_b, pr_y0, pr_y1, pr_x0);
+        pr_row = pr_y0 - halo;
+        pr_open = true;
       }
-    };
-
-    // ---- layer set-up.  Every barrier, shared-memory region and TMEM column is idle here: the previous layer
-    // ended with all MMAs complete, all accumulators drained and all TMA stores finished, followed by a CTA sync.
-    if (warp == 0) {
-      if (elect_one()) {
-        tma_prefetch_desc(tmA);
-        if (layer > 0) {
-          for (int i = 0; i < TC_MAX_SLOTS; ++i) mbar_inval(&full_bar[i]);
-          for (int i = 0; i < TC_DONE_BARS; ++i) mbar_inval(&tdone_bar[i]);
-          for (int i = 0; i < 4; ++i) { mbar_inval(&tfull_bar[i]); mbar_inval(&tempty_bar[i]); }
-          mbar_inval(&w_bar);
-        }
-        for (int i = 0; i < TC_MAX_SLOTS; ++i) mbar_init(&full_bar[i], 1);
-        for (int i = 0; i < TC_DONE_BARS; ++i) mbar_init(&tdone_bar[i], 1);
-        for (int i = 0; i < 4; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], TC_EPI_WARPS / 2); }
-        mbar_init(&w_bar, 1);
-        fence_mbar_init();
-        if (layer > 0) {
-          // the weights never depend on the previous layer: they travel while the grid barrier drains
-          mbar_arrive_expect_tx(&w_bar, (uint32_t)w_bytes);
-          bulk_load_1d(smem + w_off, p.wblob, (uint32_t)w_bytes, &w_bar);
-          grid_barrier(cp.gbar, gridDim.x);
-          produce((uint32_t)S);
-        } else if (p.pdl) {
-          // programmatic dependent launch: weights go before the grid dependency is resolved
-          mbar_arrive_expect_tx(&w_bar, (uint32_t)w_bytes);
-          bulk_load_1d(smem + w_off, p.wblob, (uint32_t)w_bytes, &w_bar);
-          griddep_wait();
-          produce((uint32_t)S);
-        } else {
-          // the strips the first tile needs are requested first (the TMA queue is served in order and the
-          // 77 KB weight copy would delay them)
-          produce((uint32_t)(1 + 2 * halo));
-          mbar_arrive_expect_tx(&w_bar, (uint32_t)w_bytes);
-          bulk_load_1d(smem + w_off, p.wblob, (uint32_t)w_bytes, &w_bar);
-          produce((uint32_t)S);
-        }
-        tma_prefetch_desc(tmO0);
-        tma_prefetch_desc(tmO1);
-        tma_prefetch_desc(tmO2);
+      if (pr_seq >= (uint32_t)S) {
+        // the slot still holds an older strip: every tile that reads it must have completed.  Its readers are
+        // up to 1 + 2*halo consecutive tiles, issued alternately by the two MMA warps, so the last reader of
+        // each warp is waited for (tile-done barriers, committed by the issuers after each tile).
+        const int ua = need_a_s[pr_slot], ub = need_b_s[pr_slot];
+        mbar_wait(&tdone_bar[ua & (TC_DONE_BARS - 1)], (uint32_t)(ua >> 3) & 1u);
+        if (ub >= 0) mbar_wait(&tdone_bar[ub & (TC_DONE_BARS - 1)], (uint32_t)(ub >> 3) & 1u);
       }
-      __syncwarp();
+      {
+        const int nrows = pr_y1 - pr_y0, j = pr_row - (pr_y0 - halo);
+        const int last = min(j, nrows - 1), first = max(0, j - 2 * halo);
+        need_a_s[pr_slot] = pr_tile_base + last;
+        need_b_s[pr_slot] = (last - 1 >= first) ? pr_tile_base + last - 1 : -1;
+      }
+      mbar_arrive_expect_tx(&full_bar[pr_slot], strip_tx);
+      uint8_t* dst = smem + ring_off + pr_slot * strip_bytes;
+      tma_load_4d(&tmA, &full_bar[pr_slot], dst, cc0, pr_x0 - halo, pr_row, pr_b);
+      if (nchunks > 1) tma_load_4d(&tmA, &full_bar[pr_slot], dst + chunk_bytes, cc1, pr_x0 - halo, pr_row, pr_b);
+      if (nchunks > 2) tma_load_4d(&tmA, &full_bar[pr_slot], dst + 2 * chunk_bytes, cc2, pr_x0 - halo, pr_row, pr_b);
+      if (nchunks > 3) tma_load_4d(&tmA, &full_bar[pr_slot], dst + 3 * chunk_bytes, cc3, pr_x0 - halo, pr_row, pr_b);
+      if (pr_row + TC_PREFETCH_ROWS < pr_y1 + halo) {   // warm L2 for the strip the ring cannot hold yet
+        tma_prefetch_4d(&tmA, cc0, pr_x0 - halo, pr_row + TC_PREFETCH_ROWS, pr_b);
+        if (nchunks > 1) tma_prefetch_4d(&tmA, cc1, pr_x0 - halo, pr_row + TC_PREFETCH_ROWS, pr_b);
+        if (nchunks > 2) tma_prefetch_4d(&tmA, cc2, pr_x0 - halo, pr_row + TC_PREFETCH_ROWS, pr_b);
+        if (nchunks > 3) tma_prefetch_4d(&tmA, cc3, pr_x0 - halo, pr_row + TC_PREFETCH_ROWS, pr_b);
+      }
+      TC_STAMP(1, pr_seq);
+      ++pr_seq;
+      if (++pr_slot == (uint32_t)S) pr_slot = 0;
+      if (++pr_row >= pr_y1 + halo) { pr_open = false; pr_tile_base += pr_y1 - pr_y0; pr_item += gridDim.x; }
     }
-    if (warp >= 2) {
-      const int tid = threadIdx.x - 64;
-      for (int i = tid; i < TC_MAX_GROUPS * 64; i += 32 * TC_EPI_WARPS) {
-        const int g = i >> 6, c = i & 63;
-        bias_s[g][c] = (g < ngroups && c < p.g[g].ncols) ? p.g[g].bias[c] : 0.f;
-      }
-      if (tid < TC_MAX_ENTRIES) ent_s[tid] = p.e[tid];
-      if (tid >= 32 && tid < 32 + TC_MAX_GROUPS) grp_s[tid - 32] = p.g[tid - 32];
-    }
-    tc_fence_before_sync();
-    __syncthreads();
-    tc_fence_after_sync();
-    const uint32_t tmem_base = tmem_base_s;
-    if (threadIdx.x == 0) {
-      TC_STAMP(0, 1);
-      if (layer == 0) griddep_launch_dependents();   // this grid is fully resident (<= 1 CTA per SM)
-    }
+  };
 
-    if (warp == 0) {
-      // ================================ TMA producer ================================
-      if (elect_one()) {
-        produce(0xffffffffu);
-        TC_STAMP(0, 2);
+  if (warp == 0) {
+    if (elect_one()) {
+      tma_prefetch_desc(&tmA);
+      for (int i = 0; i < S; ++i) mbar_init(&full_bar[i], 1);
+      for (int i = 0; i < TC_DONE_BARS; ++i) mbar_init(&tdone_bar[i], 1);
+      for (int i = 0; i < 4; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], TC_EPI_WARPS); }
+      mbar_init(&w_bar, 1);
+      fence_mbar_init();
+      // With programmatic dependent launch the weights (which never depend on the previous kernel) go before
+      // the grid dependency is resolved; otherwise the strips the first tile needs are requested first (the TMA
+      // queue is served in order and the 77 KB weight copy would delay them).
+      if (p.pdl) {
+        mbar_arrive_expect_tx(&w_bar, (uint32_t)p.w_bytes);
+        bulk_load_1d(smem + p.w_off, p.wblob, (uint32_t)p.w_bytes, &w_bar);
+        griddep_wait();
+        produce((uint32_t)S);
+      } else {
+        produce((uint32_t)(1 + 2 * halo));
+        mbar_arrive_expect_tx(&w_bar, (uint32_t)p.w_bytes);
+        bulk_load_1d(smem + p.w_off, p.wblob, (uint32_t)p.w_bytes, &w_bar);
+        produce((uint32_t)S);
       }
-      __syncwarp();
-    } else if (warp == 1 || warp == 2 + TC_EPI_WARPS) {
-      // ================================ MMA issuers =================================
-      // Two issuing threads (warp 1: even tiles, warp 10: odd tiles).  One thread cannot keep the tensor pipe
-      // busy: between two tiles it spends ~0.8k cycles on barrier traffic (commits, strip / accumulator waits)
-      // while the short MMA queue drains; with two threads that bookkeeping hides behind the other one's MMAs.
-      if (elect_one()) {
-        const uint32_t me = warp == 1 ? 0u : 1u;
-        mbar_wait(&w_bar, 0);
-        if (me == 0) TC_STAMP(0, 3);
-        const uint32_t ring_base = smem_base + ring_off;
-        const uint32_t w_lo = 0x10000u | ((smem_base + w_off) >> 4);   // descriptor low word: LBO = 1, start >> 4
-        // strips are numbered q = 0, 1, ... in the order the producer issues them: slot = q % S, phase = (q / S) & 1.
-        // `tslot/tpar` follow the top strip of the current tile; `seen` = strips this thread has already waited for
-        uint32_t tslot = 0, tpar = 0, q_top = 0, seen = 0, t = 0;
-        int last_t = -1;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-          int b, y0, y1, x0;
-          decode(item, b, y0, y1, x0);
-          const int nrows = y1 - y0;
-          for (int r = 0; r < nrows; ++r, ++t) {
-            if ((t & 1u) == me) {
-              // wait for the strips of this tile's row window that this thread has not seen yet
-              uint32_t sl = tslot, pa = tpar;
-              for (uint32_t q = q_top; q <= q_top + 2 * halo; ++q) {
-                if (q >= seen) mbar_wait(&full_bar[sl], pa);
-                if (++sl == (uint32_t)S) { sl = 0; pa ^= 1; }
-              }
-              seen = q_top + 2 * halo + 1;
-              const uint32_t aslot = t & (NS - 1);
-              if (t < 16) TC_STAMP(2, 2 * t);
-              mbar_wait(&tempty_bar[aslot], ((t >> ns_shift) & 1) ^ 1);
-              tc_fence_after_sync();
-              const uint32_t d_base = tmem_base + aslot * acc_cols;
-              const int ne = (dbg_flags & 1) ? 0 : n_entries;
-              // descriptor low words of the (up to three) strips of this tile's row window
-              uint32_t s1 = tslot + 1, s2 = tslot + 2;
-              if (s1 >= (uint32_t)S) s1 -= S;
-              if (s2 >= (uint32_t)S) s2 -= S;
-              const uint32_t rb0 = 0x10000u | ((ring_base + tslot * strip_bytes) >> 4);
-              const uint32_t rb1 = 0x10000u | ((ring_base + s1 * strip_bytes) >> 4);
-              const uint32_t rb2 = 0x10000u | ((ring_base + s2 * strip_bytes) >> 4);
-              uint4 en = *reinterpret_cast<const uint4*>(&ent_s[0]);
-              for (int ei = 0; ei < ne; ++ei) {
-                const uint4 e = en;
-                if (ei + 1 < ne) en = *reinterpret_cast<const uint4*>(&ent_s[ei + 1]);   // next entry in flight
-                const uint32_t row = e.x >> 28;
-                const uint32_t a_lo = (row == 0 ? rb0 : (row == 1 ? rb1 : rb2)) + (e.x & 0x0fffffffu);
-                const uint32_t b_lo = w_lo + e.y;
-                const uint32_t steps = (e.w >> 16) & 15u;
-                const uint32_t d = d_base + (e.w & 0xffffu);
-                umma_f16_ss_nc(d, a_lo, b_lo, e.z, (e.w >> 31) ? 0u : 1u);
-                if (steps > 1) umma_f16_ss_nc(d, a_lo + 2, b_lo + 2, e.z, 1u);
-                if (steps > 2) umma_f16_ss_nc(d, a_lo + 4, b_lo + 4, e.z, 1u);
-                if (steps > 3) umma_f16_ss_nc(d, a_lo + 6, b_lo + 6, e.z, 1u);
-              }
-              umma_commit(&tfull_bar[aslot]);
-              umma_commit(&tdone_bar[t & (TC_DONE_BARS - 1)]);
-              last_t = (int)t;
-              if (t < 16) TC_STAMP(2, 2 * t + 1);
-            }
-            ++q_top;
-            if (++tslot == (uint32_t)S) { tslot = 0; tpar ^= 1; }
-          }
-          // the next item starts 2*halo strips further down the ring
-          for (int k = 0; k < 2 * halo; ++k) {
-            ++q_top;
-            if (++tslot == (uint32_t)S) { tslot = 0; tpar ^= 1; }
-          }
-        }
-        // every MMA (and its barrier arrivals) of this thread has landed before the layer ends
-        if (last_t >= 0) mbar_wait(&tdone_bar[last_t & (TC_DONE_BARS - 1)], (uint32_t)(last_t >> 3) & 1u);
-      }
-      __syncwarp();
-    } else {
-      // ================================ epilogue ====================================
-      // Two independent sets of four warps (2..5 and 6..9), set `eg` takes the tiles with t % 2 == eg, so the
-      // latency chain of one tile (accumulator wait -> tcgen05.ld -> math -> staging -> TMA store) overlaps
-      // the other set's.  Warp w reads TMEM lanes 32*(w%4).. (hardware rule); each thread owns one pixel of the
-      // tile and walks all of its 16-column units.  Every set has its own staging buffer and store thread.
-      const int q = warp & 3;            // TMEM lane quadrant this warp may read
-      const int eg = (warp - 2) >> 2;    // epilogue set
-      const int m = q * 32 + lane;       // pixel of the tile == TMEM lane
-      const bool store_thread = ((warp - 2) & 3) == 0 && lane == 0;
-      const uint32_t bar_a = 1u + 2u * (uint32_t)eg, bar_b = 2u + 2u * (uint32_t)eg;
-      const int ps_fp32 = p.ps_fp32;
-      void* const ps_out = p.ps_out;
-      const int ng = (dbg_flags & 2) ? 0 : ngroups;
-      if (layer == 0) griddep_wait();   // residual reads, staging stores and the fused pixel-shuffle store touch global memory
-      // per-group constants in registers (the group index is a compile-time constant in the unrolled loops)
-      int gcol0[TC_MAX_GROUPS], gncols[TC_MAX_GROUPS], gmode[TC_MAX_GROUPS], gswz[TC_MAX_GROUPS];
-      int gstage[TC_MAX_GROUPS];
-      bool ggelu[TC_MAX_GROUPS];
-      float gslope[TC_MAX_GROUPS];
-#pragma unroll
-      for (int gi = 0; gi < TC_MAX_GROUPS; ++gi) {
-        const TcOutGroup& g = grp_s[gi < ngroups ? gi : 0];
-        gcol0[gi] = g.col0; gncols[gi] = gi < ng ? g.ncols : 0; gmode[gi] = g.mode; gswz[gi] = g.swizzle;
-        gstage[gi] = g.stage_off + eg * g.stage_bytes;
-        ggelu[gi] = g.act == ACT_GELU; gslope[gi] = g.slope;
-      }
-      const bool g0_has_res = ng > 0 && grp_s[0].res != nullptr;
-      const __half* const g0_res = g0_has_res ? grp_s[0].res + grp_s[0].res_coff : nullptr;
-      const int g0_res_stride = grp_s[0].res_stride, g0_res_after = grp_s[0].res_after;
-      uint32_t t = 0;
+      tma_prefetch_desc(&tmO0);
+      tma_prefetch_desc(&tmO1);
+      tma_prefetch_desc(&tmO2);
+    }
+    __syncwarp();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_s, (uint32_t)p.tmem_cols);
+  if (warp >= 2) {
+    const int tid = threadIdx.x - 64;
+    for (int i = tid; i < TC_MAX_GROUPS * 64; i += 32 * TC_EPI_WARPS) {
+      const int g = i >> 6, c = i & 63;
+      bias_s[g][c] = (g < ngroups && c < p.g[g].ncols) ? p.g[g].bias[c] : 0.f;
+    }
+    if (tid < TC_MAX_ENTRIES) ent_s[tid] = p.e[tid];
+    if (tid >= 32 && tid < 32 + TC_MAX_GROUPS) grp_s[tid - 32] = p.g[tid - 32];
+    if (tid >= 64 && tid < 64 + TC_MAX_CHUNKS) ck_s[tid - 64] = p.ck[tid - 64];
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_base_s;
+  if (threadIdx.x == 0) {
+    TC_STAMP(0, 1);
+    griddep_launch_dependents();   // this grid is fully resident (<= 1 CTA per SM): let the next kernel set up
+  }
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (elect_one()) {
+      produce(0xffffffffu);
+      TC_STAMP(0, 2);
+    }
+    __syncwarp();
+  } else if (warp == 1 || warp == 2 + TC_EPI_WARPS) {
+    // ================================ MMA issuers =================================
+    // Two issuing threads (warp 1: even tiles, warp 10: odd tiles).  One thread cannot keep the tensor pipe
+    // busy: between two tiles it spends ~0.8k cycles on barrier traffic (commits, strip / accumulator waits)
+    // while the short MMA queue drains; with two threads that bookkeeping hides behind the other one's MMAs.
+    if (elect_one()) {
+      const uint32_t me = warp == 1 ? 0u : 1u;
+      mbar_wait(&w_bar, 0);
+      if (me == 0) TC_STAMP(0, 3);
+      const uint32_t ring_base = smem_base + ring_off;
+      const uint32_t w_lo = 0x10000u | ((smem_base + p.w_off) >> 4);   // descriptor low word: LBO = 1, start >> 4
+      // strips are numbered q = 0, 1, ... in the order the producer issues them: slot = q % S, phase = (q / S) & 1.
+      // `tslot/tpar` follow the top strip of the current tile; `seen` = strips this thread has already waited for
+      uint32_t tslot = 0, tpar = 0, q_top = 0, seen = 0, t = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         int b, y0, y1, x0;
         decode(item, b, y0, y1, x0);
-        for (int y = y0; y < y1; ++y, ++t) {
-          if ((t & 1u) != (uint32_t)eg) continue;
-          const int x = x0 + m;
-          const bool valid = x < W;
-          const long long pix = ((long long)b * H + y) * W + x;
-          const uint32_t aslot = t & (NS - 1);
-          // slot s = (output group s / 4, 16-column unit s % 4), all compile-time in the unrolled loops
-          auto slot_valid = [&](int s) { return (s & 3) * 16 < gncols[s >> 2]; };
-          // residual rows (group 0 only) travel from L2 while the accumulator / the TMEM load is waited for.
-          // Written by other CTAs in an earlier layer of this launch: read around L1.
-          auto res_fetch = [&](int s, uint4 (&r)[2]) {
-            r[0] = make_uint4(0, 0, 0, 0);
-            r[1] = make_uint4(0, 0, 0, 0);
-            if ((s >> 2) == 0 && g0_has_res && valid && slot_valid(s)) {
-              const uint4* rp = reinterpret_cast<const uint4*>(g0_res + pix * g0_res_stride + (s & 3) * 16);
-              r[0] = __ldcg(rp);
-              r[1] = __ldcg(rp + 1);
+        const int nrows = y1 - y0;
+        for (int r = 0; r < nrows; ++r, ++t) {
+          if ((t & 1u) == me) {
+            // wait for the strips of this tile's row window that this thread has not seen yet
+            uint32_t sl = tslot, pa = tpar;
+            for (uint32_t q = q_top; q <= q_top + 2 * halo; ++q) {
+              if (q >= seen) mbar_wait(&full_bar[sl], pa);
+              if (++sl == (uint32_t)S) { sl = 0; pa ^= 1; }
             }
-          };
-          uint4 ra[2], rb[2], rc[2];
-          res_fetch(0, ra);
-          res_fetch(1, rb);
-          res_fetch(2, rc);
-          // this set's staging buffer was last read by the TMA store of its previous tile
-          if (store_thread) tma_store_wait_read<0>();
-          named_bar_sync(bar_a, 32 * (TC_EPI_WARPS / 2));
-          if (lane == 0 && q == 2) TC_STAMP(3, 3 * t);
-          mbar_wait(&tfull_bar[aslot], (t >> ns_shift) & 1);
-          tc_fence_after_sync();
-          if (lane == 0 && q == 2) TC_STAMP(3, 3 * t + 1);
-          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + aslot * acc_cols;
-          auto slot_load = [&](int s, uint32_t (&v)[16]) { tmem_ld16_nc(taddr + gcol0[s >> 2] + (s & 3) * 16, v); };
-          auto slot_run = [&](int s, const uint32_t (&v)[16], const uint4 (&r)[2]) {
-            const int gi = s >> 2, c0 = (s & 3) * 16;
-            const bool has_res = gi == 0 && g0_has_res;
-            uint8_t* stage_row = smem + gstage[gi] + m * (gncols[gi] * 2);
-            const int swz = gswz[gi] ? (m & 7) : 0;
-            float f[16];
-            tc_epi_math16(v, &bias_s[gi][c0], ggelu[gi], gslope[gi], has_res, r[0], r[1], g0_res_after, f);
-            tc_epi_store16(f, gmode[gi], stage_row, c0, swz, valid, ps_out, ps_fp32, b, y, x, H, W);
-          };
-          // tcgen05.ld is queued behind the MMAs already issued for the next tiles (in-order tensor pipe) and
-          // takes ~0.7k cycles to come back while both MMA warps keep the pipe busy, so the loads of three
-          // slots are issued back to back and waited for once
-          uint32_t va[16], vb[16], vc[16];
-#pragma unroll
-          for (int s0 = 0; s0 < 4 * TC_MAX_GROUPS; s0 += 3) {
-            if (!(slot_valid(s0) || slot_valid(s0 + 1) || slot_valid(s0 + 2))) continue;
-            if (s0 > 0) {
-              res_fetch(s0, ra);
-              res_fetch(s0 + 1, rb);
-              res_fetch(s0 + 2, rc);
+            seen = q_top + 2 * halo + 1;
+            const uint32_t aslot = t & (NS - 1);
+            if (t < 16) TC_STAMP(2, 2 * t);
+            mbar_wait(&tempty_bar[aslot], ((t >> ns_shift) & 1) ^ 1);
+            tc_fence_after_sync();
+            const uint32_t d_base = tmem_base + aslot * acc_cols;
+            const int ne = (dbg_flags & 1) ? 0 : n_entries;
+            // descriptor low words of the (up to three) strips of this tile's row window
+            uint32_t s1 = tslot + 1, s2 = tslot + 2;
+            if (s1 >= (uint32_t)S) s1 -= S;
+            if (s2 >= (uint32_t)S) s2 -= S;
+            const uint32_t rb0 = 0x10000u | ((ring_base + tslot * strip_bytes) >> 4);
+            const uint32_t rb1 = 0x10000u | ((ring_base + s1 * strip_bytes) >> 4);
+            const uint32_t rb2 = 0x10000u | ((ring_base + s2 * strip_bytes) >> 4);
+            uint4 en = *reinterpret_cast<const uint4*>(&ent_s[0]);
+            for (int ei = 0; ei < ne; ++ei) {
+              const uint4 e = en;
+              if (ei + 1 < ne) en = *reinterpret_cast<const uint4*>(&ent_s[ei + 1]);   // next entry in flight
+              const uint32_t row = e.x >> 28;
+              const uint32_t a_lo = (row == 0 ? rb0 : (row == 1 ? rb1 : rb2)) + (e.x & 0x0fffffffu);
+              const uint32_t b_lo = w_lo + e.y;
+              const uint32_t steps = (e.w >> 16) & 15u;
+              const uint32_t d = d_base + (e.w & 0xffffu);
+              umma_f16_ss_nc(d, a_lo, b_lo, e.z, (e.w >> 31) ? 0u : 1u);
+              if (steps > 1) umma_f16_ss_nc(d, a_lo + 2, b_lo + 2, e.z, 1u);
+              if (steps > 2) umma_f16_ss_nc(d, a_lo + 4, b_lo + 4, e.z, 1u);
+              if (steps > 3) umma_f16_ss_nc(d, a_lo + 6, b_lo + 6, e.z, 1u);
             }
-            if (slot_valid(s0)) slot_load(s0, va);
-            if (slot_valid(s0 + 1)) slot_load(s0 + 1, vb);
-            if (slot_valid(s0 + 2)) slot_load(s0 + 2, vc);
-            tmem_ld_wait();
-            if (slot_valid(s0)) slot_run(s0, va, ra);
-            if (slot_valid(s0 + 1)) slot_run(s0 + 1, vb, rb);
-            if (slot_valid(s0 + 2)) slot_run(s0 + 2, vc, rc);
+            umma_commit(&tfull_bar[aslot]);
+            umma_commit(&tdone_bar[t & (TC_DONE_BARS - 1)]);
+            if (t < 16) TC_STAMP(2, 2 * t + 1);
           }
-          // accumulator slot drained: hand it back to the MMA warps
-          tc_fence_before_sync();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[aslot]);
-          fence_proxy_async_smem();
-          named_bar_sync(bar_b, 32 * (TC_EPI_WARPS / 2));
-          if (store_thread) {
-            if (ng > 0) {
-              if (gmode[0] == 0) tma_store_4d(tmO0, smem + gstage[0], 0, x0, y, b);
-              if (ng > 1 && gmode[1] == 0) tma_store_4d(tmO1, smem + gstage[1], 0, x0, y, b);
-              if (ng > 2 && gmode[2] == 0) tma_store_4d(tmO2, smem + gstage[2], 0, x0, y, b);
-            }
-            tma_store_commit();
-            TC_STAMP(3, 3 * t + 2);
-          }
+          ++q_top;
+          if (++tslot == (uint32_t)S) { tslot = 0; tpar ^= 1; }
+        }
+        // the next item starts 2*halo strips further down the ring
+        for (int k = 0; k < 2 * halo; ++k) {
+          ++q_top;
+          if (++tslot == (uint32_t)S) { tslot = 0; tpar ^= 1; }
         }
       }
-      if (store_thread) {
-        tma_store_wait_all<0>();     // the outputs are in global memory before the layer ends
-        fence_proxy_async_all();
-        if (eg == 0) TC_STAMP(0, 4);
+    }
+    __syncwarp();
+  } else {
+    // ================================ epilogue ====================================
+    // 8 warps: warp w reads TMEM lanes 32*(w%4).. (hardware rule); the two warps of a lane quadrant split
+    // the epilogue chunks (32 or 16 accumulator columns each) between them by chunk parity
+    const int q = warp & 3;           // TMEM lane quadrant this warp may read
+    const int half = (warp - 2) >> 2; // 0: warps 2..5, 1: warps 6..9
+    const int m = q * 32 + lane;      // pixel of the tile == TMEM lane
+    const bool store_thread = (warp == 2) && (lane == 0);
+    const int ps_fp32 = p.ps_fp32;
+    void* const ps_out = p.ps_out;
+    const int ng = (dbg_flags & 2) ? 0 : ngroups;
+    const int nck = ng;
+    griddep_wait();   // residual reads, staging stores and the fused pixel-shuffle store touch global memory
+    // per-group constants in registers (the group index is a compile-time constant in the unrolled loops)
+    int gcol0[TC_MAX_GROUPS], gncols[TC_MAX_GROUPS], gmode[TC_MAX_GROUPS], gswz[TC_MAX_GROUPS];
+    int gstage[TC_MAX_GROUPS], gstage_bytes[TC_MAX_GROUPS];
+    bool ggelu[TC_MAX_GROUPS];
+    float gslope[TC_MAX_GROUPS];
+#pragma unroll
+    for (int gi = 0; gi < TC_MAX_GROUPS; ++gi) {
+      const TcOutGroup& g = grp_s[gi < ngroups ? gi : 0];
+      gcol0[gi] = g.col0; gncols[gi] = gi < ngroups ? g.ncols : 0; gmode[gi] = g.mode; gswz[gi] = g.swizzle;
+      gstage[gi] = g.stage_off; gstage_bytes[gi] = g.stage_bytes;
+      ggelu[gi] = g.act == ACT_GELU; gslope[gi] = g.slope;
+    }
+    const bool g0_has_res = ng > 0 && grp_s[0].res != nullptr;
+    const __half* const g0_res = g0_has_res ? grp_s[0].res + grp_s[0].res_coff : nullptr;
+    const int g0_res_stride = grp_s[0].res_stride;
+    uint32_t t = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      int b, y0, y1, x0;
+      decode(item, b, y0, y1, x0);
+      for (int y = y0; y < y1; ++y, ++t) {
+        const int x = x0 + m;
+        const bool valid = x < W;
+        const long long pix = ((long long)b * H + y) * W + x;
+        const uint32_t aslot = t & (NS - 1), sbuf = t & 1;
+        // residual rows (group 0 only) are fetched before the accumulator is ready: their latency hides
+        // behind the MMAs
+        uint4 rpre[2][2];
+        if (g0_has_res) {
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            rpre[k][0] = make_uint4(0, 0, 0, 0);
+            rpre[k][1] = make_uint4(0, 0, 0, 0);
+            const int c0 = (half + 2 * k) * 16;
+            if (valid && c0 < gncols[0]) {
+              const uint4* rp = reinterpret_cast<const uint4*>(g0_res + pix * g0_res_stride + c0);
+              rpre[k][0] = rp[0];
+              rpre[k][1] = rp[1];
+            }
+          }
+        }
+        // staging buffer `sbuf` was last read by the TMA store of tile t-2
+        if (store_thread) tma_store_wait_read<1>();
+        named_bar_sync(1, 32 * TC_EPI_WARPS);
+        if (threadIdx.x == 64) TC_STAMP(3, 3 * t);
+        mbar_wait(&tfull_bar[aslot], (t >> ns_shift) & 1);
+        tc_fence_after_sync();
+        if (threadIdx.x == 64) TC_STAMP(3, 3 * t + 1);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + aslot * acc_cols;
+        // tcgen05.ld is queued behind the MMAs already issued for the next tiles (in-order tensor pipe), so
+        // this warp issues ALL of its TMEM loads for the tile back to back and waits once.  Within every
+        // output group the two warps of a lane quadrant take alternate 16-column units.
+        // (group, k) slots are compile-time; slot s+1's TMEM load is in flight while slot s is converted and
+        // staged (two register buffers)
+        uint32_t va[16], vb[16];
+        auto slot_valid = [&](int s) { return (s >> 1) < ng && (half + 2 * (s & 1)) * 16 < gncols[s >> 1]; };
+        auto slot_load = [&](int s, uint32_t (&v)[16]) { tmem_ld16_nc(taddr + gcol0[s >> 1] + (half + 2 * (s & 1)) * 16, v); };
+        auto slot_run = [&](int s, const uint32_t (&v)[16]) {
+          const int gi = s >> 1, c0 = (half + 2 * (s & 1)) * 16;
+          const TcOutGroup& g = grp_s[gi];
+          const bool has_res = gi == 0 && g0_has_res;
+          uint8_t* stage_row = smem + gstage[gi] + sbuf * gstage_bytes[gi] + m * (gncols[gi] * 2);
+          const int swz = gswz[gi] == 1 ? (m & 7) : (gswz[gi] == 2 ? ((m >> 1) & 3) : (gswz[gi] == 3 ? ((m >> 2) & 1) : 0));
+          float f[16];
+          tc_epi_math16(v, &bias_s[gi][c0], ggelu[gi], gslope[gi], has_res, rpre[s & 1][0], rpre[s & 1][1], g.res_after, f);
+          tc_epi_store16(f, gmode[gi], stage_row, c0, swz, valid, ps_out, ps_fp32, b, y, x, H, W);
+        };
+        // With both MMA warps keeping the tensor pipe busy a tcgen05.ld takes ~0.7k cycles to come back, so
+        // the loads of three slots are issued back to back and waited for once (two rounds cover all six)
+        uint32_t vc[16];
+#pragma unroll
+        for (int s0 = 0; s0 < 2 * TC_MAX_GROUPS; s0 += 3) {
+          if (!(slot_valid(s0) || slot_valid(s0 + 1) || slot_valid(s0 + 2))) continue;
+          if (slot_valid(s0)) slot_load(s0, va);
+          if (slot_valid(s0 + 1)) slot_load(s0 + 1, vb);
+          if (slot_valid(s0 + 2)) slot_load(s0 + 2, vc);
+          tmem_ld_wait();
+          if (slot_valid(s0)) slot_run(s0, va);
+          if (slot_valid(s0 + 1)) slot_run(s0 + 1, vb);
+          if (slot_valid(s0 + 2)) slot_run(s0 + 2, vc);
+        }
+        if (threadIdx.x == 64 && t < 8) TC_STAMP(1, 16 + 2 * t);
+        if (threadIdx.x == 64 && t < 8) TC_STAMP(1, 17 + 2 * t);
+        // accumulator slot drained: hand it back to the MMA warp
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[aslot]);
+        fence_proxy_async_smem();
+        named_bar_sync(2, 32 * TC_EPI_WARPS);
+        if (store_thread) {
+          if (nck > 0) {
+            if (grp_s[0].mode == 0) tma_store_4d(&tmO0, smem + grp_s[0].stage_off + sbuf * grp_s[0].stage_bytes, 0, x0, y, b);
+            if (ngroups > 1 && grp_s[1].mode == 0)
+              tma_store_4d(&tmO1, smem + grp_s[1].stage_off + sbuf * grp_s[1].stage_bytes, 0, x0, y, b);
+            if (ngroups > 2 && grp_s[2].mode == 0)
+              tma_store_4d(&tmO2, smem + grp_s[2].stage_off + sbuf * grp_s[2].stage_bytes, 0, x0, y, b);
+          }
+          tma_store_commit();
+          TC_STAMP(3, 3 * t + 2);
+        }
       }
     }
-    // ---- end of layer: the CTA is quiescent after this sync (see layer set-up)
-    tc_fence_before_sync();
-    __syncthreads();
-    if (threadIdx.x == 0) TC_STAMP(0, 5);
+    if (store_thread) {
+      tma_store_wait_all<0>();
+      TC_STAMP(0, 4);
+    }
   }
-  if (warp == 1) tmem_dealloc(tmem_base_s, (uint32_t)cp.tmem_cols);
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  if (threadIdx.x == 0) TC_STAMP(0, 5);
 }
 
 }  // namespace esr

@@ -34,20 +34,13 @@ struct Plan {
   const void* in = nullptr;
   void* out = nullptr;
   void* ws = nullptr;
+  // uint8 I/O (esr_forward_u8): `in` is HWC uint8, `out` the engine's own NCHW buffer, `u8_out` the caller's HWC uint8
+  bool u8 = false;
+  float data_range = 1.f;
+  void* u8_out = nullptr;
   std::vector<Launch> launches;
   cudaGraphExec_t gexec = nullptr;
   bool graph_failed = false;
-  int n_tc_layers = 0;
-  std::vector<void*> dev_allocs;   // layer descriptors of the tcgen05 chains (freed with the plan)
-};
-
-// consecutive tcgen05 convolutions waiting to be emitted as ONE launch (a chain, conv_tc.cuh)
-struct TcPending {
-  std::vector<TcLayerDesc> layers;
-  std::vector<std::string> names;
-  double flops = 0;
-  size_t smem = 0;
-  int tmem_cols = 32, max_items = 0;
 };
 
 struct DevGraph {            // a Graph plus its device-side parameters
@@ -68,8 +61,6 @@ struct Engine {
   std::string err;
   // options
   int opt_tc = 1, opt_shift_mode = 0, opt_use_graph = 1, opt_rows_per_item = 0, opt_timeline = 0, opt_dbg_flags = 0, opt_acc_slots = 4, opt_pdl = 0;
-  int opt_chain = 1;               // consecutive tcgen05 layers share one launch (grid barrier between them)
-  uint32_t* d_gbar = nullptr;      // grid barrier state of the chain kernel
   long long* d_timeline = nullptr;  // 128 stamps per tcgen05 launch (debug option tc_timeline)
   std::list<Plan> plans;
   // host-buffer path: kHostSlots requests in flight (H2D, forward and D2H of consecutive requests overlap)
@@ -203,14 +194,17 @@ static cudaError_t launch1(K kern, dim3 grid, dim3 block, size_t smem, cudaStrea
 }
 
 static int make_tensor_map(Engine* e, CUtensorMap* m, void* base, int C_stride_elems, int c_extent, int W, int H, int B,
-                           int box_c, int box_w, bool swizzle128) {
+                           int box_c, int box_w, int swizzle /* 0 none, 1 128B, 2 64B, 3 32B */) {
   cuuint64_t dims[4] = {(cuuint64_t)c_extent, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)C_stride_elems * 2, (cuuint64_t)W * C_stride_elems * 2,
                            (cuuint64_t)H * W * C_stride_elems * 2};
   cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = e->encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                      : (swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                      : (swizzle == 3 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE)),
                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(e, ESR_E_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
   return ESR_OK;
@@ -225,45 +219,13 @@ static double op_flops(const OpDecl& op, int B, int H, int W) {
 
 static const size_t kMaxSmem = 232448 - 2048;  // 227 KB minus the kernel's static shared memory (barriers, bias)
 
-// Emits the pending chain as one launch of conv_tc_kernel.
-static int flush_tc(Engine* e, Plan& pl, TcPending& pend) {
-  if (pend.layers.empty()) return ESR_OK;
-  const int n = (int)pend.layers.size();
-  TcLayerDesc* d_layers = nullptr;
-  CUDA_TRY(e, cudaMalloc(&d_layers, sizeof(TcLayerDesc) * n));
-  pl.dev_allocs.push_back(d_layers);
-  CUDA_TRY(e, cudaMemcpy(d_layers, pend.layers.data(), sizeof(TcLayerDesc) * n, cudaMemcpyHostToDevice));
-  if (!e->d_gbar) {
-    CUDA_TRY(e, cudaMalloc(&e->d_gbar, 64));
-    CUDA_TRY(e, cudaMemset(e->d_gbar, 0, 64));
-  }
-  TcChainParams cp;
-  cp.layers = d_layers;
-  cp.nlayers = n;
-  cp.tmem_cols = pend.tmem_cols;
-  cp.gbar = e->d_gbar;
-  // every CTA of a chain must be resident for the grid barrier: at most one per SM
-  const int grid = std::min(pend.max_items, e->num_sms);
-  const size_t smem = pend.smem;
-  static size_t attr_set = 0;
-  if (smem > attr_set) {
-    CUDA_TRY(e, cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-    attr_set = kMaxSmem;
-  }
-  std::string name = "conv_tc:";
-  for (int i = 0; i < n; ++i) name += (i ? " | " : "") + pend.names[i];
-  Launch l{name, [cp, grid, smem](cudaStream_t s) { return launch_k(conv_tc_kernel, dim3(grid), dim3(TC_THREADS), smem, s, cp); }};
-  l.flops = pend.flops;
-  pl.launches.push_back(std::move(l));
-  pend = TcPending();
-  return ESR_OK;
-}
-
-static int plan_tc(Engine* e, const DevGraph& dg, const TcConv& c, const std::string& name, const WsLayout& L, Plan& pl,
-                   TcPending& pend, double flops) {
-  pend.layers.emplace_back();
-  TcLayerDesc* pk = &pend.layers.back();
-  memset(pk, 0, sizeof(TcLayerDesc));
+static int plan_tc(Engine* e, const DevGraph& dg, const TcConv& c, const std::string& name, const WsLayout& L, Plan& pl) {
+  struct Packed {
+    CUtensorMap tmA, tmO[TC_MAX_GROUPS];
+    TcParams p;
+  };
+  auto pk = std::make_shared<Packed>();
+  memset(pk.get(), 0, sizeof(Packed));
   TcParams& p = pk->p;
   const int B = pl.B, H = pl.H, W = pl.W;
   uint8_t* ws = reinterpret_cast<uint8_t*>(pl.ws);
@@ -294,7 +256,8 @@ static int plan_tc(Engine* e, const DevGraph& dg, const TcConv& c, const std::st
       CUDA_TRY(e, cudaMalloc(&e->d_timeline, 256 * 128 * sizeof(long long)));
       CUDA_TRY(e, cudaMemset(e->d_timeline, 0, 256 * 128 * sizeof(long long)));
     }
-    const int idx = pl.n_tc_layers;
+    int idx = 0;
+    for (auto& l : pl.launches) idx += l.name.rfind("conv_tc", 0) == 0 ? 1 : 0;
     if (idx < 256) p.dbg = e->d_timeline + (size_t)idx * 128;
   }
   // shared memory carve-up
@@ -303,6 +266,7 @@ static int plan_tc(Engine* e, const DevGraph& dg, const TcConv& c, const std::st
   p.w_bytes = (int)c.blob.size();
   off += (c.blob.size() + 1023) / 1024 * 1024;
   if (p.ngroups > TC_MAX_GROUPS) return fail(e, ESR_E_INVALID, name + ": too many output groups");
+  std::vector<TcChunk> chunks;
   for (int gi = 0; gi < p.ngroups; ++gi) {
     const TcGroupDecl& gd = c.groups[gi];
     TcOutGroup& g = p.g[gi];
@@ -310,7 +274,9 @@ static int plan_tc(Engine* e, const DevGraph& dg, const TcConv& c, const std::st
     g.slope = gd.act == ACT_RELU ? 0.f : (gd.act == ACT_LRELU ? gd.slope : 1.f);   // NONE/RELU/LRELU = max(v, v*slope)
     g.res_after = gd.res_after;
     g.mode = gd.mode;
-    g.swizzle = gd.ncols == 64 ? 1 : 0;
+    // staging rows are one pixel each (ncols * 2 bytes); the matching TMA swizzle keeps the 16-byte staging
+    // stores of a quarter warp on distinct banks (linear 64 B / 32 B rows conflict 4-way / 2-way)
+    g.swizzle = gd.ncols == 64 ? 1 : (gd.ncols == 32 ? 2 : (gd.ncols == 16 ? 3 : 0));
     g.bias = dg.d_params + gd.off_bias;
     g.res = nullptr;
     if (gd.res != BUF_NONE && gi != 0) return fail(e, ESR_E_INVALID, name + ": only the first output group may carry a residual");
@@ -319,16 +285,28 @@ static int plan_tc(Engine* e, const DevGraph& dg, const TcConv& c, const std::st
       g.res_stride = dg.g.bufs[gd.res].C;
       g.res_coff = gd.res_coff;
     }
+    for (int c0 = 0; c0 < gd.ncols;) {
+      const int wdt = 16;
+      TcChunk ck;
+      memset(&ck, 0, sizeof(ck));
+      ck.tcol = (uint16_t)(gd.col0 + c0); ck.group = (uint8_t)gi; ck.c0 = (uint8_t)c0; ck.width = (uint8_t)wdt;
+      chunks.push_back(ck);
+      c0 += wdt;
+    }
     if (gd.mode == 0) {
       g.stage_off = (int)off;
       g.stage_bytes = (TC_TILE_PX * gd.ncols * 2 + 1023) / 1024 * 1024;
       off += 2 * (size_t)g.stage_bytes;
       const int Cs = dg.g.bufs[gd.out].C;
       __half* base = reinterpret_cast<__half*>(ws + L.off[gd.out]) + gd.out_coff;
-      int rc = make_tensor_map(e, &pk->tmO[gi], base, Cs, gd.ncols, W, H, B, gd.ncols, TC_TILE_PX, g.swizzle != 0);
+      int rc = make_tensor_map(e, &pk->tmO[gi], base, Cs, gd.ncols, W, H, B, gd.ncols, TC_TILE_PX, g.swizzle);
       if (rc) return rc;
     }
   }
+  // 16-column units alternate between the two epilogue warp sets (unit index parity)
+  if ((int)chunks.size() > TC_MAX_CHUNKS) return fail(e, ESR_E_INVALID, name + ": too many epilogue chunks");
+  p.n_epi_chunks = (int)chunks.size();
+  for (size_t i = 0; i < chunks.size(); ++i) p.ck[i] = chunks[i];
   p.ring_off = (int)off;
   const size_t avail = kMaxSmem - 1024 - off;
   int nslots = (int)std::min<size_t>(TC_MAX_SLOTS, avail / p.strip_bytes);
@@ -338,7 +316,7 @@ static int plan_tc(Engine* e, const DevGraph& dg, const TcConv& c, const std::st
   // A operand map
   {
     const int Cs = dg.g.bufs[c.in].C;
-    int rc = make_tensor_map(e, &pk->tmA, ws + L.off[c.in], Cs, Cs, W, H, B, 64, p.strip_px, true);
+    int rc = make_tensor_map(e, &pk->tmA, ws + L.off[c.in], Cs, Cs, W, H, B, 64, p.strip_px, 1);
     if (rc) return rc;
   }
   for (int gi = 0; gi < TC_MAX_GROUPS; ++gi)   // unused descriptor slots must still hold a valid map (they are prefetched)
@@ -368,13 +346,16 @@ static int plan_tc(Engine* e, const DevGraph& dg, const TcConv& c, const std::st
     d.idesc = umma_idesc_f16((uint32_t)s.n);
     d.misc = (uint32_t)s.dcol | ((uint32_t)(s.nsteps & 15) << 16) | (s.first ? 0x80000000u : 0u);
   }
-  ++pl.n_tc_layers;
-  pend.names.push_back(name);
-  pend.flops += flops;
-  pend.smem = std::max(pend.smem, smem);
-  pend.tmem_cols = std::max(pend.tmem_cols, p.tmem_cols);
-  pend.max_items = std::max(pend.max_items, p.n_items);
-  if (!e->opt_chain) return flush_tc(e, pl, pend);
+  const int grid = std::min(p.n_items, e->num_sms);
+  static size_t attr_set = 0;
+  if (smem > attr_set) {
+    CUDA_TRY(e, cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+    attr_set = kMaxSmem;
+  }
+  pl.launches.push_back(Launch{"conv_tc:" + name, [pk, grid, smem](cudaStream_t s) {
+                                 return launch_k(conv_tc_kernel, dim3(grid), dim3(TC_THREADS), smem, s, pk->tmA, pk->tmO[0], pk->tmO[1],
+                                                 pk->tmO[2], pk->p);
+                               }});
   return ESR_OK;
 }
 
@@ -416,12 +397,7 @@ static int build_plan(Engine* e, Plan& pl) {
     return ws + L.off[b];
   };
   (void)elt;
-  TcPending pend;
   for (const OpDecl& op : g.ops) {
-    if (op.kind != OP_CONV_TC) {
-      int rc = flush_tc(e, pl, pend);
-      if (rc) return rc;
-    }
     switch (op.kind) {
       case OP_HEAD:
       case OP_BSRN_HEAD: {
@@ -432,19 +408,29 @@ static int build_plan(Engine* e, Plan& pl) {
         const int stride = g.bufs[op.out].C;
         const float* w = dg.d_params + dg.tables[op.tab].off_w;
         const float* b = dg.d_params + dg.tables[op.tab].off_b;
+        const bool u8 = pl.u8;
+        const float in_div = (float)(255.0 / (double)pl.data_range);   // uint2tensor4: .div(255. / data_range)
         if (op.kind == OP_HEAD) {
           pl.launches.push_back(Launch{"head:" + op.name, [=](cudaStream_t s) {
+            if (u8 && f16)
+              return launch_k(k_head_conv<uint8_t, __half, float>, grid, dim3(256), 0, s, (const uint8_t*)in, (__half*)out, w, b, B, H, W, stride, 64, in_div);
+            if (u8)
+              return launch_k(k_head_conv<uint8_t, float, double>, grid, dim3(256), 0, s, (const uint8_t*)in, (float*)out, w, b, B, H, W, stride, 64, in_div);
             if (f16)
-              return launch_k(k_head_conv<__half, __half, float>, grid, dim3(256), 0, s, (const __half*)in, (__half*)out, w, b, B, H, W, stride, 64);
-            return launch_k(k_head_conv<float, float, double>, grid, dim3(256), 0, s, (const float*)in, (float*)out, w, b, B, H, W, stride, 64);
+              return launch_k(k_head_conv<__half, __half, float>, grid, dim3(256), 0, s, (const __half*)in, (__half*)out, w, b, B, H, W, stride, 64, 1.f);
+            return launch_k(k_head_conv<float, float, double>, grid, dim3(256), 0, s, (const float*)in, (float*)out, w, b, B, H, W, stride, 64, 1.f);
           }});
         } else {
           const float* wd = dg.d_params + dg.tables[op.tab2].off_w;
           const float* bd = dg.d_params + dg.tables[op.tab2].off_b;
           pl.launches.push_back(Launch{"bsrn_head:" + op.name, [=](cudaStream_t s) {
+            if (u8 && f16)
+              return launch_k(k_bsrn_head<uint8_t, __half, float>, grid, dim3(128), 0, s, (const uint8_t*)in, (__half*)out, w, b, wd, bd, B, H, W, stride, 64, in_div);
+            if (u8)
+              return launch_k(k_bsrn_head<uint8_t, float, double>, grid, dim3(128), 0, s, (const uint8_t*)in, (float*)out, w, b, wd, bd, B, H, W, stride, 64, in_div);
             if (f16)
-              return launch_k(k_bsrn_head<__half, __half, float>, grid, dim3(128), 0, s, (const __half*)in, (__half*)out, w, b, wd, bd, B, H, W, stride, 64);
-            return launch_k(k_bsrn_head<float, float, double>, grid, dim3(128), 0, s, (const float*)in, (float*)out, w, b, wd, bd, B, H, W, stride, 64);
+              return launch_k(k_bsrn_head<__half, __half, float>, grid, dim3(128), 0, s, (const __half*)in, (__half*)out, w, b, wd, bd, B, H, W, stride, 64, 1.f);
+            return launch_k(k_bsrn_head<float, float, double>, grid, dim3(128), 0, s, (const float*)in, (float*)out, w, b, wd, bd, B, H, W, stride, 64, 1.f);
           }});
         }
         break;
@@ -595,15 +581,26 @@ static int build_plan(Engine* e, Plan& pl) {
       }
       case OP_CONV_TC: {
         if (!f16) return fail(e, ESR_E_INVALID, "tcgen05 path is fp16 only");
-        int rc = plan_tc(e, dg, g.tc[op.tc], op.name, L, pl, pend, op_flops(op, B, H, W));
+        int rc = plan_tc(e, dg, g.tc[op.tc], op.name, L, pl);
         if (rc) return rc;
-        continue;   // emitted (with its FLOPs) when the chain is flushed
+        break;
       }
       default: return fail(e, ESR_E_INVALID, "unknown op");
     }
     pl.launches.back().flops = op_flops(op, B, H, W);
   }
-  return flush_tc(e, pl, pend);
+  if (pl.u8) {   // tensor2uint of the reference, on the engine's NCHW output
+    const void* src = pl.out;
+    uint8_t* dst = reinterpret_cast<uint8_t*>(pl.u8_out);
+    const float dr = pl.data_range;
+    const long long total = (long long)B * 16 * H * W;
+    const int nblk = (int)std::min<long long>((total + 255) / 256, (long long)e->num_sms * 16);
+    pl.launches.push_back(Launch{"tensor2uint:out", [=](cudaStream_t s) {
+      if (f16) return launch_k(k_tensor2uint<__half>, dim3(nblk), dim3(256), 0, s, (const __half*)src, dst, B, 4 * H, 4 * W, dr);
+      return launch_k(k_tensor2uint<float>, dim3(nblk), dim3(256), 0, s, (const float*)src, dst, B, 4 * H, 4 * W, dr);
+    }});
+  }
+  return ESR_OK;
 }
 
 static int check_shape(Engine* e, int B, int H, int W, int dtype) {
@@ -629,19 +626,18 @@ static int ensure_graph(Engine* e, int gid) {
   return ESR_OK;
 }
 
-static void free_plan(Plan& p) {
-  if (p.gexec) cudaGraphExecDestroy(p.gexec);
-  p.gexec = nullptr;
-  if (!p.dev_allocs.empty()) cudaDeviceSynchronize();   // a replay may still read the descriptors
-  for (void* d : p.dev_allocs) cudaFree(d);
-  p.dev_allocs.clear();
-}
+struct IoMode {   // uint8 HWC I/O of esr_forward_u8 (u8 = false: the plain NCHW float tensors of esr_forward)
+  bool u8 = false;
+  float data_range = 1.f;
+  void* u8_out = nullptr;
+};
 
-static Plan* get_plan(Engine* e, const void* in, void* out, int B, int H, int W, int dtype, void* ws, int& rc) {
+static Plan* get_plan(Engine* e, const void* in, void* out, int B, int H, int W, int dtype, void* ws, int& rc,
+                      const IoMode& io = IoMode()) {
   const int gid = graph_id(e, dtype);
   for (auto it = e->plans.begin(); it != e->plans.end(); ++it)
     if (it->B == B && it->H == H && it->W == W && it->dtype == dtype && it->gid == gid && it->in == in && it->out == out &&
-        it->ws == ws) {
+        it->ws == ws && it->u8 == io.u8 && it->u8_out == io.u8_out && (!io.u8 || it->data_range == io.data_range)) {
       e->plans.splice(e->plans.begin(), e->plans, it);
       rc = ESR_OK;
       return &e->plans.front();
@@ -650,18 +646,20 @@ static Plan* get_plan(Engine* e, const void* in, void* out, int B, int H, int W,
   if (rc) return nullptr;
   Plan pl;
   pl.B = B; pl.H = H; pl.W = W; pl.dtype = dtype; pl.gid = gid; pl.in = in; pl.out = out; pl.ws = ws;
+  pl.u8 = io.u8; pl.data_range = io.data_range; pl.u8_out = io.u8_out;
   rc = build_plan(e, pl);
-  if (rc) { free_plan(pl); return nullptr; }
+  if (rc) return nullptr;
   e->plans.push_front(std::move(pl));
   while (e->plans.size() > 16) {
-    free_plan(e->plans.back());
+    if (e->plans.back().gexec) cudaGraphExecDestroy(e->plans.back().gexec);
     e->plans.pop_back();
   }
   return &e->plans.front();
 }
 
 static void drop_plans(Engine* e) {
-  for (auto& p : e->plans) free_plan(p);
+  for (auto& p : e->plans)
+    if (p.gexec) cudaGraphExecDestroy(p.gexec);
   e->plans.clear();
 }
 
@@ -764,8 +762,18 @@ size_t esr_workspace_bytes(esr_handle* h, int B, int H, int W, int dtype) {
   return m;
 }
 
-int esr_forward(esr_handle* h, const void* in_nchw, void* out_nchw, int B, int H, int W, int dtype, void* workspace,
-                size_t workspace_bytes, void* stream) {
+static size_t u8_nchw_bytes(int B, int H, int W, int dtype) {
+  const size_t b = (size_t)B * 3 * 16 * H * W * (dtype == ESR_DTYPE_F16 ? 2 : 4);
+  return (b + 1023) / 1024 * 1024;
+}
+
+size_t esr_workspace_bytes_u8(esr_handle* h, int B, int H, int W, int dtype) {
+  const size_t base = esr_workspace_bytes(h, B, H, W, dtype);
+  return base ? base + u8_nchw_bytes(B, H, W, dtype) : 0;
+}
+
+static int forward_impl(esr_handle* h, const void* in_nchw, void* out_nchw, int B, int H, int W, int dtype, void* workspace,
+                        size_t workspace_bytes, void* stream, IoMode io) {
   if (!h) return ESR_E_INVALID;
   if (!h->finalized) return fail(h, ESR_E_STATE, "esr_forward before esr_finalize");
   if (!h->has_gpu) return fail(h, ESR_E_NOGPU, "no sm_100 device bound to this handle (the engine has no CPU fallback)");
@@ -773,12 +781,18 @@ int esr_forward(esr_handle* h, const void* in_nchw, void* out_nchw, int B, int H
   if (rc) return rc;
   if (!in_nchw || !out_nchw || !workspace) return fail(h, ESR_E_INVALID, "null device pointer");
   const size_t need = esr_workspace_bytes(h, B, H, W, dtype);
-  if (workspace_bytes < need)
-    return fail(h, ESR_E_INVALID, "workspace too small: need " + std::to_string(need) + " bytes");
-  if ((reinterpret_cast<uintptr_t>(in_nchw) & 15) || (reinterpret_cast<uintptr_t>(out_nchw) & 15))
+  if (workspace_bytes < need + (io.u8 ? u8_nchw_bytes(B, H, W, dtype) : 0))
+    return fail(h, ESR_E_INVALID, "workspace too small: need " +
+                                      std::to_string(need + (io.u8 ? u8_nchw_bytes(B, H, W, dtype) : 0)) + " bytes");
+  if (!io.u8 && ((reinterpret_cast<uintptr_t>(in_nchw) & 15) || (reinterpret_cast<uintptr_t>(out_nchw) & 15)))
     return fail(h, ESR_E_INVALID, "input / output must be 16-byte aligned");
+  if (io.u8 && !(io.data_range > 0.f)) return fail(h, ESR_E_INVALID, "data_range must be positive");
   // internal buffers need 1024-byte alignment (TMA, swizzle atoms); esr_workspace_bytes includes the slack
   workspace = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
+  if (io.u8) {   // the network's NCHW output lives behind the activation buffers; tensor2uint reads it
+    io.u8_out = out_nchw;
+    out_nchw = reinterpret_cast<uint8_t*>(workspace) + (need - 1024);
+  }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   CUDA_TRY(h, cudaSetDevice(h->device));
   if (h->ws_zeroed != workspace || h->ws_zeroed_sz < need) {
@@ -788,7 +802,7 @@ int esr_forward(esr_handle* h, const void* in_nchw, void* out_nchw, int B, int H
     h->ws_zeroed = workspace;
     h->ws_zeroed_sz = need;
   }
-  Plan* pl = get_plan(h, in_nchw, out_nchw, B, H, W, dtype, workspace, rc);
+  Plan* pl = get_plan(h, in_nchw, out_nchw, B, H, W, dtype, workspace, rc, io);
   if (!pl) return rc;
   struct PdlScope { PdlScope(bool on) { g_pdl = on; } ~PdlScope() { g_pdl = false; } } pdl_scope(h->opt_pdl != 0);
   if (h->opt_use_graph && !pl->graph_failed) {
@@ -823,6 +837,19 @@ int esr_forward(esr_handle* h, const void* in_nchw, void* out_nchw, int B, int H
   return ESR_OK;
 }
 
+int esr_forward(esr_handle* h, const void* in_nchw, void* out_nchw, int B, int H, int W, int dtype, void* workspace,
+                size_t workspace_bytes, void* stream) {
+  return forward_impl(h, in_nchw, out_nchw, B, H, W, dtype, workspace, workspace_bytes, stream, IoMode());
+}
+
+int esr_forward_u8(esr_handle* h, const uint8_t* in_hwc, uint8_t* out_hwc, int B, int H, int W, float data_range, int dtype,
+                   void* workspace, size_t workspace_bytes, void* stream) {
+  IoMode io;
+  io.u8 = true;
+  io.data_range = data_range;
+  return forward_impl(h, in_hwc, out_hwc, B, H, W, dtype, workspace, workspace_bytes, stream, io);
+}
+
 int esr_host_wait(esr_handle* h, long long ticket) {
   if (!h) return ESR_E_INVALID;
   if (!h->has_gpu) return fail(h, ESR_E_NOGPU, "no sm_100 device bound to this handle (the engine has no CPU fallback)");
@@ -835,8 +862,8 @@ int esr_host_wait(esr_handle* h, long long ticket) {
   return ESR_OK;
 }
 
-int esr_forward_host_async(esr_handle* h, const void* in_host, void* out_host, int B, int H, int W, int dtype,
-                           long long* ticket_out) {
+static int forward_host_impl(esr_handle* h, const void* in_host, void* out_host, int B, int H, int W, int dtype,
+                             long long* ticket_out, IoMode io) {
   if (!h) return ESR_E_INVALID;
   if (!h->finalized) return fail(h, ESR_E_STATE, "esr_forward_host before esr_finalize");
   if (!h->has_gpu) return fail(h, ESR_E_NOGPU, "no sm_100 device bound to this handle (the engine has no CPU fallback)");
@@ -844,8 +871,9 @@ int esr_forward_host_async(esr_handle* h, const void* in_host, void* out_host, i
   if (rc) return rc;
   if (!in_host || !out_host) return fail(h, ESR_E_INVALID, "null host pointer");
   CUDA_TRY(h, cudaSetDevice(h->device));
-  const size_t elt = dtype == ESR_DTYPE_F16 ? 2 : 4;
-  const size_t in_b = (size_t)B * 3 * H * W * elt, out_b = in_b * 16, ws_b = esr_workspace_bytes(h, B, H, W, dtype);
+  const size_t elt = io.u8 ? 1 : (dtype == ESR_DTYPE_F16 ? 2 : 4);
+  const size_t in_b = (size_t)B * 3 * H * W * elt, out_b = in_b * 16;
+  const size_t ws_b = io.u8 ? esr_workspace_bytes_u8(h, B, H, W, dtype) : esr_workspace_bytes(h, B, H, W, dtype);
   if (!h->s_cmp) {
     CUDA_TRY(h, cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
     CUDA_TRY(h, cudaStreamCreateWithFlags(&h->s_cmp, cudaStreamNonBlocking));
@@ -878,7 +906,7 @@ int esr_forward_host_async(esr_handle* h, const void* in_host, void* out_host, i
   CUDA_TRY(h, cudaMemcpyAsync(sl.d_in, in_host, in_b, cudaMemcpyHostToDevice, h->s_h2d));
   CUDA_TRY(h, cudaEventRecord(sl.ev_in, h->s_h2d));
   CUDA_TRY(h, cudaStreamWaitEvent(h->s_cmp, sl.ev_in, 0));
-  rc = esr_forward(h, sl.d_in, sl.d_out, B, H, W, dtype, h->h_ws, h->h_ws_sz, h->s_cmp);
+  rc = forward_impl(h, sl.d_in, sl.d_out, B, H, W, dtype, h->h_ws, h->h_ws_sz, h->s_cmp, io);
   if (rc) return rc;
   CUDA_TRY(h, cudaEventRecord(sl.ev_fwd, h->s_cmp));
   CUDA_TRY(h, cudaStreamWaitEvent(h->s_d2h, sl.ev_fwd, 0));
@@ -888,6 +916,27 @@ int esr_forward_host_async(esr_handle* h, const void* in_host, void* out_host, i
   sl.ticket = ticket;
   if (ticket_out) *ticket_out = ticket;
   return ESR_OK;
+}
+
+int esr_forward_host_async(esr_handle* h, const void* in_host, void* out_host, int B, int H, int W, int dtype,
+                           long long* ticket_out) {
+  return forward_host_impl(h, in_host, out_host, B, H, W, dtype, ticket_out, IoMode());
+}
+
+int esr_forward_host_u8_async(esr_handle* h, const uint8_t* in_host_hwc, uint8_t* out_host_hwc, int B, int H, int W,
+                              float data_range, int dtype, long long* ticket_out) {
+  IoMode io;
+  io.u8 = true;
+  io.data_range = data_range;
+  return forward_host_impl(h, in_host_hwc, out_host_hwc, B, H, W, dtype, ticket_out, io);
+}
+
+int esr_forward_host_u8(esr_handle* h, const uint8_t* in_host_hwc, uint8_t* out_host_hwc, int B, int H, int W, float data_range,
+                        int dtype) {
+  long long ticket = -1;
+  int rc = esr_forward_host_u8_async(h, in_host_hwc, out_host_hwc, B, H, W, data_range, dtype, &ticket);
+  if (rc) return rc;
+  return esr_host_wait(h, ticket);
 }
 
 int esr_forward_host(esr_handle* h, const void* in_host, void* out_host, int B, int H, int W, int dtype) {
@@ -904,20 +953,12 @@ static Plan* dry_plan(esr_handle* h, int B, int H, int W, int dtype, Plan& tmp) 
     if (p.B == B && p.H == H && p.W == W && p.dtype == dtype && p.gid == gid) return &p;
   // names only: one launch per op
   tmp.launches.clear();
-  bool prev_tc = false;
   for (auto& op : h->graphs[gid].g.ops) {
     static const char* kn[] = {"head", "bsrn_head", "conv_generic", "dwconv", "maxpool", "esa_apply", "conv_tc", "esa_apply2",
                                "esa_conv2_pool", "esa_chain"};
     std::string kname = kn[op.kind];
     if (op.kind == OP_CONV && !op.ps && h->graphs[gid].tables[op.tab].cin8 == 16 && h->graphs[gid].tables[op.tab].cout16 == 16)
       kname = "conv16";
-    const bool merge = op.kind == OP_CONV_TC && h->opt_chain && prev_tc;
-    prev_tc = op.kind == OP_CONV_TC;
-    if (merge) {
-      tmp.launches.back().name += " | " + op.name;
-      tmp.launches.back().flops += op_flops(op, B, H, W);
-      continue;
-    }
     tmp.launches.push_back(Launch{kname + ":" + op.name, nullptr, op_flops(op, B, H, W)});
   }
   return &tmp;
@@ -1008,7 +1049,6 @@ int esr_set_option(esr_handle* h, const char* key, int value) {
   else if (k == "tc_dbg_flags") h->opt_dbg_flags = value;
   else if (k == "tc_acc_slots") h->opt_acc_slots = value == 4 ? 4 : 2;
   else if (k == "use_pdl") h->opt_pdl = value ? 1 : 0;
-  else if (k == "tc_chain") h->opt_chain = value ? 1 : 0;
   else return fail(h, ESR_E_INVALID, "unknown option: " + k);
   drop_plans(h);
   return ESR_OK;
@@ -1047,7 +1087,6 @@ void esr_destroy(esr_handle* h) {
     if (h->s_cmp) cudaStreamDestroy(h->s_cmp);
     if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
     if (h->d_timeline) cudaFree(h->d_timeline);
-    if (h->d_gbar) cudaFree(h->d_gbar);
   }
   delete h;
 }

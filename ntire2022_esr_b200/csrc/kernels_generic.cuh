@@ -7,6 +7,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 namespace esr {
 
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
@@ -63,6 +65,25 @@ __device__ __forceinline__ float ldf(const __half* p) { return __half2float(*p);
 __device__ __forceinline__ void stf(float* p, float v) { *p = v; }
 __device__ __forceinline__ void stf(__half* p, float v) { *p = __float2half_rn(v); }
 
+// Network input accessor: planar NCHW fp32 / fp16 (the reference's tensor), or interleaved HWC uint8 with the
+// scaling of the reference's uint2tensor4 folded into the load (utils/utils_image.py:190-193:
+// float(u8) / (255 / data_range), `in_div` = 255 / data_range as fp32).  In the fp16 engine the scaled value
+// is rounded to fp16 first, so the result is identical to feeding uint2tensor4(img).half().
+template <typename TStore>
+__device__ __forceinline__ float ldin(const float* in, int b, int ci, int y, int x, int H, int W, float) {
+  return in[(((long long)b * 3 + ci) * H + y) * W + x];
+}
+template <typename TStore>
+__device__ __forceinline__ float ldin(const __half* in, int b, int ci, int y, int x, int H, int W, float) {
+  return __half2float(in[(((long long)b * 3 + ci) * H + y) * W + x]);
+}
+template <typename TStore>
+__device__ __forceinline__ float ldin(const uint8_t* in, int b, int ci, int y, int x, int H, int W, float in_div) {
+  const float v = (float)in[(((long long)b * H + y) * W + x) * 3 + ci] / in_div;
+  if (std::is_same<TStore, __half>::value) return __half2float(__float2half_rn(v));
+  return v;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Head: 3x3 conv (pad 1) on the NCHW 3-channel input, NHWC output with `cstore` channels
 // (channels >= cout are written as zero so padded lanes stay finite).
@@ -71,7 +92,7 @@ __device__ __forceinline__ void stf(__half* p, float v) { *p = __float2half_rn(v
 template <typename TIn, typename TOut, typename TAcc>
 __global__ void __launch_bounds__(256) k_head_conv(const TIn* __restrict__ in, TOut* __restrict__ out,
                                                    const float* __restrict__ w, const float* __restrict__ bias,
-                                                   int B, int H, int W, int out_stride, int cstore) {
+                                                   int B, int H, int W, int out_stride, int cstore, float in_div) {
   // block = up to 256 consecutive pixels of one image row; thread = 4 consecutive pixels x 16 output
   // channels (64 accumulators): every weight fetched from shared memory (broadcast LDS.128) feeds 4 FMAs
   // per lane, which is what keeps a CUDA-core convolution off the shared-memory bandwidth limit.
@@ -93,7 +114,7 @@ __global__ void __launch_bounds__(256) k_head_conv(const TIn* __restrict__ in, T
       const int xx = i % 258, r = (i / 258) % 3, ci = i / 774;
       const int gy = y + r - 1, gx = x0 + xx - 1;
       const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
-      xs[ci][r][xx] = ok ? ldf(in + (((long long)b * 3 + ci) * H + gy) * W + gx) : 0.f;
+      xs[ci][r][xx] = ok ? ldin<TOut>(in, b, ci, gy, gx, H, W, in_div) : 0.f;
     }
   }
   __syncthreads();
@@ -151,7 +172,7 @@ template <typename TIn, typename TOut, typename TAcc>
 __global__ void __launch_bounds__(128) k_bsrn_head(const TIn* __restrict__ in, TOut* __restrict__ out,
                                                    const float* __restrict__ wpw, const float* __restrict__ bpw,
                                                    const float* __restrict__ wdw, const float* __restrict__ bdw,
-                                                   int B, int H, int W, int out_stride, int cstore) {
+                                                   int B, int H, int W, int out_stride, int cstore, float in_div) {
   __shared__ float s_wpw[3 * 64], s_bpw[64], s_wdw[9 * 64], s_bdw[64];
   for (int i = threadIdx.x; i < 3 * 64; i += blockDim.x) s_wpw[i] = wpw[i];
   for (int i = threadIdx.x; i < 9 * 64; i += blockDim.x) s_wdw[i] = wdw[i];
@@ -175,7 +196,7 @@ __global__ void __launch_bounds__(128) k_bsrn_head(const TIn* __restrict__ in, T
       okt[ky * 3 + kx] = ok;
 #pragma unroll
       for (int ci = 0; ci < 3; ++ci)
-        xin[(ky * 3 + kx) * 3 + ci] = ok ? ldf(in + (((long long)b * 3 + ci) * H + yy) * W + xx) : 0.f;
+        xin[(ky * 3 + kx) * 3 + ci] = ok ? ldin<TOut>(in, b, ci, yy, xx, H, W, in_div) : 0.f;
     }
   TOut* o = out + pix * out_stride;
   for (int c0 = 0; c0 < cstore; c0 += 8) {
@@ -937,6 +958,28 @@ __global__ void __launch_bounds__(256) k_esa_chain(const EsaChainParams p) {
             *reinterpret_cast<float2*>(p.out + (((long long)b * p.H3 + gy) * p.W3 + gx) * 64 + g2 * 2) =
                 make_float2(acc[py * 2 + px][0], acc[py * 2 + px][1]);
         }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// tensor2uint of the reference (utils/utils_image.py:204-208) on the device: planar NCHW output of the network
+// -> interleaved HWC uint8: clamp to [0, data_range], * 255 / data_range in fp32, round half to even (np.round).
+// thread = one output pixel (three coalesced planar reads, three adjacent byte writes).
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_tensor2uint(const T* __restrict__ in, uint8_t* __restrict__ out, int B, int Ho,
+                                                     int Wo, float data_range) {
+  pdl_wait();
+  const long long plane = (long long)Ho * Wo, total = (long long)B * plane;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / plane, r = i - b * plane;
+    const T* src = in + b * 3 * plane + r;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float v = fminf(fmaxf(ldf(src + c * plane), 0.f), data_range);
+      v = __fdiv_rn(__fmul_rn(v, 255.0f), data_range);
+      out[i * 3 + c] = (uint8_t)rintf(v);
     }
   }
 }

@@ -91,6 +91,18 @@ class B200SRModel(nn.Module):
         return self.engine(x.device).forward(x)
 
 
+def forward_uint8(img_lr, model: B200SRModel, data_range: float, half: bool = True):
+    """The per-image body of the reference's run() (test_demo.py:422-434) in one device call:
+    `util.tensor2uint(forward(util.uint2tensor4(img_lr, data_range).to(device), model), data_range)`.
+
+    img_lr: uint8 (H,W,3) or (B,H,W,3), a numpy array (host path: copies in, runs, copies out) or a CUDA tensor.
+    Returns uint8 (4H,4W,3) / (B,4H,4W,3) of the same kind."""
+    if isinstance(img_lr, torch.Tensor):
+        return model.engine(img_lr.device).forward_uint8(img_lr, data_range, half=half)
+    dev = next(model.parameters()).device
+    return model.engine(dev).forward_host_uint8(img_lr, data_range, half=half)
+
+
 def _find_checkpoint(fname: str) -> str:
     # the reference resolves 'model_zoo/<file>' against the CWD (test_demo.py:21,28,56,154)
     cands = [os.path.join("model_zoo", fname)]

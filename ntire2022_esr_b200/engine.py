@@ -141,6 +141,56 @@ class Engine:
                                     self._ws.numel(), stream))
         return out
 
+    def forward_uint8(self, img, data_range: float, half: bool = True, out=None):
+        """img: CUDA uint8 tensor (B,H,W,3) or (H,W,3) -> uint8 (B,4H,4W,3) / (4H,4W,3).
+
+        One call for the reference's uint2tensor4 -> forward -> tensor2uint (test_demo.py:423-434)."""
+        import torch
+
+        if not img.is_cuda or img.dtype != torch.uint8:
+            raise EsrError(_cabi.E_INVALID, "expected a CUDA uint8 tensor (the engine has no CPU fallback)")
+        squeeze = img.dim() == 3
+        if squeeze:
+            img = img.unsqueeze(0)
+        if img.dim() != 4 or img.shape[3] != 3:
+            raise EsrError(_cabi.E_INVALID, f"expected (B,H,W,3), got {tuple(img.shape)}")
+        img = img.contiguous()
+        B, H, W, _ = img.shape
+        dt = _cabi.DTYPE_F16 if half else _cabi.DTYPE_F32
+        need = lib.esr_workspace_bytes_u8(self._h, B, H, W, dt)
+        if need == 0:
+            raise EsrError(_cabi.E_INVALID, (lib.esr_last_error(self._h) or b"").decode())
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=img.device)
+        if out is None:
+            out = torch.empty((B, 4 * H, 4 * W, 3), dtype=torch.uint8, device=img.device)
+        stream = torch.cuda.current_stream(img.device).cuda_stream
+        self._check(lib.esr_forward_u8(self._h, img.data_ptr(), out.data_ptr(), B, H, W, float(data_range), dt,
+                                       self._ws.data_ptr(), self._ws.numel(), stream))
+        return out[0] if squeeze else out
+
+    def forward_host_uint8(self, img: np.ndarray, data_range: float, half: bool = True) -> np.ndarray:
+        """Host uint8 (B,H,W,3) / (H,W,3) in, host uint8 out (esr_forward_host_u8)."""
+        img = np.ascontiguousarray(img)
+        if img.dtype != np.uint8:
+            raise EsrError(_cabi.E_INVALID, f"unsupported dtype {img.dtype}")
+        squeeze = img.ndim == 3
+        if squeeze:
+            img = img[None]
+        if img.ndim != 4 or img.shape[3] != 3:
+            raise EsrError(_cabi.E_INVALID, f"expected (B,H,W,3), got {img.shape}")
+        B, H, W, _ = img.shape
+        out = np.empty((B, 4 * H, 4 * W, 3), dtype=np.uint8)
+        self._check(lib.esr_forward_host_u8(self._h, img.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p),
+                                            B, H, W, float(data_range), _cabi.DTYPE_F16 if half else _cabi.DTYPE_F32))
+        return out[0] if squeeze else out
+
+    def forward_host_u8_async_ptr(self, in_ptr: int, out_ptr: int, B: int, H: int, W: int, data_range: float, dt: int) -> int:
+        t = ctypes.c_longlong(-1)
+        self._check(lib.esr_forward_host_u8_async(self._h, in_ptr, out_ptr, B, H, W, float(data_range), dt, ctypes.byref(t)))
+        return t.value
+
     def forward_host(self, x: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
         """x: host array (B,3,H,W) float32 / float16; copies in, runs, copies out, synchronises."""
         x = np.ascontiguousarray(x)

@@ -246,3 +246,32 @@ def test_div2k_shaped_input_fp16_finite_and_close():
     assert torch.isfinite(y16).all()
     mse = torch.mean((y32 - y16) ** 2).item() / 255.0 ** 2
     assert 10 * np.log10(1.0 / mse) >= FP16_PSNR_BAR
+
+
+@pytest.mark.parametrize("mid,arch", ARCHS)
+def test_uint8_io_path_matches_reference_pre_and_post_processing(mid, arch):
+    """esr_forward_u8 = util.tensor2uint(forward(util.uint2tensor4(img))) (test_demo.py:423-434).  Integer output:
+    bit-exact against the oracle's tensor2uint of this engine's own float output for the oracle's uint2tensor4
+    input (fp32 and fp16 engines), device and host entry points, batch of 2; and against the reference's own
+    uint8 golden (fp32 engine, <= 1e-3 of the pixels differ by one LSB: the reference's fp32-vs-fp64 level)."""
+    from ntire2022_esr_b200 import forward_uint8
+
+    img = np.load(os.path.join(ROOT, "tests", "golden", "test_bmp.npz"))["img"]
+    dr = O.MODELS[mid]["data_range"]
+    m = _model(mid)
+    small = np.ascontiguousarray(np.stack([img[:40, :56], img[100:140, 60:116]]))     # (2, 40, 56, 3)
+    for half in (False, True):
+        x = np.concatenate([O.uint2tensor4(s, dr) for s in small])
+        y = _run(mid, x.astype(np.float16) if half else x)
+        want = np.stack([O.tensor2uint(y[i:i + 1], dr) for i in range(2)])
+        got_dev = forward_uint8(torch.from_numpy(small).cuda(), m, dr, half=half).cpu().numpy()
+        got_host = forward_uint8(small, m, dr, half=half)
+        assert got_dev.shape == (2, 160, 224, 3) and got_dev.dtype == np.uint8
+        assert np.array_equal(got_dev, want), (arch, half, int((got_dev != want).sum()))
+        assert np.array_equal(got_host, want)
+        one = forward_uint8(torch.from_numpy(small[1]).cuda(), m, dr, half=half).cpu().numpy()   # (H,W,3) form
+        assert np.array_equal(one, want[1])
+    z = np.load(os.path.join(ROOT, "tests", "golden", f"ref_{arch}_256.npz"))
+    full = forward_uint8(torch.from_numpy(np.ascontiguousarray(img)).cuda(), m, dr, half=False).cpu().numpy()
+    assert full.shape == (1024, 1024, 3)
+    assert (full[::8, ::8] != z["uint8_sub"]).mean() < 1e-3

@@ -35,7 +35,6 @@ def main():
     ap.add_argument("--slots", type=int, default=4)
     ap.add_argument("--nocheck", type=int, default=0)
     ap.add_argument("--pdl", type=int, default=0)
-    ap.add_argument("--chain", type=int, default=1)
     a = ap.parse_args()
     import torch
     from ntire2022_esr_b200 import Engine
@@ -55,7 +54,6 @@ def main():
     eng.set_option("tc_dbg_flags", a.dbg)
     eng.set_option("tc_acc_slots", a.slots)
     eng.set_option("use_pdl", a.pdl)
-    eng.set_option("tc_chain", a.chain)
     eng.load_state_dict(w)
     if a.host:
         y = eng.forward_host(x)
@@ -109,8 +107,7 @@ def extras(a, eng, xt, yt):
         for name, fl, ms in eng.profile_launches(xt, yt, reps=a.profile):
             print(f"PROF {name:45s} {ms * 1e3:8.2f} us  {fl / 1e9:7.3f} GF  {fl / (ms * 1e-3) / 1e12 if ms > 0 else 0:7.1f} TF/s", flush=True)
     if a.timeline:
-        names = [m for n in eng.launch_names(a.batch, a.size[0], a.size[1], 1) if n.startswith("conv_tc")
-                 for m in n[len("conv_tc:"):].split(" | ")]   # timeline records are per layer of a chain
+        names = [n for n in eng.launch_names(a.batch, a.size[0], a.size[1], 1) if n.startswith("conv_tc")]
         eng.set_option("use_graph", 0)
         for _ in range(3):
             eng.forward(xt, out=yt)
