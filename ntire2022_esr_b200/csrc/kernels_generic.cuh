@@ -648,7 +648,7 @@ struct EsaApply2Params {
   int B, H, W, cg8;   // cg8: 8-channel groups per pixel
 };
 template <typename T>
-__global__ void __launch_bounds__(256) k_esa_apply2(const EsaApply2Params p) {
+__global__ void __launch_bounds__(256, 4) k_esa_apply2(const EsaApply2Params p) {
   pdl_wait();
   const long long total = (long long)p.B * p.H * p.W * p.cg8;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {

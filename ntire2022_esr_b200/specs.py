@@ -120,7 +120,7 @@ def bsrn_spec(nf=48, nb=5):
 SPECS = {"imdn": imdn_spec, "rfdn": rfdn_spec, "rlfn": rlfn_spec, "bsrn": bsrn_spec}
 
 # model registry: id -> (arch, ctor kwargs, checkpoint file, state-dict wrapper key, name, data_range)
-# (test_demo.py:17-23 IMDN, :24-30 RFDN, :52-58 RLFN, :150-157 BSRN, :203-209 IMDN nb=7)
+# (test_demo.py:17-23 IMDN, :24-30 RFDN, :52-58 RLFN, :150-157 BSRN, :175-181 RFDN40, :203-209 IMDN nb=7)
 REGISTRY: Dict[int, dict] = {
     -1: dict(arch="imdn", kwargs=dict(nf=64, nblocks=8), file="imdn_baseline.pth", wrap=None,
              name="IMDN_baseline", data_range=1.0),
@@ -130,4 +130,7 @@ REGISTRY: Dict[int, dict] = {
             name="RLFN", data_range=255.0),
     18: dict(arch="bsrn", kwargs=dict(nf=48, nblocks=5), file="team18_bsrn.pth", wrap="params",
              name="RFDNFINALB5", data_range=1.0),
+    # RFDN40 (models/team22_rep_rfdn.py:134-165, test_demo.py:175-181): the RFDN graph at nf = 40, data range 1
+    22: dict(arch="rfdn", kwargs=dict(nf=40, nblocks=4), file="team22_rep_rfdn.pth", wrap=None,
+             name="RFDN40", data_range=1.0),
 }

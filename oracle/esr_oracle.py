@@ -314,6 +314,8 @@ MODELS = {
     0: dict(arch="rfdn", name="00_RFDN_baseline", data_range=255.0, weights="rfdn_baseline", fn=rfdn_forward),
     4: dict(arch="rlfn", name="04_RLFN", data_range=255.0, weights="team04_rlfn", fn=rlfn_forward),
     18: dict(arch="bsrn", name="18_RFDNFINALB5", data_range=1.0, weights="team18_bsrn", fn=bsrn_forward),
+    # id 22: the same RFDN graph at nf = 40 (models/team22_rep_rfdn.py:101-165, test_demo.py:175-181)
+    22: dict(arch="rfdn", name="22_RFDN40", data_range=1.0, weights="team22_rep_rfdn", fn=rfdn_forward),
 }
 FORWARD = {"imdn": imdn_forward, "rfdn": rfdn_forward, "rlfn": rlfn_forward, "bsrn": bsrn_forward}
 

@@ -11,6 +11,8 @@ matplotlib, force map_location, chdir to the reference root) and writes, next to
   ref_<arch>_256.npz      reference output on test.bmp (256x256): crops, strided subsample, stats
   ref_rfdn_tiled.npz      reference tiled forward (tile=32, overlap=8) on a 48x40 input
 
+    python tests/golden/make_golden.py 22         # only the listed model ids
+
 Nothing at test/bench time reads /root/reference; these files are the pin.
 """
 import copy
@@ -38,16 +40,21 @@ from utils import utils_image as util  # noqa: E402
 torch.set_num_threads(os.cpu_count())
 
 MODELS = {-1: ("imdn", "imdn_baseline.pth"), 0: ("rfdn", "rfdn_baseline.pth"),
-          4: ("rlfn", "team04_rlfn.pth"), 18: ("bsrn", "team18_bsrn.pth")}
+          4: ("rlfn", "team04_rlfn.pth"), 18: ("bsrn", "team18_bsrn.pth"),
+          22: ("rfdn40", "team22_rep_rfdn.pth")}   # id 22 = RFDN at nf = 40 (test_demo.py:175-181): same graph, SURVEY row N1
 SMALL_SIZES = [(15, 15), (24, 20), (33, 47), (64, 64)]
 CROPS = [(0, 0), (0, 992), (992, 0), (992, 992), (500, 500), (0, 480), (700, 0), (301, 777)]
 
 
 def main():
+    only = [int(a) for a in sys.argv[1:]]   # optional: model ids to (re)generate; default = all
     os.makedirs(os.path.join(HERE, "weights"), exist_ok=True)
     img = util.imread_uint(os.path.join(REF, "utils", "test.bmp"), n_channels=3)
-    np.savez_compressed(os.path.join(HERE, "test_bmp.npz"), img=img)
+    if not only:
+        np.savez_compressed(os.path.join(HERE, "test_bmp.npz"), img=img)
     for mid, (arch, fname) in MODELS.items():
+        if only and mid not in only:
+            continue
         args = types.SimpleNamespace(model_id=mid)
         model, name, data_range, tile = test_demo.select_model(args, torch.device("cpu"))
         sd = {k: v.detach().cpu().numpy().astype(np.float32) for k, v in model.state_dict().items()}

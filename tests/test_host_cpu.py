@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
 
     header = open(os.path.join(ROOT, "include", "esr_b200.h")).read()
     header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
-    declared = set(re.findall(r"\b(esr_[a-z_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(esr_[a-z0-9_]+)\s*\(", header))
     assert declared, "no declarations parsed"
     bound = {s[0] for s in _cabi.SYMBOLS}
     assert declared == bound, (declared ^ bound)

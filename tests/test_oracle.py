@@ -8,13 +8,14 @@ import pytest
 from oracle import esr_oracle as O
 
 ARCHS = [(-1, "imdn"), (0, "rfdn"), (4, "rlfn"), (18, "bsrn")]
+GOLDEN = ARCHS + [(22, "rfdn40")]   # (model id, golden file tag); id 22 = the RFDN graph at nf = 40
 
 
 def _weights(golden_dir, mid):
     return O.load_weights(os.path.join(golden_dir, "weights", O.MODELS[mid]["weights"] + ".npz"))
 
 
-@pytest.mark.parametrize("mid,arch", ARCHS)
+@pytest.mark.parametrize("mid,arch", GOLDEN)
 def test_oracle_matches_reference_small_inputs(golden_dir, mid, arch):
     z = np.load(os.path.join(golden_dir, f"ref_{arch}_small.npz"))
     dr = float(z["data_range"])
@@ -23,7 +24,7 @@ def test_oracle_matches_reference_small_inputs(golden_dir, mid, arch):
     w = _weights(golden_dir, mid)
     for i in range(4):
         x, y = z[f"x{i}"], z[f"y{i}"]
-        yo = O.forward(arch, w, x, dtype=np.float64)
+        yo = O.forward(O.MODELS[mid]["arch"], w, x, dtype=np.float64)
         assert yo.shape == y.shape == (x.shape[0], 3, 4 * x.shape[2], 4 * x.shape[3])
         # the golden is the reference's fp32 output; its own fp32-vs-fp64 noise is <= 1.3e-6 of range
         # on test.bmp and up to 5.7e-6 on uniform-noise inputs (BSRN, 64x64)

@@ -18,6 +18,7 @@ from oracle import esr_oracle as O  # noqa: E402
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ARCHS = [(-1, "imdn"), (0, "rfdn"), (4, "rlfn"), (18, "bsrn")]
+GOLDEN = ARCHS + [(22, "rfdn40")]   # (model id, golden file tag); id 22 = the RFDN graph at nf = 40
 FP32_BAR = 1e-5
 FP16_PSNR_BAR = 60.0
 
@@ -58,7 +59,7 @@ def test_extension_is_loaded_and_gpu_is_blackwell():
     assert _cabi.lib.esr_device_ok(0) == 1, "needs an sm_100 GPU"
 
 
-@pytest.mark.parametrize("mid,arch", ARCHS)
+@pytest.mark.parametrize("mid,arch", GOLDEN)
 def test_fp32_matches_reference_golden_small(mid, arch):
     z = np.load(os.path.join(ROOT, "tests", "golden", f"ref_{arch}_small.npz"))
     dr = float(z["data_range"])
@@ -69,7 +70,7 @@ def test_fp32_matches_reference_golden_small(mid, arch):
         assert err <= FP32_BAR, (arch, i, err)
 
 
-@pytest.mark.parametrize("mid,arch", ARCHS)
+@pytest.mark.parametrize("mid,arch", GOLDEN)
 def test_fp32_matches_reference_golden_test_bmp_256(mid, arch):
     z = np.load(os.path.join(ROOT, "tests", "golden", f"ref_{arch}_256.npz"))
     img = np.load(os.path.join(ROOT, "tests", "golden", "test_bmp.npz"))["img"]
@@ -84,7 +85,7 @@ def test_fp32_matches_reference_golden_test_bmp_256(mid, arch):
     assert (u8 != z["uint8_sub"]).mean() < 1e-3
 
 
-@pytest.mark.parametrize("mid,arch", ARCHS)
+@pytest.mark.parametrize("mid,arch", GOLDEN)
 def test_fp16_tcgen05_path_vs_oracle(mid, arch):
     dr = O.MODELS[mid]["data_range"]
     rng = np.random.default_rng(5)
@@ -92,7 +93,7 @@ def test_fp16_tcgen05_path_vs_oracle(mid, arch):
     for shape in [(1, 3, 64, 64), (2, 3, 33, 47), (1, 3, 15, 15), (1, 3, 130, 260)]:
         x = (rng.random(shape, dtype=np.float32) * dr).astype(np.float16)
         y = _run(mid, x)
-        ref = O.forward(arch, w, x.astype(np.float32), dtype=np.float32)
+        ref = O.forward(O.MODELS[mid]["arch"], w, x.astype(np.float32), dtype=np.float32)
         assert np.isfinite(y).all()
         p = _psnr(y, ref, dr)
         assert p >= FP16_PSNR_BAR, (arch, shape, p)
@@ -248,7 +249,7 @@ def test_div2k_shaped_input_fp16_finite_and_close():
     assert 10 * np.log10(1.0 / mse) >= FP16_PSNR_BAR
 
 
-@pytest.mark.parametrize("mid,arch", ARCHS)
+@pytest.mark.parametrize("mid,arch", GOLDEN)
 def test_uint8_io_path_matches_reference_pre_and_post_processing(mid, arch):
     """esr_forward_u8 = util.tensor2uint(forward(util.uint2tensor4(img))) (test_demo.py:423-434).  Integer output:
     bit-exact against the oracle's tensor2uint of this engine's own float output for the oracle's uint2tensor4
