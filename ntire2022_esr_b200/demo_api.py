@@ -172,8 +172,10 @@ def forward(img_lq, model, tile=None, tile_overlap=32, scale=4):
     coords = [(y0, x0) for y0 in ys for x0 in xs]
     acc = torch.zeros(b, c, h * scale, w * scale, dtype=img_lq.dtype, device=img_lq.device)
     cover = torch.zeros_like(acc)
-    for k0 in range(0, len(coords), TILE_BATCH):
-        chunk = coords[k0:k0 + TILE_BATCH]
+    # any other nn.Module is evaluated tile by tile exactly like the reference (it may couple the images of a batch)
+    per_call = TILE_BATCH if isinstance(model, B200SRModel) else 1
+    for k0 in range(0, len(coords), per_call):
+        chunk = coords[k0:k0 + per_call]
         # (tiles, b, c, tile, tile) -> one batch of len(chunk) * b images
         patches = torch.stack([img_lq[..., y0:y0 + tile, x0:x0 + tile] for y0, x0 in chunk])
         out = model(patches.reshape(len(chunk) * b, c, tile, tile).contiguous())
