@@ -25,8 +25,9 @@ extern "C" {
 
 typedef struct esr_engine esr_handle;
 
-/* architectures: the four networks SURVEY.md section 8(a) puts on the hot path */
-enum { ESR_ARCH_IMDN = 0, ESR_ARCH_RFDN = 1, ESR_ARCH_RLFN = 2, ESR_ARCH_BSRN = 3 };
+/* architectures: the four networks SURVEY.md section 8(a) puts on the hot path, plus the pruned RFDN of row N1
+ * (models/team40_rfdn_pruned.py: RFDBs without the inner residual adds, ESA width 12) */
+enum { ESR_ARCH_IMDN = 0, ESR_ARCH_RFDN = 1, ESR_ARCH_RLFN = 2, ESR_ARCH_BSRN = 3, ESR_ARCH_RFDN_PRUNED = 4 };
 /* I/O + storage dtype of a forward call (math is fp32-accumulate in both) */
 enum { ESR_DTYPE_F32 = 0, ESR_DTYPE_F16 = 1 };
 enum {
@@ -39,8 +40,8 @@ enum {
 };
 
 /* Replaces the module constructors at test_demo.py:22 (IMDN(nc=64, nb=8)), :29 (RFDN()),
- * :57 (RLFN_cut()) and :155 (BSRN(num_feat=48, num_block=5)).  nf / nblocks <= 0 pick those
- * defaults.  `device` is the CUDA ordinal the handle is bound to. */
+ * :57 (RLFN_cut()), :155 (BSRN(num_feat=48, num_block=5)), :180 (RFDN40() = ESR_ARCH_RFDN with nf = 40) and
+ * :307 (RFDNPrune(nf=40)).  nf / nblocks <= 0 pick those defaults.  `device` is the CUDA ordinal the handle is bound to. */
 int esr_create(esr_handle** out, int arch, int nf, int nblocks, int device);
 
 /* Replaces `model.load_state_dict(torch.load(path), strict=True)` (test_demo.py:23,30,58,157):

@@ -17,7 +17,7 @@
 
 namespace esr {
 
-static const int kNumArch = 4;
+static const int kNumArch = 5;
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -104,6 +104,7 @@ static std::string build_dev_graph(Engine& e, int gid) {
   const bool tc = gid == 1;
   switch (e.arch) {
     case ESR_ARCH_RFDN: gb.build_rfdn(e.nf, e.nblocks, tc); break;
+    case ESR_ARCH_RFDN_PRUNED: gb.build_rfdn(e.nf, e.nblocks, tc, /*residual=*/false, /*esa_f=*/12); break;
     case ESR_ARCH_RLFN: gb.build_rlfn(e.nf, e.nblocks, tc); break;
     case ESR_ARCH_IMDN: gb.build_imdn(e.nf, e.nblocks, tc); break;
     case ESR_ARCH_BSRN: gb.build_bsrn(e.nf, e.nblocks, tc); break;
@@ -606,7 +607,7 @@ static int build_plan(Engine* e, Plan& pl) {
 static int check_shape(Engine* e, int B, int H, int W, int dtype) {
   if (B < 1 || H < 1 || W < 1) return fail(e, ESR_E_INVALID, "B, H, W must be positive");
   if (dtype != ESR_DTYPE_F32 && dtype != ESR_DTYPE_F16) return fail(e, ESR_E_INVALID, "unknown dtype");
-  if (e->arch != ESR_ARCH_IMDN) {
+  if (e->arch != ESR_ARCH_IMDN) {   // every other network has an ESA branch
     int H2, W2, H3, W3;
     esa_dims(H, W, H2, W2, H3, W3);
     if (H2 < 7 || W2 < 7 || H < 3 || W < 3)
@@ -690,11 +691,12 @@ int esr_create(esr_handle** out, int arch, int nf, int nblocks, int device) {
   if (arch < 0 || arch >= kNumArch) return ESR_E_INVALID;
   esr_engine* e = new esr_engine();
   e->arch = arch;
-  static const int def_nf[4] = {64, 50, 46, 48}, def_nb[4] = {8, 4, 4, 5};
+  static const int def_nf[kNumArch] = {64, 50, 46, 48, 40}, def_nb[kNumArch] = {8, 4, 4, 5, 4};
   e->nf = nf > 0 ? nf : def_nf[arch];
   e->nblocks = nblocks > 0 ? nblocks : def_nb[arch];
   const bool ok_cfg = (arch == ESR_ARCH_IMDN && e->nf == 64 && e->nblocks <= 16) ||
-                      (arch == ESR_ARCH_RFDN && e->nf >= 16 && e->nf <= 64 && e->nf % 4 == 0 + 0 && e->nblocks <= 4) ||
+                      ((arch == ESR_ARCH_RFDN || arch == ESR_ARCH_RFDN_PRUNED) && e->nf >= 16 && e->nf <= 64 && e->nf % 4 == 0 &&
+                       e->nblocks <= 4) ||
                       (arch == ESR_ARCH_RLFN && e->nf >= 16 && e->nf <= 48 && e->nblocks <= 8) ||
                       (arch == ESR_ARCH_BSRN && e->nf == 48 && e->nblocks <= 5);
   if (!ok_cfg && !(arch == ESR_ARCH_RFDN && e->nf == 50)) {

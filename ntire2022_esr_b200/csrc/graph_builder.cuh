@@ -481,8 +481,10 @@ struct GraphBuilder {
   // =============================================================================================
   // RFDN
   // =============================================================================================
-  void build_rfdn(int nf, int nblocks, bool tc) {
-    const int dc = nf / 2, f = nf / 4;
+  // residual = false, esa_f = 12: the pruned RFDN of models/team40_rfdn_pruned.py:103-166 (RFDBs without the inner
+  // `+ input` adds, ESA width fixed at 50 // 4)
+  void build_rfdn(int nf, int nblocks, bool tc, bool residual = true, int esa_f = 0) {
+    const int dc = nf / 2, f = esa_f > 0 ? esa_f : nf / 4;
     const float sl = 0.05f;
     const int fea = buf(BK_FULL, 64), cat = buf(BK_FULL, 64 * nblocks), t0 = buf(BK_FULL, 64), t1 = buf(BK_FULL, 64),
               dist = buf(BK_FULL, 128), c5o = buf(BK_FULL, 64), esa = buf(BK_FULL, tc ? 16 : 32);
@@ -517,12 +519,12 @@ struct GraphBuilder {
         if (!tc) {
           conv_op(p + n + "_d", dense_table(md, 64, 32, pos_id(), pos_id()), cur, curc, dist, 32 * s, ACT_LRELU, sl);
           OpDecl& o = conv_op(p + n + "_r", dense_table(mr, 64, 64, pos_id(), pos_id()), cur, curc, nxt, 0, ACT_LRELU, sl);
-          o.res = cur; o.res_coff = curc; o.res_after = 0;
+          if (residual) { o.res = cur; o.res_coff = curc; o.res_after = 0; }
         } else {
           TcBuild b = tc_begin(1, 96, {{0, 64}, {64, 32}});
           tc_add(b, mr, pos_id(), pos_id());
           tc_add(b, md, pos_id(), pos_id(64));
-          tc_add_identity(b, nf);
+          if (residual) tc_add_identity(b, nf);
           tc_emit(p + n + "_r+d", b, cur, curc, 1,
                   {tc_group(0, 64, ACT_LRELU, sl, nxt, 0), tc_group(64, 32, ACT_LRELU, sl, dist, 32 * s)});
         }

@@ -14,7 +14,8 @@ import numpy as np
 from . import _cabi
 from ._cabi import EsrError, lib
 
-ARCHS = {"imdn": _cabi.ARCH_IMDN, "rfdn": _cabi.ARCH_RFDN, "rlfn": _cabi.ARCH_RLFN, "bsrn": _cabi.ARCH_BSRN}
+ARCHS = {"imdn": _cabi.ARCH_IMDN, "rfdn": _cabi.ARCH_RFDN, "rlfn": _cabi.ARCH_RLFN, "bsrn": _cabi.ARCH_BSRN,
+         "rfdn_pruned": _cabi.ARCH_RFDN_PRUNED}
 
 
 def _as_f32_numpy(v) -> np.ndarray:

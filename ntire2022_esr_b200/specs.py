@@ -39,9 +39,10 @@ def imdn_spec(nc=64, nb=8) -> "OrderedDict[str, Tuple[int, ...]]":
     return d
 
 
-def rfdn_spec(nf=50, nb=4):
+def rfdn_spec(nf=50, nb=4, f=None):
     d = OrderedDict()
-    dc, f = nf // 2, nf // 4
+    dc = nf // 2
+    f = f or nf // 4
     _conv(d, "fea_conv", nf, 3, 3)
     for b in range(1, nb + 1):
         p = f"B{b}."
@@ -117,10 +118,15 @@ def bsrn_spec(nf=48, nb=5):
     return d
 
 
-SPECS = {"imdn": imdn_spec, "rfdn": rfdn_spec, "rlfn": rlfn_spec, "bsrn": bsrn_spec}
+def rfdn_pruned_spec(nf=40, nb=4):
+    """models/team40_rfdn_pruned.py:103-115,133-146: RFDN shapes with the ESA width fixed at 50 // 4 = 12."""
+    return rfdn_spec(nf, nb, f=12)
+
+
+SPECS = {"imdn": imdn_spec, "rfdn": rfdn_spec, "rlfn": rlfn_spec, "bsrn": bsrn_spec, "rfdn_pruned": rfdn_pruned_spec}
 
 # model registry: id -> (arch, ctor kwargs, checkpoint file, state-dict wrapper key, name, data_range)
-# (test_demo.py:17-23 IMDN, :24-30 RFDN, :52-58 RLFN, :150-157 BSRN, :175-181 RFDN40, :203-209 IMDN nb=7)
+# (test_demo.py:17-23 IMDN, :24-30 RFDN, :52-58 RLFN, :150-157 BSRN, :175-181 RFDN40, :203-209 IMDN nb=7, :302-308 pruned RFDN)
 REGISTRY: Dict[int, dict] = {
     -1: dict(arch="imdn", kwargs=dict(nf=64, nblocks=8), file="imdn_baseline.pth", wrap=None,
              name="IMDN_baseline", data_range=1.0),
@@ -133,4 +139,8 @@ REGISTRY: Dict[int, dict] = {
     # RFDN40 (models/team22_rep_rfdn.py:134-165, test_demo.py:175-181): the RFDN graph at nf = 40, data range 1
     22: dict(arch="rfdn", kwargs=dict(nf=40, nblocks=4), file="team22_rep_rfdn.pth", wrap=None,
              name="RFDN40", data_range=1.0),
+    # pruned RFDN (models/team40_rfdn_pruned.py:186-213, test_demo.py:302-308): nf = 40, RFDBs without the inner
+    # residual adds, ESA width 12
+    40: dict(arch="rfdn_pruned", kwargs=dict(nf=40, nblocks=4), file="team40_rfdn_pruned.pth", wrap=None,
+             name="RFDNPrune", data_range=255.0),
 }

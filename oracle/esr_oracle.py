@@ -151,34 +151,42 @@ def _esa_rfdn(wt, p, x):
     return x * sigmoid(c4)
 
 
-def _rfdb(wt, p, x, slope=0.05):
-    """RFDB.forward, models/rfdn_baseline/block.py:148-166 (residual add BEFORE the activation)."""
+def _rfdb(wt, p, x, slope=0.05, residual=True):
+    """RFDB.forward, models/rfdn_baseline/block.py:148-166 (residual add BEFORE the activation);
+    residual=False: the pruned variant without the inner adds, models/team40_rfdn_pruned.py:148-166."""
+    k = 1.0 if residual else 0.0
     d1 = leaky_relu(_conv(wt, p + "c1_d", x), slope)
-    r1 = leaky_relu(_conv(wt, p + "c1_r", x, padding=1) + x, slope)
+    r1 = leaky_relu(_conv(wt, p + "c1_r", x, padding=1) + k * x, slope)
     d2 = leaky_relu(_conv(wt, p + "c2_d", r1), slope)
-    r2 = leaky_relu(_conv(wt, p + "c2_r", r1, padding=1) + r1, slope)
+    r2 = leaky_relu(_conv(wt, p + "c2_r", r1, padding=1) + k * r1, slope)
     d3 = leaky_relu(_conv(wt, p + "c3_d", r2), slope)
-    r3 = leaky_relu(_conv(wt, p + "c3_r", r2, padding=1) + r2, slope)
+    r3 = leaky_relu(_conv(wt, p + "c3_r", r2, padding=1) + k * r2, slope)
     r4 = leaky_relu(_conv(wt, p + "c4", r3, padding=1), slope)
     out = np.concatenate([d1, d2, d3, r4], axis=1)
     return _esa_rfdn(wt, p + "esa.", _conv(wt, p + "c5", out))
 
 
-def rfdn_forward(weights, x, dtype=np.float32, return_intermediates=False):
-    """RFDN.forward, models/rfdn_baseline/RFDN.py:29-41."""
+def rfdn_forward(weights, x, dtype=np.float32, return_intermediates=False, residual=True):
+    """RFDN.forward, models/rfdn_baseline/RFDN.py:29-41 (channel counts come from the weights)."""
     wt = _cast(weights, dtype)
     x = np.asarray(x, dtype=dtype)
     fea = _conv(wt, "fea_conv", x, padding=1)
-    b1 = _rfdb(wt, "B1.", fea)
-    b2 = _rfdb(wt, "B2.", b1)
-    b3 = _rfdb(wt, "B3.", b2)
-    b4 = _rfdb(wt, "B4.", b3)
+    b1 = _rfdb(wt, "B1.", fea, residual=residual)
+    b2 = _rfdb(wt, "B2.", b1, residual=residual)
+    b3 = _rfdb(wt, "B3.", b2, residual=residual)
+    b4 = _rfdb(wt, "B4.", b3, residual=residual)
     out_b = leaky_relu(_conv(wt, "c.0", np.concatenate([b1, b2, b3, b4], axis=1)), 0.05)
     out_lr = _conv(wt, "LR_conv", out_b, padding=1) + fea
     y = pixel_shuffle(_conv(wt, "upsampler.0", out_lr, padding=1), 4)
     if return_intermediates:
         return y, dict(fea=fea, b1=b1, b2=b2, b3=b3, b4=b4, out_b=out_b, out_lr=out_lr)
     return y
+
+
+def rfdn_pruned_forward(weights, x, dtype=np.float32):
+    """RFDN.forward of models/team40_rfdn_pruned.py:186-213: the RFDN graph with RFDBs that drop the inner
+    residual adds (:148-166) and an ESA of fixed width 12 (:106); the widths come from the weights."""
+    return rfdn_forward(weights, x, dtype=dtype, residual=False)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -316,8 +324,11 @@ MODELS = {
     18: dict(arch="bsrn", name="18_RFDNFINALB5", data_range=1.0, weights="team18_bsrn", fn=bsrn_forward),
     # id 22: the same RFDN graph at nf = 40 (models/team22_rep_rfdn.py:101-165, test_demo.py:175-181)
     22: dict(arch="rfdn", name="22_RFDN40", data_range=1.0, weights="team22_rep_rfdn", fn=rfdn_forward),
+    # id 40: pruned RFDN, nf = 40, no inner residuals, ESA width 12 (test_demo.py:302-308)
+    40: dict(arch="rfdn_pruned", name="40_RFDNPrune", data_range=255.0, weights="team40_rfdn_pruned", fn=rfdn_pruned_forward),
 }
-FORWARD = {"imdn": imdn_forward, "rfdn": rfdn_forward, "rlfn": rlfn_forward, "bsrn": bsrn_forward}
+FORWARD = {"imdn": imdn_forward, "rfdn": rfdn_forward, "rlfn": rlfn_forward, "bsrn": bsrn_forward,
+           "rfdn_pruned": rfdn_pruned_forward}
 
 
 def forward(arch, weights, x, dtype=np.float32):

@@ -55,16 +55,18 @@ def _esa(w, p, x, kind):
     return x * torch.sigmoid(one("conv4", c3 + one("conv_f", c1_)))
 
 
-def rfdn_forward(w, x):
+def rfdn_forward(w, x, residual=True):
+    """residual=False: models/team40_rfdn_pruned.py:148-166 (RFDB without the inner adds)."""
     a = lambda t: F.leaky_relu(t, 0.05)
+    k = 1.0 if residual else 0.0
     fea = _conv(w, "fea_conv", x, padding=1)
     outs, t = [], fea
     nb = sum(1 for k in w if k.endswith(".c5.weight"))
     for b in range(1, nb + 1):
         p = f"B{b}."
-        d1 = a(_conv(w, p + "c1_d", t)); r1 = a(_conv(w, p + "c1_r", t, padding=1) + t)
-        d2 = a(_conv(w, p + "c2_d", r1)); r2 = a(_conv(w, p + "c2_r", r1, padding=1) + r1)
-        d3 = a(_conv(w, p + "c3_d", r2)); r3 = a(_conv(w, p + "c3_r", r2, padding=1) + r2)
+        d1 = a(_conv(w, p + "c1_d", t)); r1 = a(_conv(w, p + "c1_r", t, padding=1) + k * t)
+        d2 = a(_conv(w, p + "c2_d", r1)); r2 = a(_conv(w, p + "c2_r", r1, padding=1) + k * r1)
+        d3 = a(_conv(w, p + "c3_d", r2)); r3 = a(_conv(w, p + "c3_r", r2, padding=1) + k * r2)
         r4 = a(_conv(w, p + "c4", r3, padding=1))
         t = _esa(w, p + "esa.", _conv(w, p + "c5", torch.cat([d1, d2, d3, r4], 1)), "rfdn")
         outs.append(t)
@@ -123,7 +125,8 @@ def bsrn_forward(w, x):
     return F.pixel_shuffle(_conv(w, "upsampler.upsampleOneStep.0", out_lr, padding=1), 4)
 
 
-FORWARD = {"imdn": imdn_forward, "rfdn": rfdn_forward, "rlfn": rlfn_forward, "bsrn": bsrn_forward}
+FORWARD = {"imdn": imdn_forward, "rfdn": rfdn_forward, "rlfn": rlfn_forward, "bsrn": bsrn_forward,
+           "rfdn_pruned": lambda w, x: rfdn_forward(w, x, residual=False)}
 
 
 def forward(arch, weights, x, dtype=torch.float32):

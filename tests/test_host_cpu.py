@@ -139,3 +139,21 @@ def test_tiled_forward_accumulate_and_divide():
     np.testing.assert_allclose(out.numpy(), e / wsum, rtol=1e-6, atol=1e-6)
     assert out.shape == (2, 3, 148, 116)
     torch.testing.assert_close(forward(x, Up(), tile=None), Up()(x))
+
+
+@pytest.mark.parametrize("mid", [22, 40])
+def test_next_row_models_load_strictly_and_plan(mid):
+    """RFDN40 (id 22) and the pruned RFDN (id 40) reuse the RFDN graph builder; the module facade
+    takes the reference state-dict with strict=True and the engine plans both flavours (host-only handle)."""
+    from ntire2022_esr_b200 import Engine, _cabi, build_model, specs
+
+    w = _weights(mid)
+    reg = specs.REGISTRY[mid]
+    m = build_model(mid, state_dict=w)
+    assert set(m.state_dict()) == set(w)
+    e = Engine(reg["arch"], device=-1, nf=reg["kwargs"]["nf"], nblocks=reg["kwargs"]["nblocks"])
+    e.load_state_dict(w)
+    n16 = e.launch_names(1, 64, 64, _cabi.DTYPE_F16)
+    assert sum(n.startswith("conv_tc") for n in n16) == 23 and len(n16) == 36
+    with pytest.raises(Exception, match="size mismatch|missing key|unexpected key"):
+        Engine("rfdn", device=-1, nf=50).load_state_dict(w)      # a 40-channel checkpoint in the nf = 50 graph

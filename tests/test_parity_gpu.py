@@ -18,7 +18,7 @@ from oracle import esr_oracle as O  # noqa: E402
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ARCHS = [(-1, "imdn"), (0, "rfdn"), (4, "rlfn"), (18, "bsrn")]
-GOLDEN = ARCHS + [(22, "rfdn40")]   # (model id, golden file tag); id 22 = the RFDN graph at nf = 40
+GOLDEN = ARCHS + [(22, "rfdn40"), (40, "rfdn_pruned")]   # (model id, golden file tag): SURVEY row N1 (RFDN at nf = 40, pruned RFDN)
 FP32_BAR = 1e-5
 FP16_PSNR_BAR = 60.0
 
