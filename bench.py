@@ -260,19 +260,19 @@ def run_b200(a):
     pipe_ms = p0.elapsed_time(p1)
     t_c1 = time.perf_counter()
     # ---- end to end through the C ABI with host buffers (pinned), copies inside the timed region --------
-    hx = [(torch.rand(B, 3, h, wd, generator=g) * RANGE[a.model]).to(tdt).pin_memory() for _ in range(4)]
-    hy = [torch.empty(B, 3, 4 * h, 4 * wd, dtype=tdt).pin_memory() for _ in range(4)]
+    nbuf = 6
+    hx = [(torch.rand(B, 3, h, wd, generator=g) * RANGE[a.model]).to(tdt).pin_memory() for _ in range(nbuf)]
+    hy = [torch.empty(B, 3, 4 * h, 4 * wd, dtype=tdt).pin_memory() for _ in range(nbuf)]
     dtc = _cabi.DTYPE_F16 if a.dtype == "f16" else _cabi.DTYPE_F32
     n_e2e = max(8, min(a.steps, 200))
-    nbuf = 4
-    for i in range(4):
+    for i in range(nbuf):
         eng.forward_host_ptr(hx[i % nbuf].data_ptr(), hy[i % nbuf].data_ptr(), B, h, wd, dtc)
     barrier()
     t0 = time.perf_counter()
     tickets = []
     for i in range(n_e2e):
-        # request i reuses host buffer i % 4: its previous occupant (request i-4) must be complete;
-        # the engine keeps 3 requests in flight
+        # request i reuses host buffer i % nbuf: its previous occupant (request i - nbuf) must be complete;
+        # the engine keeps 4 requests in flight
         if i >= nbuf:
             eng.host_wait(tickets[i - nbuf])
         tickets.append(eng.forward_host_async_ptr(hx[i % nbuf].data_ptr(), hy[i % nbuf].data_ptr(), B, h, wd, dtc))
@@ -313,7 +313,7 @@ def run_b200(a):
                "vs_baseline": None, "dtype": a.dtype, "data": "synthetic", "config": workload_config(a, world),
                "e2e": {"value": world * B * n_e2e / (e2e_ms * 1e-3), "unit": "images/s", "h2d_bytes_per_step": in_b,
                        "d2h_bytes_per_step": out_b, "steps": n_e2e,
-                       "api": "esr_forward_host_async + esr_host_wait (C ABI, pinned host buffers, 3 requests in flight, each "
+                       "api": "esr_forward_host_async + esr_host_wait (C ABI, pinned host buffers, 4 requests in flight, each "
                               "on its own stream and workspace; every step copies its input H2D and its output D2H)"},
                "pipelined": {"value": world * B * a.steps / (pipe_ms * 1e-3), "unit": "images/s", "requests_in_flight": n_pipe,
                              "note": "same K device-resident steps issued round-robin on 3 engine handles / streams; "

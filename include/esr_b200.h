@@ -87,8 +87,9 @@ int esr_forward_host_u8_async(esr_handle* h, const uint8_t* in_host_hwc, uint8_t
 int esr_forward_host(esr_handle* h, const void* in_host, void* out_host, int B, int H, int W, int dtype);
 
 /* Pipelined form of the same path for serving loops (run() of the reference, test_demo.py:416-434, one
- * image after another): returns once the request is queued on the engine's streams; up to 3 requests are
- * in flight, so the H2D copy, the forward and the D2H copy of consecutive requests overlap.  Host buffers
+ * image after another): returns once the request is queued on the engine's streams; up to 4 requests are
+ * in flight, each on its own compute stream and workspace, so the H2D copy, the forward and the D2H copy of
+ * consecutive requests overlap and the forwards of independent requests run concurrently.  Host buffers
  * should be pinned.  *ticket identifies the request; esr_host_wait(h, ticket) blocks until its output (and
  * every earlier one) is in out_host; ticket < 0 waits for all. */
 int esr_forward_host_async(esr_handle* h, const void* in_host, void* out_host, int B, int H, int W, int dtype,

@@ -68,7 +68,7 @@ struct Engine {
   // of independent requests run concurrently: at batch 1 a forward is a chain of ~36 short kernels whose launch
   // gaps, epilogue tails and small ESA kernels leave most SMs idle (measured: 2274 img/s on one stream, 2688 on
   // two, 2985 on three, 3036 on four; tools/gpu_two_streams.py).
-  static const int kHostSlots = 3;
+  static const int kHostSlots = 4;
   struct HostSlot {
     void* d_in = nullptr; void* d_out = nullptr;
     size_t in_sz = 0, out_sz = 0;

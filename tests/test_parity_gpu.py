@@ -200,7 +200,7 @@ def test_host_buffer_entry_point_equals_device_path(half):
 
 
 def test_pipelined_host_entry_point_matches_sync_path():
-    """esr_forward_host_async keeps 3 requests in flight; every output must equal the synchronous result."""
+    """esr_forward_host_async keeps 4 requests in flight (one stream and workspace each); every output must equal the synchronous result."""
     from ntire2022_esr_b200 import _cabi
 
     m = _model(0)
