@@ -60,6 +60,11 @@ struct TcOutGroup {
   int32_t stage_bytes; // bytes of one staging buffer
   const float* bias;   // [ncols]
   const __half* res;   // nullptr = none
+  // First group only, nullptr = none: bias per border class [9][64], class = 3 * (y == 0 ? 0 : y == H-1 ? 2 : 1) +
+  // (x == 0 ? 0 : x == W-1 ? 2 : 1).  A BSConvU (pointwise Linear, THEN zero-padded depthwise 3x3) run as one dense
+  // 3x3 convolution needs it: the Linear's bias reaches an output pixel only through the taps that lie inside the
+  // image (models/team18_bsrn.py:82-88).  Used instead of `bias` for that group.
+  const float* bias9;
 };
 
 // one unit of epilogue work: 16 accumulator columns of one output group
@@ -130,8 +135,34 @@ __device__ __forceinline__ void umma_f16_ss_nc(uint32_t tmem_d, uint32_t adesc_l
       ::"r"(tmem_d), "r"(adesc_lo), "r"(bdesc_lo), "r"(idesc), "r"(accumulate), "r"(0x40004040u));
 }
 
-// out of line on purpose: erff is ~40 instructions and would be replicated 16x in the epilogue otherwise
-__device__ __noinline__ float tc_gelu(float v) { return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f)); }
+// GELU of 16 accumulator columns (gelu_fast of kernels_generic.cuh), written stage by stage over 8 values so that
+// eight independent chains (two MUFU each) are in flight.  As an out-of-line call every element paid the call
+// ABI's register save / restore around a 168-register caller (measured: 13 k cycles per tile for 96 GELU columns).
+__device__ __forceinline__ void tc_gelu16(float (&f)[16]) {
+#pragma unroll
+  for (int h = 0; h < 16; h += 8) {
+    float x[8], t[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = fabsf(f[h + j]) * 0.70710678118654752440f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t[j] = __fdividef(1.f, fmaf(0.3275911f, x[j], 1.f));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = __expf(-x[j] * x[j]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) q[j] = fmaf(t[j], 1.061405429f, -1.453152027f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) q[j] = fmaf(q[j], t[j], 1.421413741f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) q[j] = fmaf(q[j], t[j], -0.284496736f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) q[j] = fmaf(q[j], t[j], 0.254829592f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float e = 1.f - q[j] * t[j] * x[j];   // erf(|v| / sqrt 2)
+      f[h + j] = 0.5f * f[h + j] * (1.f + copysignf(e, f[h + j]));
+    }
+  }
+}
 
 // bias + residual + activation on 16 accumulator columns of one pixel.  NONE / RELU / LRELU are all
 // max(v, v * slope) with slope 1 / 0 / s (set by the host), so the common path has no activation branch.
@@ -167,8 +198,7 @@ __device__ __forceinline__ void tc_epi_math16(const uint32_t (&v)[16], const flo
     for (int j = 0; j < 16; ++j) f[j] += rv[j];
   }
   if (gelu) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) f[j] = tc_gelu(f[j]);   // (a dynamically indexed loop would push f[] to local memory)
+    tc_gelu16(f);
   } else {
 #pragma unroll
     for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], f[j] * slope);
@@ -214,6 +244,10 @@ __device__ __forceinline__ void tc_epi_store16(const float (&f)[16], int mode, u
   }
 }
 
+// One kernel for every network.  (A second instantiation without the GELU / border-class-bias code measured 1-2 %
+// faster on RFDN but failed intermittently - "unspecified launch failure" in the 1x1 c5 layer at 16 x 270x480 -
+// while this one and its predecessor never did; unexplained, so the split was dropped and that shape is now a
+// stress test, tests/test_parity_gpu.py::test_large_batch_odd_shape_stress.)
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmO0,
                const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ CUtensorMap tmO2,
@@ -223,9 +257,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __shared__ int need_a_s[TC_MAX_SLOTS], need_b_s[TC_MAX_SLOTS];   // producer-private: last reader tiles of the strip in each slot
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float bias_s[TC_MAX_GROUPS][64];
+  __shared__ __align__(16) float bias9_s[9][64];
   __shared__ __align__(16) TcEntry ent_s[TC_MAX_ENTRIES];
   __shared__ TcOutGroup grp_s[TC_MAX_GROUPS];
-  __shared__ TcChunk ck_s[TC_MAX_CHUNKS];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   long long* const dbg = p.dbg;
@@ -338,9 +372,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int g = i >> 6, c = i & 63;
       bias_s[g][c] = (g < ngroups && c < p.g[g].ncols) ? p.g[g].bias[c] : 0.f;
     }
+    if (p.g[0].bias9 != nullptr)
+      for (int i = tid; i < 9 * 64; i += 32 * TC_EPI_WARPS) bias9_s[i >> 6][i & 63] = p.g[0].bias9[i];
     if (tid < TC_MAX_ENTRIES) ent_s[tid] = p.e[tid];
     if (tid >= 32 && tid < 32 + TC_MAX_GROUPS) grp_s[tid - 32] = p.g[tid - 32];
-    if (tid >= 64 && tid < 64 + TC_MAX_CHUNKS) ck_s[tid - 64] = p.ck[tid - 64];
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -452,6 +487,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       gstage[gi] = g.stage_off; gstage_bytes[gi] = g.stage_bytes;
       ggelu[gi] = g.act == ACT_GELU; gslope[gi] = g.slope;
     }
+    const bool g0_bias9 = grp_s[0].bias9 != nullptr;
     const bool g0_has_res = ng > 0 && grp_s[0].res != nullptr;
     const __half* const g0_res = g0_has_res ? grp_s[0].res + grp_s[0].res_coff : nullptr;
     const int g0_res_stride = grp_s[0].res_stride;
@@ -482,6 +518,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         // staging buffer `sbuf` was last read by the TMA store of tile t-2
         if (store_thread) tma_store_wait_read<1>();
+        __syncwarp();   // bar.sync is a warp-aligned instruction: the store thread's lane must have rejoined its warp
         named_bar_sync(1, 32 * TC_EPI_WARPS);
         if (threadIdx.x == 64) TC_STAMP(3, 3 * t);
         mbar_wait(&tfull_bar[aslot], (t >> ns_shift) & 1);
@@ -503,7 +540,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint8_t* stage_row = smem + gstage[gi] + sbuf * gstage_bytes[gi] + m * (gncols[gi] * 2);
           const int swz = gswz[gi] == 1 ? (m & 7) : (gswz[gi] == 2 ? ((m >> 1) & 3) : (gswz[gi] == 3 ? ((m >> 2) & 1) : 0));
           float f[16];
-          tc_epi_math16(v, &bias_s[gi][c0], ggelu[gi], gslope[gi], has_res, rpre[s & 1][0], rpre[s & 1][1], g.res_after, f);
+          const float* bias_row = &bias_s[gi][c0];
+          if (gi == 0 && g0_bias9)   // border class of this thread's pixel
+            bias_row = &bias9_s[3 * (y == 0 ? 0 : (y == H - 1 ? 2 : 1)) + (x == 0 ? 0 : (x == W - 1 ? 2 : 1))][c0];
+          tc_epi_math16(v, bias_row, ggelu[gi], gslope[gi], has_res, rpre[s & 1][0], rpre[s & 1][1], g.res_after, f);
           tc_epi_store16(f, gmode[gi], stage_row, c0, swz, valid, ps_out, ps_fp32, b, y, x, H, W);
         };
         // With both MMA warps keeping the tensor pipe busy a tcgen05.ld takes ~0.7k cycles to come back, so
@@ -527,6 +567,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[aslot]);
         fence_proxy_async_smem();
+        __syncwarp();
         named_bar_sync(2, 32 * TC_EPI_WARPS);
         if (store_thread) {
           if (nck > 0) {

@@ -53,6 +53,7 @@ struct TcGroupDecl {
   int mode = 0;                 // 0: NHWC store, 1: pixel-shuffle into the network output
   int out = BUF_NONE, out_coff = 0;
   size_t off_bias = 0;          // float offset in the parameter arena
+  long long off_bias9 = -1;     // >= 0: border-class bias table [9][64] (first group only), see TcOutGroup::bias9
 };
 struct TcConv {
   int in = BUF_NONE;

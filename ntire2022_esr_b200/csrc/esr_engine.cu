@@ -129,7 +129,10 @@ static std::string build_dev_graph(Engine& e, int gid) {
   for (auto& c : dg.g.tc) {
     c.off_blob = nblob;
     nblob += (c.blob.size() + 1023) / 1024 * 1024;
-    for (auto& gd : c.groups) gd.off_bias = dg.tables[gd.off_bias].off_b;
+    for (auto& gd : c.groups) {
+      gd.off_bias = dg.tables[gd.off_bias].off_b;
+      if (gd.off_bias9 >= 0) gd.off_bias9 = (long long)dg.tables[gd.off_bias9].off_b;
+    }
   }
   if (e.has_gpu) {
     std::vector<float> host(nf32, 0.f);
@@ -222,7 +225,7 @@ static double op_flops(const OpDecl& op, int B, int H, int W) {
   return 2.0 * op.macs_pp * px * B;
 }
 
-static const size_t kMaxSmem = 232448 - 2048;  // 227 KB minus the kernel's static shared memory (barriers, bias)
+static const size_t kMaxSmem = 232448 - 4096;  // 227 KB minus the kernel's static shared memory (barriers, bias)
 
 static int plan_tc(Engine* e, const DevGraph& dg, const TcConv& c, const std::string& name, const WsLayout& L, Plan& pl) {
   struct Packed {
@@ -283,6 +286,8 @@ static int plan_tc(Engine* e, const DevGraph& dg, const TcConv& c, const std::st
     // stores of a quarter warp on distinct banks (linear 64 B / 32 B rows conflict 4-way / 2-way)
     g.swizzle = gd.ncols == 64 ? 1 : (gd.ncols == 32 ? 2 : (gd.ncols == 16 ? 3 : 0));
     g.bias = dg.d_params + gd.off_bias;
+    g.bias9 = gd.off_bias9 >= 0 ? dg.d_params + gd.off_bias9 : nullptr;
+    if (g.bias9 && gi != 0) return fail(e, ESR_E_INVALID, name + ": only the first output group may carry a border-class bias");
     g.res = nullptr;
     if (gd.res != BUF_NONE && gi != 0) return fail(e, ESR_E_INVALID, name + ": only the first output group may carry a residual");
     if (gd.res != BUF_NONE) {
@@ -352,10 +357,10 @@ static int plan_tc(Engine* e, const DevGraph& dg, const TcConv& c, const std::st
     d.misc = (uint32_t)s.dcol | ((uint32_t)(s.nsteps & 15) << 16) | (s.first ? 0x80000000u : 0u);
   }
   const int grid = std::min(p.n_items, e->num_sms);
-  static size_t attr_set = 0;
-  if (smem > attr_set) {
+  static bool attr_set = false;
+  if (!attr_set) {
     CUDA_TRY(e, cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-    attr_set = kMaxSmem;
+    attr_set = true;
   }
   pl.launches.push_back(Launch{"conv_tc:" + name, [pk, grid, smem](cudaStream_t s) {
                                  return launch_k(conv_tc_kernel, dim3(grid), dim3(TC_THREADS), smem, s, pk->tmA, pk->tmO[0], pk->tmO[1],
@@ -496,6 +501,15 @@ static int build_plan(Engine* e, Plan& pl) {
         const dim3 grid((unsigned)((total + 127) / 128));
         const bool in32 = is_f32(op.in), out32 = is_f32(op.out);
         const bool dbl = !f16;
+        if (!in32 && !out32 && !dbl && p.c8 <= 64 && (op.res < 0 || !is_f32(op.res)) && p.W >= 64) {
+          // full-resolution fp16 layer: 4 pixels x 8 channels per thread
+          const long long t4 = (long long)B * p.H * ((p.W + 3) / 4) * (p.c8 / 8);
+          const dim3 grid4((unsigned)((t4 + 255) / 256));
+          pl.launches.push_back(Launch{"dwconv:" + op.name, [=](cudaStream_t s) {
+            return launch1(k_dwconv3x3_h4, grid4, dim3(256), 0, s, p);
+          }});
+          break;
+        }
         pl.launches.push_back(Launch{"dwconv:" + op.name, [=](cudaStream_t s) {
           return dbl ? launch_dw<double>(in32, out32, grid, s, p) : launch_dw<float>(in32, out32, grid, s, p);
         }});

@@ -118,6 +118,45 @@ struct GraphBuilder {
     return C;
   }
 
+  // BSConvU (models/team18_bsrn.py:44-88: Linear over the channels, THEN a zero-padded depthwise 3x3) as one dense
+  // 3x3 convolution for the tensor cores: W[o][i][t] = dw[o][t] * pw[o][i] (formed in double, rounded once).  The
+  // Linear's bias passes through the depthwise taps that lie inside the image only, so the bias of an output
+  // pixel depends on its border class: bias9[class][o] = b_dw[o] + b_pw[o] * sum_{valid taps t} dw[o][t],
+  // class = 3 * (top, middle, bottom) + (left, middle, right).  Returns the matrix with a zero bias.
+  Mat bsconv_dense(const std::string& name, int O, int I, std::vector<float>* bias9 /* [9][64] */) {
+    const Mat pw = linear_mat(name + ".pw", O, I);
+    const HostTensor& dw = wts.get(name + ".dw.weight", {O, 1, 3, 3});
+    const HostTensor& db = wts.get(name + ".dw.bias", {O});
+    Mat m;
+    m.O = O; m.I = I; m.k = 3;
+    m.w.assign((size_t)O * I * 9, 0.0);
+    m.b.assign(O, 0.0);
+    for (int o = 0; o < O; ++o)
+      for (int i = 0; i < I; ++i)
+        for (int t = 0; t < 9; ++t) m.at(o, i, t) = (double)dw.data[(size_t)o * 9 + t] * pw.at(o, i, 0);
+    bias9->assign(9 * 64, 0.f);
+    for (int cy = 0; cy < 3; ++cy)
+      for (int cx = 0; cx < 3; ++cx)
+        for (int o = 0; o < O; ++o) {
+          double sum = 0;
+          for (int ky = 0; ky < 3; ++ky)
+            for (int kx = 0; kx < 3; ++kx) {
+              const bool in_y = !(cy == 0 && ky == 0) && !(cy == 2 && ky == 2);
+              const bool in_x = !(cx == 0 && kx == 0) && !(cx == 2 && kx == 2);
+              if (in_y && in_x) sum += (double)dw.data[(size_t)o * 9 + ky * 3 + kx];
+            }
+          (*bias9)[(size_t)(cy * 3 + cx) * 64 + o] = (float)((double)db.data[o] + pw.b[o] * sum);
+        }
+    return m;
+  }
+  void tc_attach_bias9(int tci, const std::vector<float>& bias9) {
+    Table t;
+    t.k = 0; t.cin8 = 0; t.cout16 = 9 * 64;
+    t.b = bias9;
+    tables.push_back(std::move(t));
+    g.tc[tci].groups[0].off_bias9 = (long long)tables.size() - 1;   // table index; resolved to an offset at upload
+  }
+
   // ---- CUDA-core tables ---------------------------------------------------------------------
   int new_table(int k, int cin8, int cout16) {
     Table t;
@@ -478,6 +517,43 @@ struct GraphBuilder {
     g.ops.push_back(ap);
   }
 
+  // fp16 / tcgen05 flavour of BSRN's ESA tail (models/team18_bsrn.py:109-122): the low-resolution chain keeps its
+  // small pointwise + depthwise kernels (0.3 % of the forward), conv4 is commuted through the bilinear upsample
+  // exactly as for RFDN (M3 = conv4(c3) on the pooled map, cf' = conv4(conv_f(c1_)) + b4 from the c5 GEMM), which
+  // replaces a 16 -> nf mat-vec per full-resolution pixel on the CUDA cores by the elementwise ESA tail.
+  void esa_tail_bsrn_commuted(const std::string& p, const EsaBufs& eb, int m3buf, int f, int nf, int x, int cfp, int dst,
+                              const Mat& conv4) {
+    {
+      const Mat m = conv_mat(p + "conv2", f, f, 3);
+      conv_op(p + "conv2", dense_table(m, 16, 16, pos_id(), pos_id()), eb.esa, 0, eb.s2, 0, ACT_NONE, 0.f, 2, 0);
+    }
+    OpDecl pool;
+    pool.kind = OP_POOL;
+    pool.name = p + "max_pool";
+    pool.in = eb.s2; pool.out = eb.s3a;
+    g.ops.push_back(pool);
+    const char* names[3] = {"conv_max", "conv3", "conv3_"};
+    for (int i = 0; i < 3; ++i) {
+      const Mat pw = linear_mat(p + names[i] + ".pw", f, f);
+      conv_op(p + names[i] + ".pw", dense_table(pw, 16, 16, pos_id(), pos_id()), eb.s3a, 0, eb.s3b, 0, ACT_NONE);
+      dw_op(p + names[i] + ".dw", dw_table(p + names[i] + ".dw", f, 16), eb.s3b, 0, eb.s3a, 0, i < 2 ? ACT_GELU : ACT_NONE);
+    }
+    Mat c4nb = conv4;
+    std::fill(c4nb.b.begin(), c4nb.b.end(), 0.0);   // b4 travels with cf'
+    conv_op(p + "conv4@pooled", dense_table(c4nb, 16, 64, pos_id(), pos_id()), eb.s3a, 0, m3buf, 0, ACT_NONE);
+    g.ops.back().macs_pp = 0;   // conv4's algorithmic MACs are counted with cf' (full resolution)
+    OpDecl ap;
+    ap.kind = OP_ESA_APPLY2;
+    ap.name = p + "apply";
+    ap.in = x; ap.in_coff = 0;
+    ap.c1 = cfp; ap.c1_coff = 0;
+    ap.c3 = m3buf;
+    ap.out = dst; ap.out_coff = 0;
+    ap.cgroups = (nf + 7) / 8;
+    ap.f = f;
+    g.ops.push_back(ap);
+  }
+
   // =============================================================================================
   // RFDN
   // =============================================================================================
@@ -747,8 +823,9 @@ struct GraphBuilder {
     const int dc = nf / 2, f = 12;  // ESA(num_feat, ...) uses f = 12? -> esa_channels = 16 arg is unused: f = num_feat // 4
     const int fea = buf(BK_FULL, 64), cat = buf(BK_FULL, 64 * nblocks), t0 = buf(BK_FULL, 64), t1 = buf(BK_FULL, 64),
               t2 = buf(BK_FULL, 64), dist = buf(BK_FULL, 128), c5o = buf(BK_FULL, 64), eo = buf(BK_FULL, 64),
-              esa = buf(BK_FULL, 32);
+              esa = buf(BK_FULL, tc ? 16 : 32);   // tc path: c1_ only (cf' travels in its own buffer)
     EsaBufs eb{esa, buf(BK_S2, 16, true), buf(BK_S3, 16, true), buf(BK_S3, 16, true)};
+    const int cfpb = tc ? buf(BK_FULL, 64) : BUF_NONE, m3b = tc ? buf(BK_S3, 64, true) : BUF_NONE;
     {
       OpDecl op;
       op.kind = OP_BSRN_HEAD;
@@ -792,21 +869,36 @@ struct GraphBuilder {
         if (!tc) {
           lin(n + "_d", md, 64, 32, pos_id(), cur, curc, dist, 32 * s, ACT_GELU);
           lin(n + "_r.pw", mp, 64, 64, pos_id(), cur, curc, t2, 0, ACT_NONE);
+          OpDecl& o = dw_op(n + "_r.dw", dw_table(n + "_r.dw", nf, 64), t2, 0, nxt, 0, ACT_GELU);
+          o.res = cur; o.res_coff = curc;
         } else {
-          // distillation Linear and the pointwise half of BSConvU share the A operand
+          // r = gelu(BSConvU(x) + x), d = gelu(Linear(x)): the BSConvU as one dense 3x3 (border-class bias), the
+          // distillation Linear as extra columns of its centre tap, the residual as an identity tap - the same
+          // launch shape as an RFDN stage (the depthwise pass and its HBM round trip disappear)
+          std::vector<float> b9;
+          const Mat mdense = bsconv_dense(n + "_r", nf, nf, &b9);
           TcBuild b = tc_begin(1, 96, {{0, 64}, {64, 32}});
-          tc_add(b, mp, pos_id(), pos_id());
+          tc_add(b, mdense, pos_id(), pos_id(), (double)nf * nf + 9.0 * nf);
           tc_add(b, md, pos_id(), pos_id(64));
-          tc_emit(n + "_r.pw+d", b, cur, curc, 0,
-                  {tc_group(0, 64, ACT_NONE, 0.f, t2, 0), tc_group(64, 32, ACT_GELU, 0.f, dist, 32 * s)});
+          tc_add_identity(b, nf);
+          const int tci = tc_emit(n + "_r.pw+dw+d", b, cur, curc, 1,
+                                  {tc_group(0, 64, ACT_GELU, 0.f, nxt, 0), tc_group(64, 32, ACT_GELU, 0.f, dist, 32 * s)});
+          tc_attach_bias9(tci, b9);
         }
-        OpDecl& o = dw_op(n + "_r.dw", dw_table(n + "_r.dw", nf, 64), t2, 0, nxt, 0, ACT_GELU);
-        o.res = cur; o.res_coff = curc;
         cur = nxt; curc = 0;
       }
-      const Mat m4 = linear_mat(p + "c4.pw", dc, nf);
-      lin(p + "c4.pw", m4, 64, 32, pos_id(), cur, curc, t2, 0, ACT_NONE);
-      dw_op(p + "c4.dw", dw_table(p + "c4.dw", dc, 32), t2, 0, dist, 96, ACT_GELU);
+      if (!tc) {
+        const Mat m4 = linear_mat(p + "c4.pw", dc, nf);
+        lin(p + "c4.pw", m4, 64, 32, pos_id(), cur, curc, t2, 0, ACT_NONE);
+        dw_op(p + "c4.dw", dw_table(p + "c4.dw", dc, 32), t2, 0, dist, 96, ACT_GELU);
+      } else {
+        std::vector<float> b9;
+        const Mat m4 = bsconv_dense(p + "c4", dc, nf, &b9);
+        TcBuild b4 = tc_begin(1, 32, {{0, 32}});
+        tc_add(b4, m4, pos_id(), pos_id(), (double)dc * nf + 9.0 * dc);
+        const int tci = tc_emit(p + "c4.pw+dw", b4, cur, curc, 1, {tc_group(0, 32, ACT_GELU, 0.f, dist, 96)});
+        tc_attach_bias9(tci, b9);
+      }
       const Mat m5 = linear_mat(p + "c5", nf, dc * 4);
       const Mat e1 = linear_mat(p + "esa.conv1", f, nf), ef = linear_mat(p + "esa.conv_f", f, f),
                 e4 = linear_mat(p + "esa.conv4", nf, f);
@@ -815,16 +907,20 @@ struct GraphBuilder {
         lin(p + "c5", m5, 128, 64, pos_slots(dc, 32), dist, 0, c5o, 0, ACT_NONE);
         lin(p + "esa.conv1", e1, 64, 16, pos_id(), c5o, 0, esa, 0, ACT_NONE);
       } else {
-        const Mat c1c = compose(e1, m5), cfc = compose(ef, c1c);
-        TcBuild b5 = tc_begin(2, 96, {{0, 64}, {64, 32}});
+        const Mat c1c = compose(e1, m5), cfc = compose(ef, c1c), cfp = compose(e4, cfc);
+        TcBuild b5 = tc_begin(2, 144, {{0, 64}, {64, 16}, {80, 64}});
         tc_add(b5, m5, pos_slots(dc, 32), pos_id());
         tc_add(b5, c1c, pos_slots(dc, 32), pos_id(64), (double)e1.O * e1.I);
-        tc_add(b5, cfc, pos_slots(dc, 32), pos_id(80), (double)ef.O * ef.I);
-        tc_emit(p + "c5+esa.conv1+esa.conv_f", b5, dist, 0, 0,
-                {tc_group(0, 64, ACT_NONE, 0.f, c5o, 0), tc_group(64, 32, ACT_NONE, 0.f, esa, 0)});
+        tc_add(b5, cfp, pos_slots(dc, 32), pos_id(80), (double)ef.O * ef.I + (double)e4.O * e4.I);
+        tc_emit(p + "c5+esa.conv1+esa.conv_f+esa.conv4", b5, dist, 0, 0,
+                {tc_group(0, 64, ACT_NONE, 0.f, c5o, 0), tc_group(64, 16, ACT_NONE, 0.f, esa, 0),
+                 tc_group(80, 64, ACT_NONE, 0.f, cfpb, 0)});
         cf_ready = 1;
       }
-      esa_tail(p + "esa.", ESR_ARCH_BSRN, eb, f, nf, c5o, 0, eo, 0, 4, cf_ready, ef, e4);
+      if (tc)
+        esa_tail_bsrn_commuted(p + "esa.", eb, m3b, f, nf, c5o, cfpb, eo, e4);
+      else
+        esa_tail(p + "esa.", ESR_ARCH_BSRN, eb, f, nf, c5o, 0, eo, 0, 4, cf_ready, ef, e4);
       // conv_out(esa(out) * cw) + input: the per-channel scale is folded into conv_out's columns
       Mat mo = linear_mat(p + "conv_out", nf, nf);
       const HostTensor& cw = wts.get(p + "cw", {1, nf});
@@ -835,16 +931,40 @@ struct GraphBuilder {
     }
     const Mat mc1 = linear_mat("c1", nf, nf * nblocks), mc2 = linear_mat("c2.pw", nf, nf),
               mup = conv_mat("upsampler.upsampleOneStep.0", 48, nf, 3);
-    if (!tc || nblocks > 4) {
-      OpDecl& o = conv_op("c1", dense_table(mc1, 64 * nblocks, 64, pos_slots(nf, 64), pos_id()), cat, 0, t0, 0, ACT_GELU);
-      (void)o;
+    if (!tc) {
+      conv_op("c1", dense_table(mc1, 64 * nblocks, 64, pos_slots(nf, 64), pos_id()), cat, 0, t0, 0, ACT_GELU);
+    } else if (nblocks > 4) {
+      // K = 64 * nblocks does not fit one launch (four 64-channel chunks per strip): the first four blocks go
+      // through a bias-free, activation-free GEMM into t1, the rest adds it as the epilogue residual before GELU
+      // (one extra fp16 rounding of the partial sum)
+      auto cols = [&](int i0, int i1, bool with_bias) {
+        Mat m;
+        m.O = mc1.O; m.I = i1 - i0; m.k = 1;
+        m.w.resize((size_t)m.O * m.I);
+        m.b.assign(m.O, 0.0);
+        for (int o = 0; o < m.O; ++o) {
+          for (int i = i0; i < i1; ++i) m.at(o, i - i0, 0) = mc1.at(o, i, 0);
+          if (with_bias) m.b[o] = mc1.b[o];
+        }
+        return m;
+      };
+      const Mat ma = cols(0, 4 * nf, false), mb = cols(4 * nf, nblocks * nf, true);
+      lin("c1[0:4]", ma, 256, 64, pos_slots(nf, 64), cat, 0, t1, 0, ACT_NONE);
+      lin("c1[4:]", mb, 64 * (nblocks - 4), 64, pos_slots(nf, 64), cat, 256, t0, 0, ACT_GELU, t1, 0);
     } else {
       lin("c1", mc1, 64 * nblocks, 64, pos_slots(nf, 64), cat, 0, t0, 0, ACT_GELU);
     }
-    lin("c2.pw", mc2, 64, 64, pos_id(), t0, 0, t2, 0, ACT_NONE);
-    {
+    if (!tc) {
+      lin("c2.pw", mc2, 64, 64, pos_id(), t0, 0, t2, 0, ACT_NONE);
       OpDecl& o = dw_op("c2.dw", dw_table("c2.dw", nf, 64), t2, 0, t1, 0, ACT_NONE);
       o.res = fea; o.res_coff = 0;
+    } else {
+      std::vector<float> b9;
+      const Mat m2 = bsconv_dense("c2", nf, nf, &b9);
+      TcBuild b2 = tc_begin(1, 64, {{0, 64}});
+      tc_add(b2, m2, pos_id(), pos_id(), (double)nf * nf + 9.0 * nf);
+      const int tci = tc_emit("c2.pw+dw", b2, t0, 0, 1, {tc_group(0, 64, ACT_NONE, 0.f, t1, 0, fea, 0, 0)});
+      tc_attach_bias9(tci, b9);
     }
     if (!tc) {
       OpDecl& u = conv_op("upsampler", dense_table(mup, 64, 48, pos_id(), pos_id()), t1, 0, BUF_OUT, 0, ACT_NONE);
