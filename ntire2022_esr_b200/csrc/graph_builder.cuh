@@ -659,7 +659,11 @@ struct GraphBuilder {
   void build_rlfn(int nf, int nblocks, bool tc) {
     const int mf = 48, f = 16;
     const float sl = 0.05f;
-    const int fea = buf(BK_FULL, 64), xa = buf(BK_FULL, 64), xb = buf(BK_FULL, 64), t0 = buf(BK_FULL, 64),
+    // tc flavour: the block input x and the last conv's output u live side by side in one 128-channel buffer
+    // [x | u], so that c5(u + x) is ONE GEMM over K = 128 with c5's weights on both halves (exact: the sum forms in
+    // the fp32 accumulator) and c3_r needs no residual in its epilogue (measured 73 vs 47 us per launch at batch 8)
+    const int xw = tc ? 128 : 64;
+    const int fea = buf(BK_FULL, xw), xa = buf(BK_FULL, xw), xb = buf(BK_FULL, xw), t0 = buf(BK_FULL, 64),
               t1 = buf(BK_FULL, 64), esa = buf(BK_FULL, tc ? 16 : 32);
     EsaBufs eb{esa, buf(BK_S2, 16, true), buf(BK_S3, 16, true), buf(BK_S3, 16, true)};
     const int cfpb = tc ? buf(BK_FULL, 64) : BUF_NONE, m3b = tc ? buf(BK_S3, 64, true) : BUF_NONE;
@@ -704,13 +708,17 @@ struct GraphBuilder {
         tc_emit(p + "c2_r", b2, t0, 0, 1, {tc_group(0, 48, ACT_LRELU, sl, t1, 0)});
         TcBuild b3 = tc_begin(1, 48, {{0, 48}});
         tc_add(b3, m3, pos_id(), pos_id());
-        tc_emit(p + "c3_r", b3, t1, 0, 1, {tc_group(0, 48, ACT_LRELU, sl, t0, 0, x, 0, 1)});
+        tc_emit(p + "c3_r", b3, t1, 0, 1, {tc_group(0, 48, ACT_LRELU, sl, x, 64)});   // u, next to x
         const Mat c1c = compose(e1, m5), cfc = compose(ef, c1c), cfp = compose(e4, cfc);
-        TcBuild b5 = tc_begin(1, 112, {{0, 48}, {48, 16}, {64, 48}});
-        tc_add(b5, m5, pos_id(), pos_id());
+        auto no_bias = [](Mat m) { std::fill(m.b.begin(), m.b.end(), 0.0); return m; };
+        TcBuild b5 = tc_begin(2, 112, {{0, 48}, {48, 16}, {64, 48}});
+        tc_add(b5, m5, pos_id(), pos_id());                                  // x half (with the biases)
         tc_add(b5, c1c, pos_id(), pos_id(48), (double)e1.O * e1.I);
         tc_add(b5, cfp, pos_id(), pos_id(64), (double)ef.O * ef.I + (double)e4.O * e4.I);
-        tc_emit(p + "c5+esa.conv1+esa.conv_f+esa.conv4", b5, t0, 0, 0,
+        tc_add(b5, no_bias(m5), pos_id(64), pos_id(), 0.0);                  // u half: same weights, counted once
+        tc_add(b5, no_bias(c1c), pos_id(64), pos_id(48), 0.0);
+        tc_add(b5, no_bias(cfp), pos_id(64), pos_id(64), 0.0);
+        tc_emit(p + "c5+esa.conv1+esa.conv_f+esa.conv4", b5, x, 0, 0,
                 {tc_group(0, 48, ACT_NONE, 0.f, t1, 0), tc_group(48, 16, ACT_NONE, 0.f, esa, 0),
                  tc_group(64, 48, ACT_NONE, 0.f, cfpb, 0)});
         esa_tail_commuted(p + "esa.", ESR_ARCH_RLFN, eb, m3b, f, nf, t1, 0, cfpb, xn, 0, 6, e4);
