@@ -11,10 +11,15 @@
 // column strip keeping a ring of row strips in shared memory; weights are staged once per CTA as
 // pre-swizzled blocks.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (one elected
-// lane each), warps 2..5 = epilogue (TMEM -> registers -> bias/residual/activation -> fp16 ->
-// swizzled staging -> TMA store, or the fused pixel-shuffle store of the network tail).  Two TMEM
-// accumulator slots let the epilogue of tile t overlap the MMAs of tile t+1.
+// Warp roles (352 threads, one CTA per SM): warp 0 = TMA producer, warps 1 and 10 = MMA issuers for even / odd
+// tiles (one elected lane each; warp 1 also owns the TMEM allocation), warps 2..9 = epilogue (TMEM ->
+// registers -> bias/residual/activation -> fp16 -> swizzled staging -> TMA store, or the fused pixel-shuffle
+// store of the network tail).  Two or four TMEM accumulator slots let the epilogue of tile t overlap the MMAs
+// of the following tiles.
+//
+// What bounds it (profiles/README.md): both MMA operands come from shared memory, 268 KB per tile of the
+// 3x3 50->50(+25) layer = 2.06 k cycles at 128 B/clk against 1.35 k cycles of tensor math; with the epilogue's
+// staging traffic the kernel sits at ~90 % of its shared-memory roofline (3.1 k cycles per tile at batch 16).
 //
 // Measured on B200 (tools/micro/mma_bench.cu): an M=128, K=16 SS-mode MMA costs 32 + N/4 cycles for
 // N <= 128 (A and B are both fetched from shared memory at 128 B/clk), i.e. 48 cycles at N = 64.
@@ -30,9 +35,8 @@ constexpr int TC_MAX_ENTRIES = 16;
 constexpr int TC_TILE_PX = 128;
 constexpr int TC_MAX_SLOTS = 8;
 constexpr int TC_MAX_GROUPS = 3;
-constexpr int TC_MAX_CHUNKS = 10;
-constexpr int TC_MAX_UNITS = 5;
-constexpr int TC_PREFETCH_ROWS = 6;  // L2 prefetch distance of the producer, in image rows     // 16-column units per epilogue warp set = ceil(TC_MAX_CHUNKS / 2)
+constexpr int TC_MAX_CHUNKS = 10;    // 16-column epilogue units of a layer (host-side table only)
+constexpr int TC_PREFETCH_ROWS = 6;  // L2 prefetch distance of the producer, in image rows
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_THREADS = 96 + 32 * TC_EPI_WARPS;  // warp 0 TMA, warp 1 + warp 10 MMA issuers, warps 2..9 epilogue
 constexpr int TC_DONE_BARS = 8;

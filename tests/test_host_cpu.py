@@ -157,3 +157,20 @@ def test_next_row_models_load_strictly_and_plan(mid):
     assert sum(n.startswith("conv_tc") for n in n16) == 23 and len(n16) == 36
     with pytest.raises(Exception, match="size mismatch|missing key|unexpected key"):
         Engine("rfdn", device=-1, nf=50).load_state_dict(w)      # a 40-channel checkpoint in the nf = 50 graph
+
+
+def test_uint8_entry_points_refuse_without_a_gpu():
+    """esr_forward_u8 / esr_forward_host_u8 on a host-only handle: loud ESR_E_NOGPU, never a CPU fallback; the
+    workspace query works without a device (it is pure arithmetic on the plan)."""
+    from ntire2022_esr_b200 import Engine, EsrError, _cabi
+
+    e = Engine("rfdn", device=-1)
+    e.load_state_dict(_weights(0))
+    base = _cabi.lib.esr_workspace_bytes(e._h, 2, 64, 48, _cabi.DTYPE_F16)
+    u8 = _cabi.lib.esr_workspace_bytes_u8(e._h, 2, 64, 48, _cabi.DTYPE_F16)
+    assert u8 >= base + 2 * 3 * 16 * 64 * 48 * 2           # + the engine's own NCHW output
+    with pytest.raises(EsrError) as ei:
+        e.forward_host_uint8(np.zeros((1, 32, 32, 3), np.uint8), 255.0)
+    assert ei.value.code == _cabi.E_NOGPU
+    with pytest.raises(EsrError):
+        e.forward_host_uint8(np.zeros((1, 32, 32, 3), np.float32), 255.0)   # wrong dtype
