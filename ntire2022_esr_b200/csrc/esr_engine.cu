@@ -570,15 +570,22 @@ static int build_plan(Engine* e, Plan& pl) {
         if (op.npre > 1) { p.wpre1 = dg.d_params + dg.tables[op.tab2].off_w; p.bpre1 = dg.d_params + dg.tables[op.tab2].off_b; }
         p.wl = dg.d_params + dg.tables[op.tab3].off_w; p.bl = dg.d_params + dg.tables[op.tab3].off_b;
         p.B = B; p.H3 = L.H[op.in]; p.W3 = L.W[op.in];
-        const int nblk = B * ((p.H3 + 5) / 6) * ((p.W3 + 5) / 6);
+        // 6x6 output tiles; 4x4 when those would leave most SMs idle (256x256 at batch 1: 49 tiles vs 121).  The
+        // chain is latency bound there and the smaller tiles shorten every layer (fewer work items per thread)
+        const int n6 = B * ((p.H3 + 5) / 6) * ((p.W3 + 5) / 6);
+        const bool small = n6 < e->num_sms;
+        const int ts = small ? 4 : 6;
+        const int nblk = B * ((p.H3 + ts - 1) / ts) * ((p.W3 + ts - 1) / ts);
         const size_t smem = (size_t)(9 * 16 * 64 + 2 * 9 * 256 + 144 * 16 + 100 * 16) * sizeof(float);
         static bool attr_done = false;
         if (!attr_done) {
-          CUDA_TRY(e, cudaFuncSetAttribute(k_esa_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          CUDA_TRY(e, cudaFuncSetAttribute(k_esa_chain<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          CUDA_TRY(e, cudaFuncSetAttribute(k_esa_chain<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
           attr_done = true;
         }
         pl.launches.push_back(Launch{"esa_chain:" + op.name, [=](cudaStream_t s) {
-          return launch_k(k_esa_chain, dim3(nblk), dim3(256), smem, s, p);
+          if (small) return launch_k(k_esa_chain<4>, dim3(nblk), dim3(256), smem, s, p);
+          return launch_k(k_esa_chain<6>, dim3(nblk), dim3(256), smem, s, p);
         }});
         break;
       }

@@ -889,7 +889,7 @@ __global__ void __launch_bounds__(128) k_esa_conv2_pool(const EsaFrontParams p) 
 // ---------------------------------------------------------------------------------------------
 // Fused ESA low-resolution chain (fp16 path) on the pooled map: [conv_max + ReLU, conv3 + ReLU] (RFDN;
 // none for RLFN) followed by the last 3x3 composed with conv4 (f -> nf, no activation) - one launch,
-// intermediates in shared memory.  block = 6x6 outputs; halo = number of 3x3 layers.
+// intermediates in shared memory.  block = TS x TS outputs (6, or 4 at small batch); halo = number of 3x3 layers.
 //   in : pooled map NHWC fp32 16 ch;  wpre: npre x [9][16][16], bpre: npre x [16];  wl: [9][16][64], bl[64]
 //   out: M3 NHWC fp32 64 ch.   Zero padding applies to every layer's input: intermediate values at positions
 //   outside the map are forced to 0.
@@ -899,11 +899,13 @@ struct EsaChainParams {
   const float* wpre0; const float* bpre0; const float* wpre1; const float* bpre1; const float* wl; const float* bl;
   int npre, B, H3, W3;
 };
+// TS = output tile extent (6, or 4 when there are too few 6x6 tiles to fill the GPU: batch 1 has 49 of them)
+template <int TS>
 __global__ void __launch_bounds__(256) k_esa_chain(const EsaChainParams p) {
   extern __shared__ __align__(16) float sm[];
   const int npre = p.npre;
   const int halo = npre + 1;
-  const int T0 = 6 + 2 * halo;                 // input tile extent
+  const int T0 = TS + 2 * halo;                // input tile extent
   float* wl = sm;                              // [9][16][64]
   float* wpre = wl + 9 * 16 * 64;              // npre x [9][16][16]
   float* buf0 = wpre + 2 * 9 * 256;            // [16][12*12]  (channel-major: conflict-free window reads)
@@ -932,9 +934,9 @@ __global__ void __launch_bounds__(256) k_esa_chain(const EsaChainParams p) {
     }
   }
   pdl_wait();
-  const int tx = (p.W3 + 5) / 6, ty = (p.H3 + 5) / 6;
+  const int tx = (p.W3 + TS - 1) / TS, ty = (p.H3 + TS - 1) / TS;
   const int bx = blockIdx.x % tx, by = (blockIdx.x / tx) % ty, b = blockIdx.x / (tx * ty);
-  const int oy0 = by * 6, ox0 = bx * 6;
+  const int oy0 = by * TS, ox0 = bx * TS;
   // input tile with zero padding outside the map
   for (int i = threadIdx.x; i < T0 * T0 * 4; i += 256) {
     const int q = i & 3, pos = i >> 2;
@@ -1004,11 +1006,12 @@ __global__ void __launch_bounds__(256) k_esa_chain(const EsaChainParams p) {
     float* t = cur; cur = nxt; nxt = t;
     Tin = Tout;
   }
-  // ---- last layer 16 -> 64 (composed with conv4), 6x6 outputs: item = (2x2 outputs, 2 channels): 288 items
+  // ---- last layer 16 -> 64 (composed with conv4), TS x TS outputs: item = (2x2 outputs, 2 channels)
   {
-    for (int item = threadIdx.x; item < 9 * 32; item += 256) {
+    constexpr int QL = TS / 2;
+    for (int item = threadIdx.x; item < QL * QL * 32; item += 256) {
       const int g2 = item & 31, blk = item >> 5;
-      const int y2 = (blk / 3) * 2, x2 = (blk % 3) * 2;
+      const int y2 = (blk / QL) * 2, x2 = (blk % QL) * 2;
       float acc[4][2];
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
