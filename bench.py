@@ -298,9 +298,9 @@ def run_b200(a):
         n_l, fl, m = by[dom]
         ach = fl / (m * 1e-3) / 1e12 if m > 0 else 0.0
         # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture of this workload
-        # (profiles/r1_conv_tc_b1_ncu_summary.csv: dram read 8.55 MB, write 256 B - at batch 1 the outputs stay
+        # (profiles/r1_conv_tc_b1_ncu_summary.csv: dram read 8.56 MB, write 0 B - at batch 1 the outputs stay
         # in L2; algorithmic bytes of the layer: 8.39 MB in + 12.58 MB out); null for other workloads
-        traffic = 8.55e6 if (a.model, B, h, wd, a.dtype) == ("rfdn", 1, 256, 256, "f16") else None
+        traffic = 8.56e6 if (a.model, B, h, wd, a.dtype) == ("rfdn", 1, 256, 256, "f16") else None
         roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s",
                 "frac": ach / pk["tf_sust"], "traffic": traffic, "peak_source": pk["src"] + ", sustained bf16",
                 "launches_per_step": n_l, "kernel_share_of_step": m / tot_ms if tot_ms else None,
