@@ -249,9 +249,8 @@ __device__ __forceinline__ void tc_epi_store16(const float (&f)[16], int mode, u
 }
 
 // One kernel for every network.  (A second instantiation without the GELU / border-class-bias code measured 1-2 %
-// faster on RFDN but failed intermittently - "unspecified launch failure" in the 1x1 c5 layer at 16 x 270x480 -
-// while this one and its predecessor never did; unexplained, so the split was dropped and that shape is now a
-// stress test, tests/test_parity_gpu.py::test_large_batch_odd_shape_stress.)
+// faster on RFDN; it also made a latent barrier bug - see the strip waits of the MMA issuers below - fail often
+// enough to be found.  The split itself was not worth keeping.)
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmO0,
                const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ CUtensorMap tmO2,
@@ -416,14 +415,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         decode(item, b, y0, y1, x0);
         const int nrows = y1 - y0;
         for (int r = 0; r < nrows; ++r, ++t) {
-          if ((t & 1u) == me) {
-            // wait for the strips of this tile's row window that this thread has not seen yet
+          {
+            // Wait for the strips of this tile's row window that this thread has not seen yet - for EVERY tile,
+            // also the ones the other issuing thread owns.  A parity wait is only valid one phase deep: with
+            // halo = 0 and an odd ring (the 1x1 c5 layers: S = 3) a thread that only waited for its own tiles'
+            // strips skipped every other phase of each slot, and a wait for strip q + 6 returned at once while
+            // strip q + 3 was still in flight (TMA completions are not ordered).  The thread then ran one phase
+            // ahead for the rest of the kernel and the CTA could exit with loads outstanding: the intermittent
+            // "unspecified launch failure" at 16 x 270x480.
             uint32_t sl = tslot, pa = tpar;
             for (uint32_t q = q_top; q <= q_top + 2 * halo; ++q) {
               if (q >= seen) mbar_wait(&full_bar[sl], pa);
               if (++sl == (uint32_t)S) { sl = 0; pa ^= 1; }
             }
             seen = q_top + 2 * halo + 1;
+          }
+          if ((t & 1u) == me) {
             const uint32_t aslot = t & (NS - 1);
             if (t < 16) TC_STAMP(2, 2 * t);
             mbar_wait(&tempty_bar[aslot], ((t >> ns_shift) & 1) ^ 1);
