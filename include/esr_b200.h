@@ -121,6 +121,16 @@ int esr_set_option(esr_handle* h, const char* key, int value);
  * (128 per launch: 4 roles x 32 events); copies the first n_launches records to `out`. */
 int esr_debug_timeline(esr_handle* h, long long* out, int n_launches);
 
+/* Test aid (host only, works on a handle without a GPU): the packed form of the index-th tcgen05 layer of the
+ * fp16 plan - what conv_tc_kernel is handed - so that the weight packing, the algebraic folds and the MMA entry
+ * list can be replayed on the CPU (tests/test_tc_packing_cpu.py).  index < 0 returns the number of layers.
+ * meta[12] = {nchunks, halo, acc_cols, n_entries, ngroups, blob_bytes, 0, has_bias9, chunk_c0[4]};
+ * entries[n][8] = {dy, dx, chunk, k16_steps, n, first_column, overwrite, blob_offset};
+ * groups[g][8] = {col0, ncols, act, has_residual, residual_after_act, mode, slope (float bits), has_bias9};
+ * bias[3][64]; bias9[9][64] (border classes, first group); blob = pre-swizzled fp16 [n x 64] K-major blocks. */
+int esr_debug_tc_layer(esr_handle* h, int index, char* name, int name_cap, int32_t* meta, int32_t* entries, int32_t* groups,
+                       float* bias, float* bias9, uint8_t* blob, size_t blob_cap);
+
 const char* esr_last_error(esr_handle* h);
 void esr_destroy(esr_handle* h);
 

@@ -42,6 +42,9 @@ SYMBOLS = [
                                         _c.c_void_p, _c.c_size_t, _c.c_int, _c.POINTER(_c.c_float), _c.c_int, _c.c_void_p]),
     ("esr_set_option", _c.c_int, [_c.c_void_p, _c.c_char_p, _c.c_int]),
     ("esr_debug_timeline", _c.c_int, [_c.c_void_p, _c.POINTER(_c.c_longlong), _c.c_int]),
+    ("esr_debug_tc_layer", _c.c_int, [_c.c_void_p, _c.c_int, _c.c_char_p, _c.c_int, _c.POINTER(_c.c_int32),
+                                      _c.POINTER(_c.c_int32), _c.POINTER(_c.c_int32), _c.POINTER(_c.c_float),
+                                      _c.POINTER(_c.c_float), _c.c_void_p, _c.c_size_t]),
     ("esr_last_error", _c.c_char_p, [_c.c_void_p]),
     ("esr_destroy", None, [_c.c_void_p]),
     ("esr_version", _c.c_char_p, []),

@@ -1098,6 +1098,57 @@ int esr_debug_timeline(esr_handle* h, long long* out, int n_launches) {
   return ESR_OK;
 }
 
+int esr_debug_tc_layer(esr_handle* h, int index, char* name, int name_cap, int32_t* meta, int32_t* entries, int32_t* groups,
+                       float* bias, float* bias9, uint8_t* blob, size_t blob_cap) {
+  if (!h) return ESR_E_INVALID;
+  if (!h->finalized) return fail(h, ESR_E_STATE, "esr_debug_tc_layer before esr_finalize");
+  const DevGraph& dg = h->graphs[1];
+  const int n = (int)dg.g.tc.size();
+  if (index < 0) return n;                     // query: number of tcgen05 layers of the fp16 graph
+  if (index >= n || !meta || !entries || !groups || !bias || !bias9) return fail(h, ESR_E_INVALID, "bad argument");
+  const TcConv& c = dg.g.tc[index];
+  if (name && name_cap > 0) {
+    name[0] = 0;
+    for (auto& op : dg.g.ops)
+      if (op.kind == OP_CONV_TC && op.tc == index) snprintf(name, (size_t)name_cap, "%s", op.name.c_str());
+  }
+  if (c.entries.size() > (size_t)TC_MAX_ENTRIES || c.groups.size() > (size_t)TC_MAX_GROUPS)
+    return fail(h, ESR_E_INVALID, "layer exceeds the kernel's table sizes");
+  meta[0] = c.nchunks; meta[1] = c.halo; meta[2] = c.acc_cols; meta[3] = (int)c.entries.size();
+  meta[4] = (int)c.groups.size(); meta[5] = (int)c.blob.size(); meta[6] = 0; meta[7] = 0;
+  for (int i = 0; i < 4; ++i) meta[8 + i] = c.chunk_c0[i];
+  for (size_t i = 0; i < c.entries.size(); ++i) {
+    const TcPlaneEntry& e = c.entries[i];
+    int32_t* d = entries + 8 * i;
+    d[0] = e.dy; d[1] = e.dx; d[2] = e.chunk; d[3] = e.nsteps; d[4] = e.n; d[5] = e.dcol; d[6] = e.first; d[7] = (int32_t)e.b_off;
+  }
+  // biases live in the parameter tables; the group records hold their arena offsets
+  auto table_b = [&](size_t off) -> const std::vector<float>* {
+    for (auto& t : dg.tables)
+      if (t.off_b == off && !t.b.empty()) return &t.b;
+    return nullptr;
+  };
+  for (size_t gi = 0; gi < c.groups.size(); ++gi) {
+    const TcGroupDecl& gd = c.groups[gi];
+    int32_t* d = groups + 8 * gi;
+    d[0] = gd.col0; d[1] = gd.ncols; d[2] = gd.act; d[3] = gd.res != BUF_NONE ? 1 : 0; d[4] = gd.res_after; d[5] = gd.mode;
+    memcpy(&d[6], &gd.slope, 4);
+    d[7] = gd.off_bias9 >= 0 ? 1 : 0;
+    const std::vector<float>* b = table_b(gd.off_bias);
+    for (int j = 0; j < 64; ++j) bias[gi * 64 + j] = (b && j < (int)b->size()) ? (*b)[j] : 0.f;
+    if (gi == 0 && gd.off_bias9 >= 0) {
+      const std::vector<float>* b9 = table_b((size_t)gd.off_bias9);
+      for (int j = 0; j < 9 * 64; ++j) bias9[j] = (b9 && j < (int)b9->size()) ? (*b9)[j] : 0.f;
+      meta[7] = 1;
+    }
+  }
+  if (blob) {
+    if (blob_cap < c.blob.size()) return fail(h, ESR_E_INVALID, "blob buffer too small");
+    memcpy(blob, c.blob.data(), c.blob.size());
+  }
+  return ESR_OK;
+}
+
 const char* esr_last_error(esr_handle* h) { return h ? h->err.c_str() : "null handle"; }
 
 void esr_destroy(esr_handle* h) {
