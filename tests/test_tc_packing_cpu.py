@@ -171,3 +171,43 @@ def test_every_layer_fits_the_kernel_tables(arch, mid, kw):
         assert (cover == 1).all(), (name, "every accumulator column is overwritten exactly once per tile")
         for col0, ncols, act, has_res, res_after, mode, slope_bits, b9 in L["groups"]:
             assert ncols % 16 == 0 and col0 + ncols <= L["acc_cols"], name
+
+
+def test_rlfn_block_residual_inside_the_c5_gemm():
+    """B2.c5+...: c5(u + x) as one GEMM over the two halves [x | u] of a 128-channel buffer with c5's weights on
+    both (team04_rlfn.py:109-122: out = c3_r(...) + input; c5(out); esa)."""
+    w = {k: v.astype(np.float64) for k, v in _weights(4).items()}
+    L = _layers("rlfn", _weights(4))["B2.c5+esa.conv1+esa.conv_f+esa.conv4"]
+    assert (L["nchunks"], L["halo"], L["acc_cols"]) == (2, 0, 112) and list(L["chunk_c0"][:2]) == [0, 64]
+    rng = np.random.default_rng(3)
+    buf = np.zeros((4, 6, 128))
+    buf[..., :46] = rng.standard_normal((4, 6, 46))            # x
+    buf[..., 64:110] = rng.standard_normal((4, 6, 46))         # u = lrelu(c3_r(...))
+    acc = _replay(L, buf) + np.concatenate([L["bias"][0, :48], L["bias"][1, :16], L["bias"][2, :48]])[None, None]
+    s = (buf[..., :46] + buf[..., 64:110]).transpose(2, 0, 1)[None]
+    c5 = O.conv2d(s, w["B2.c5.weight"], w["B2.c5.bias"])
+    c1_ = O.conv2d(c5, w["B2.esa.conv1.weight"], w["B2.esa.conv1.bias"])
+    cfp = O.conv2d(O.conv2d(c1_, w["B2.esa.conv_f.weight"], w["B2.esa.conv_f.bias"]), w["B2.esa.conv4.weight"], w["B2.esa.conv4.bias"])
+    for got, ref in [(acc[..., :46], c5), (acc[..., 48:64], c1_), (acc[..., 64:110], cfp)]:
+        ref = ref[0].transpose(1, 2, 0)
+        assert np.abs(got - ref).max() < 3e-3 * np.abs(ref).max()
+    assert not L["groups"][:, 3].any()                           # no epilogue residual anywhere in this launch
+
+
+def test_imdn_split_as_permuted_output_columns_and_pixel_shuffle_tail():
+    """model.1.sub.0.conv2: out channels permuted to [remaining 48 | distilled 16] so the next conv reads a
+    contiguous K = 48 (basicblock.py:259-265); model.2: the tail writes through the fused PixelShuffle (mode 1)."""
+    w = _weights(-1)
+    Ls = _layers("imdn", w)
+    L = Ls["model.1.sub.0.conv2"]
+    rng = np.random.default_rng(4)
+    x = np.zeros((5, 6, 64))
+    x[..., :48] = rng.standard_normal((5, 6, 48))
+    acc = _replay(L, x)
+    full = O.conv2d(_nchw(x, 48), _h(w["model.1.sub.0.conv2.0.weight"]), None, 1, 1)[0].transpose(1, 2, 0)   # (H, W, 64)
+    assert np.abs(acc[..., :48] - full[..., 16:]).max() < 1e-10      # remaining channels first
+    assert np.abs(acc[..., 48:64] - full[..., :16]).max() < 1e-10    # then the distilled 16
+    b = w["model.1.sub.0.conv2.0.bias"]
+    np.testing.assert_array_equal(np.concatenate([L["bias"][0, :48], L["bias"][1, :16]]), np.concatenate([b[16:], b[:16]]))
+    tail = Ls["model.2"]
+    assert list(tail["groups"][:, 5]) == [1] and tail["acc_cols"] == 48     # one group, pixel-shuffle store
