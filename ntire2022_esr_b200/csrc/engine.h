@@ -55,6 +55,11 @@ struct TcGroupDecl {
   size_t off_bias = 0;          // float offset in the parameter arena
   long long off_bias9 = -1;     // >= 0: border-class bias table [9][64] (first group only), see TcOutGroup::bias9
 };
+struct TcDensePlane {   // one tap of a layer before packing: w[cin (64 per chunk)][accumulator column]
+  int dy = 0, dx = 0;
+  bool identity = false;   // the exact `+ x` plane of a block residual
+  std::vector<float> w;
+};
 struct TcConv {
   int in = BUF_NONE;
   int nchunks = 1;
@@ -65,6 +70,25 @@ struct TcConv {
   std::vector<TcGroupDecl> groups;
   std::vector<uint8_t> blob;    // pre-swizzled fp16 B blocks
   size_t off_blob = 0;          // byte offset in the device blob arena
+  // unpacked form, kept for the fused-chain packing (conv_chain.cuh)
+  int accP = 0;
+  std::vector<TcDensePlane> dense;
+  std::vector<std::pair<int, int>> segs;
+  std::vector<float> bias;      // [accP]
+};
+
+// A run of consecutive 3x3 tcgen05 layers that conv_chain_kernel executes as one launch
+struct ChainLayerDecl {
+  int tc = -1;                  // index into Graph::tc
+  int np = 0, ksteps = 0, ctr_n = 0, part_bytes = 0, res_smem = 0;
+  int n0 = 0, n1 = 0, g1_ctr = 0, col1 = 0;
+  size_t w_goff = 0;            // offset of the layer inside the chain blob
+};
+struct ChainDecl {
+  int first_op = 0, n_ops = 0;
+  std::vector<ChainLayerDecl> layers;
+  std::vector<uint8_t> blob;    // per layer: 3 dy parts (atoms interleaved over dx), centre block, 128 bias floats
+  size_t off_blob = 0;
 };
 
 struct OpDecl {
@@ -90,6 +114,8 @@ struct Graph {
   std::vector<BufDecl> bufs;
   std::vector<OpDecl> ops;
   std::vector<TcConv> tc;
+  std::vector<ChainDecl> chains;
+  int chain_buf[3] = {BUF_NONE, BUF_NONE, BUF_NONE};   // global copies of the intermediate rows of a chain (halo exchange)
 };
 
 }  // namespace esr

@@ -10,6 +10,8 @@
 #include <cstring>
 #include <list>
 
+#include "chain_host.cuh"
+#include "conv_chain.cuh"
 #include "conv_tc.cuh"
 #include "engine.h"
 #include "graph_builder.cuh"
@@ -61,6 +63,8 @@ struct Engine {
   std::string err;
   // options
   int opt_tc = 1, opt_shift_mode = 0, opt_use_graph = 1, opt_rows_per_item = 0, opt_timeline = 0, opt_dbg_flags = 0, opt_acc_slots = 4, opt_pdl = 0;
+  int opt_chain = 1, opt_chain_store_all = 0, opt_chain_mask = -1;   // mask: bit k enables the k-th chain of the graph (debug)
+  bool attr_tc = false, attr_chain = false, attr_esa = false;   // per-handle (= per-device) function attribute opt-ins
   long long* d_timeline = nullptr;  // 128 stamps per tcgen05 launch (debug option tc_timeline)
   std::list<Plan> plans;
   // host-buffer path: kHostSlots requests in flight.  Every slot owns its device buffers, its workspace and its
@@ -119,6 +123,13 @@ static std::string build_dev_graph(Engine& e, int gid) {
     if (!kv.second.used) return "unexpected key in state_dict: " + kv.first;
   dg.g = std::move(gb.g);
   dg.tables = std::move(gb.tables);
+  if (tc) {
+    for (int i = 0; i < 3; ++i) {
+      dg.g.bufs.push_back(BufDecl{BK_FULL, 64, false});
+      dg.g.chain_buf[i] = (int)dg.g.bufs.size() - 1;
+    }
+    find_chains(dg.g);
+  }
   // parameter arena layout
   size_t nf32 = 0;
   for (auto& t : dg.tables) {
@@ -134,6 +145,10 @@ static std::string build_dev_graph(Engine& e, int gid) {
       if (gd.off_bias9 >= 0) gd.off_bias9 = (long long)dg.tables[gd.off_bias9].off_b;
     }
   }
+  for (auto& ch : dg.g.chains) {
+    ch.off_blob = nblob;
+    nblob += (ch.blob.size() + 1023) / 1024 * 1024;
+  }
   if (e.has_gpu) {
     std::vector<float> host(nf32, 0.f);
     for (auto& t : dg.tables) {
@@ -146,6 +161,7 @@ static std::string build_dev_graph(Engine& e, int gid) {
     if (nblob) {
       std::vector<uint8_t> hb(nblob, 0);
       for (auto& c : dg.g.tc) std::copy(c.blob.begin(), c.blob.end(), hb.begin() + c.off_blob);
+      for (auto& ch : dg.g.chains) std::copy(ch.blob.begin(), ch.blob.end(), hb.begin() + ch.off_blob);
       if (cudaMalloc(&dg.d_blobs, nblob) != cudaSuccess) return "cudaMalloc(blobs) failed";
       if (cudaMemcpy(dg.d_blobs, hb.data(), nblob, cudaMemcpyHostToDevice) != cudaSuccess) return "cudaMemcpy(blobs) failed";
     }
@@ -158,8 +174,13 @@ static std::string build_dev_graph(Engine& e, int gid) {
 struct WsLayout {
   std::vector<size_t> off;
   std::vector<int> H, W;
+  size_t flags_off = 0, flags_bytes = 0;   // halo flags of the fused chains (conv_chain.cuh), zeroed at the start of a forward
   size_t total = 0;
 };
+static size_t chain_flag_ints(int B, int H, int W, int n_layers) {
+  const int nbands = (H + n_layers - 1 + CH_R - 1) / CH_R, strips = (W + TC_TILE_PX - 1) / TC_TILE_PX;
+  return (size_t)B * nbands * strips * n_layers;
+}
 static WsLayout ws_layout(const Graph& g, int B, int H, int W, int dtype) {
   WsLayout L;
   int H2, W2, H3, W3;
@@ -175,6 +196,9 @@ static WsLayout ws_layout(const Graph& g, int B, int H, int W, int dtype) {
     const size_t bytes = (size_t)B * h * w * b.C * (b.f32 ? 4 : elt);
     off += (bytes + 1023) / 1024 * 1024;
   }
+  L.flags_off = off;
+  for (auto& ch : g.chains) L.flags_bytes += (chain_flag_ints(B, H, W, ch.n_ops) * sizeof(int) + 1023) / 1024 * 1024;
+  off += L.flags_bytes;
   L.total = off + 2048;
   return L;
 }
@@ -266,7 +290,7 @@ static int plan_tc(Engine* e, const DevGraph& dg, const TcConv& c, const std::st
     }
     int idx = 0;
     for (auto& l : pl.launches) idx += l.name.rfind("conv_tc", 0) == 0 ? 1 : 0;
-    if (idx < 256) p.dbg = e->d_timeline + (size_t)idx * 128;
+    if (idx < 224) p.dbg = e->d_timeline + (size_t)idx * 128;
   }
   // shared memory carve-up
   size_t off = 0;
@@ -357,15 +381,189 @@ static int plan_tc(Engine* e, const DevGraph& dg, const TcConv& c, const std::st
     d.misc = (uint32_t)s.dcol | ((uint32_t)(s.nsteps & 15) << 16) | (s.first ? 0x80000000u : 0u);
   }
   const int grid = std::min(p.n_items, e->num_sms);
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!e->attr_tc) {   // function attributes are per device: tracked per handle (a handle is bound to one device)
     CUDA_TRY(e, cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-    attr_set = true;
+    e->attr_tc = true;
   }
   pl.launches.push_back(Launch{"conv_tc:" + name, [pk, grid, smem](cudaStream_t s) {
                                  return launch_k(conv_tc_kernel, dim3(grid), dim3(TC_THREADS), smem, s, pk->tmA, pk->tmO[0], pk->tmO[1],
                                                  pk->tmO[2], pk->p);
                                }});
+  return ESR_OK;
+}
+
+
+// Is the chain starting at op `oi` executed as one fused launch for this call?
+static const ChainDecl* chain_at(const Engine* e, const Graph& g, int oi, int W) {
+  if (!e->opt_chain) return nullptr;
+  if ((W + TC_TILE_PX - 1) / TC_TILE_PX > 8) return nullptr;   // one cluster (<= 8 CTAs) spans the strips of a band
+  for (size_t k = 0; k < g.chains.size(); ++k)
+    if (g.chains[k].first_op == oi) return ((e->opt_chain_mask >> (k < 31 ? k : 31)) & 1) ? &g.chains[k] : nullptr;
+  return nullptr;
+}
+
+static int plan_chain(Engine* e, const DevGraph& dg, const ChainDecl& ch, const WsLayout& L, size_t flags_off, Plan& pl,
+                      std::string* name_out) {
+  struct Packed {
+    ChainMaps maps;
+    ChainParams p;
+  };
+  auto pk = std::make_shared<Packed>();
+  memset(pk.get(), 0, sizeof(Packed));
+  ChainParams& p = pk->p;
+  const Graph& g = dg.g;
+  const int B = pl.B, H = pl.H, W = pl.W, nL = ch.n_ops;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(pl.ws);
+  p.B = B; p.H = H; p.W = W; p.n_layers = nL;
+  p.strips = (W + TC_TILE_PX - 1) / TC_TILE_PX;
+  p.nbands = (H + nL - 1 + CH_R - 1) / CH_R;
+  p.n_items = B * p.nbands;
+  p.store_all = e->opt_chain_store_all;
+  p.ps_fp32 = 0;
+  p.ps_out = pl.out;
+  p.flags = reinterpret_cast<int32_t*>(ws + flags_off);
+  p.wblob = dg.d_blobs + ch.off_blob;
+  p.dbg = nullptr;
+  if (e->opt_timeline) {
+    if (!e->d_timeline) {
+      CUDA_TRY(e, cudaMalloc(&e->d_timeline, 256 * 128 * sizeof(long long)));
+      CUDA_TRY(e, cudaMemset(e->d_timeline, 0, 256 * 128 * sizeof(long long)));
+    }
+    int idx = 0;
+    for (auto& l : pl.launches) idx += l.name.rfind("conv_chain", 0) == 0 ? 1 : 0;
+    if (idx < 8) p.dbg = e->d_timeline + (size_t)(224 + 2 * idx) * 128;   // chain records: two 128-stamp slots each, from slot 224
+  }
+  int nmaps = 0;
+  auto add_map = [&](void* base, int Cs, int c_extent, int box_c, int box_w, int swz) -> int {
+    if (nmaps >= CH_MAX_MAPS) return -1;
+    if (make_tensor_map(e, &pk->maps.m[nmaps], base, Cs, c_extent, W, H, B, box_c, box_w, swz)) return -1;
+    return nmaps++;
+  };
+  std::string name;
+  int stage_cols = 0;
+  for (int l = 0; l < nL; ++l) {
+    const ChainLayerDecl& d = ch.layers[l];
+    const TcConv& c = g.tc[d.tc];
+    ChLayer& Lr = p.L[l];
+    const bool last = l == nL - 1;
+    Lr.np = d.np; Lr.ksteps = d.ksteps; Lr.ctr_n = d.ctr_n; Lr.part_bytes = d.part_bytes;
+    Lr.w_goff = (int)d.w_goff;
+    Lr.ring_out = last ? 0 : 1;
+    Lr.res_smem = d.res_smem;
+    const TcGroupDecl& g0 = c.groups[0];
+    auto slope_of = [](const TcGroupDecl& gd) { return gd.act == ACT_RELU ? 0.f : (gd.act == ACT_LRELU ? gd.slope : 1.f); };
+    Lr.n0 = d.n0; Lr.slope0 = slope_of(g0); Lr.mode0 = g0.mode;
+    Lr.swz0 = d.n0 == 64 ? 1 : (d.n0 == 32 ? 2 : (d.n0 == 16 ? 3 : 0));
+    Lr.res = nullptr;
+    if (g0.res != BUF_NONE) {
+      Lr.res = reinterpret_cast<const __half*>(ws + L.off[g0.res]);
+      Lr.res_stride = g.bufs[g0.res].C;
+      Lr.res_coff = g0.res_coff;
+      Lr.res_after = g0.res_after;
+    }
+    Lr.n1 = d.n1; Lr.g1_ctr = d.g1_ctr; Lr.col1 = d.col1;
+    // input maps (box 128 px and box 8 px): layer 0 reads the chain's input buffer, layer l > 0 the global copy of
+    // layer l-1's rows (chain buffer l-1)
+    {
+      __half* base;
+      int Cs;
+      if (l == 0) { Cs = g.bufs[c.in].C; base = reinterpret_cast<__half*>(ws + L.off[c.in]) + c.chunk_c0[0]; }
+      else { Cs = 64; base = reinterpret_cast<__half*>(ws + L.off[g.chain_buf[l - 1]]); }
+      Lr.map_in = add_map(base, Cs, 64, 64, TC_TILE_PX, 1);
+      const int m8 = add_map(base, Cs, 64, 64, 8, 1);
+      if (Lr.map_in < 0 || m8 != Lr.map_in + 1) return fail(e, ESR_E_INVALID, "chain: too many tensor maps");
+    }
+    if (!last) {
+      if (l >= 3) return fail(e, ESR_E_INVALID, "chain: more than three intermediate layers");
+      Lr.map_out = add_map(ws + L.off[g.chain_buf[l]], 64, 64, 64, TC_TILE_PX, 1);
+    } else if (g0.mode == 0) {
+      const int Cs = g.bufs[g0.out].C;
+      __half* base = reinterpret_cast<__half*>(ws + L.off[g0.out]) + g0.out_coff;
+      Lr.map_out = add_map(base, Cs, d.n0, d.n0, TC_TILE_PX, Lr.swz0);
+      stage_cols = std::max(stage_cols, d.n0);
+    }
+    if (d.n1 > 0) {
+      const TcGroupDecl& g1 = c.groups[1];
+      Lr.slope1 = slope_of(g1);
+      Lr.swz1 = d.n1 == 64 ? 1 : (d.n1 == 32 ? 2 : (d.n1 == 16 ? 3 : 0));
+      const int Cs = g.bufs[g1.out].C;
+      __half* base = reinterpret_cast<__half*>(ws + L.off[g1.out]) + g1.out_coff;
+      Lr.map_g1 = add_map(base, Cs, d.n1, d.n1, TC_TILE_PX, Lr.swz1);
+      stage_cols = std::max(stage_cols, d.n1);
+    }
+    if (Lr.map_out < 0 || Lr.map_g1 < 0) return fail(e, ESR_E_INVALID, "chain: too many tensor maps");
+    name += (l ? " | " : "") + g.ops[ch.first_op + l].name;
+  }
+  // TMEM: the centre blocks' accumulators sit at columns [256, 384); a layer hands its accumulator of output row j to
+  // the next layer row by row (ready[j]), which is only valid when both use the same columns for row j.  A layer whose
+  // width differs from its predecessor's therefore gets a region disjoint from it.
+  {
+    bool any_ctr = false;
+    for (int l = 0; l < nL; ++l) any_ctr = any_ctr || ch.layers[l].ctr_n > 0;
+    p.ctr_acc_col = 256;
+    for (int l = 0; l < nL; ++l) {
+      ChLayer& Lr = p.L[l];
+      if (l == 0) { Lr.acc_col = 0; continue; }
+      const ChLayer& P = p.L[l - 1];
+      if (P.np == Lr.np) { Lr.acc_col = P.acc_col; continue; }
+      const int need = CH_R * Lr.np;
+      int pick = -1;
+      for (int cand : {0, 256, 384}) {
+        if (cand + need > 512) continue;
+        if (any_ctr && cand < 384 && cand + need > 256) continue;                       // the centre blocks' columns
+        if (cand < P.acc_col + CH_R * P.np && P.acc_col < cand + need) continue;         // the predecessor's columns
+        pick = cand;
+        break;
+      }
+      if (pick < 0) return fail(e, ESR_E_INVALID, "chain: no disjoint TMEM region for layer " + std::to_string(l));
+      Lr.acc_col = pick;
+    }
+  }
+  for (int i = nmaps; i < CH_MAX_MAPS; ++i) pk->maps.m[i] = pk->maps.m[0];   // every slot is prefetched: keep them valid
+  // shared memory carve-up
+  p.ring_off = 0;
+  p.w_off = CH_SLOTS * CH_SLOT_BYTES;
+  p.ctr_off = p.w_off + CH_W_BYTES;
+  p.stage_off = p.ctr_off + CH_CTR_BYTES;
+  p.stage_bytes = (TC_TILE_PX * std::max(stage_cols, 16) * 2 + 1023) / 1024 * 1024;
+  const size_t smem = (size_t)p.stage_off + 2 * (size_t)p.stage_bytes + 1024;
+  if (smem > kMaxSmem) return fail(e, ESR_E_INVALID, "chain: shared memory budget exceeded");
+  p.tmem_cols = 512;
+  if (!e->attr_chain) {
+    CUDA_TRY(e, cudaFuncSetAttribute(conv_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+    e->attr_chain = true;
+  }
+  // persistent grid: as many clusters (one per band in flight) as fit the device
+  const int strips = p.strips;
+  int max_clusters = e->num_sms / strips;
+  {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(strips * max_clusters)); cfg.blockDim = dim3(CH_THREADS); cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)strips; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, conv_chain_kernel, &cfg) == cudaSuccess && n > 0) max_clusters = std::min(max_clusters, n);
+    else cudaGetLastError();
+  }
+  const int nclusters = std::max(1, std::min(p.n_items, max_clusters));
+  const int grid = nclusters * strips;
+  pl.launches.push_back(Launch{"conv_chain:" + name, [pk, grid, strips, smem](cudaStream_t s) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(CH_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)strips; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = g_pdl ? 2 : 1;
+    return cudaLaunchKernelEx(&cfg, conv_chain_kernel, pk->maps, pk->p);
+  }});
+  if (name_out) *name_out = name;
   return ESR_OK;
 }
 
@@ -407,7 +605,28 @@ static int build_plan(Engine* e, Plan& pl) {
     return ws + L.off[b];
   };
   (void)elt;
-  for (const OpDecl& op : g.ops) {
+  size_t flags_off = L.flags_off;
+  bool flags_cleared = false;
+  for (size_t oi = 0; oi < g.ops.size(); ++oi) {
+    const OpDecl& op = g.ops[oi];
+    if (f16 && op.kind == OP_CONV_TC) {
+      if (const ChainDecl* ch = chain_at(e, g, (int)oi, W)) {
+        if (!flags_cleared) {   // one memset for the halo flags of every chain of the forward
+          void* fp = ws + L.flags_off;
+          const size_t fb = L.flags_bytes;
+          pl.launches.insert(pl.launches.begin(), Launch{"memset:chain_flags", [fp, fb](cudaStream_t s) { return cudaMemsetAsync(fp, 0, fb, s); }});
+          flags_cleared = true;
+        }
+        int rc = plan_chain(e, dg, *ch, L, flags_off, pl, nullptr);
+        if (rc) return rc;
+        flags_off += (chain_flag_ints(B, H, W, ch->n_ops) * sizeof(int) + 1023) / 1024 * 1024;
+        double fl = 0;
+        for (int k = 0; k < ch->n_ops; ++k) fl += op_flops(g.ops[oi + k], B, H, W);
+        pl.launches.back().flops = fl;
+        oi += ch->n_ops - 1;
+        continue;
+      }
+    }
     switch (op.kind) {
       case OP_HEAD:
       case OP_BSRN_HEAD: {
@@ -577,11 +796,10 @@ static int build_plan(Engine* e, Plan& pl) {
         const int ts = small ? 4 : 6;
         const int nblk = B * ((p.H3 + ts - 1) / ts) * ((p.W3 + ts - 1) / ts);
         const size_t smem = (size_t)(9 * 16 * 64 + 2 * 9 * 256 + 144 * 16 + 100 * 16) * sizeof(float);
-        static bool attr_done = false;
-        if (!attr_done) {
+        if (!e->attr_esa) {
           CUDA_TRY(e, cudaFuncSetAttribute(k_esa_chain<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
           CUDA_TRY(e, cudaFuncSetAttribute(k_esa_chain<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          attr_done = true;
+          e->attr_esa = true;
         }
         pl.launches.push_back(Launch{"esa_chain:" + op.name, [=](cudaStream_t s) {
           if (small) return launch_k(k_esa_chain<4>, dim3(nblk), dim3(256), smem, s, p);
@@ -988,7 +1206,24 @@ static Plan* dry_plan(esr_handle* h, int B, int H, int W, int dtype, Plan& tmp) 
     if (p.B == B && p.H == H && p.W == W && p.dtype == dtype && p.gid == gid) return &p;
   // names only: one launch per op
   tmp.launches.clear();
-  for (auto& op : h->graphs[gid].g.ops) {
+  const Graph& dgr = h->graphs[gid].g;
+  bool any_chain = false;
+  for (size_t oi = 0; oi < dgr.ops.size(); ++oi) {
+    const OpDecl& op = dgr.ops[oi];
+    if (dtype == ESR_DTYPE_F16 && op.kind == OP_CONV_TC) {
+      if (const ChainDecl* ch = chain_at(h, dgr, (int)oi, W)) {
+        std::string name;
+        double fl = 0;
+        for (int k = 0; k < ch->n_ops; ++k) {
+          name += (k ? " | " : "") + dgr.ops[oi + k].name;
+          fl += op_flops(dgr.ops[oi + k], B, H, W);
+        }
+        tmp.launches.push_back(Launch{"conv_chain:" + name, nullptr, fl});
+        any_chain = true;
+        oi += ch->n_ops - 1;
+        continue;
+      }
+    }
     static const char* kn[] = {"head", "bsrn_head", "conv_generic", "dwconv", "maxpool", "esa_apply", "conv_tc", "esa_apply2",
                                "esa_conv2_pool", "esa_chain"};
     std::string kname = kn[op.kind];
@@ -996,6 +1231,7 @@ static Plan* dry_plan(esr_handle* h, int B, int H, int W, int dtype, Plan& tmp) 
       kname = "conv16";
     tmp.launches.push_back(Launch{kname + ":" + op.name, nullptr, op_flops(op, B, H, W)});
   }
+  if (any_chain) tmp.launches.insert(tmp.launches.begin(), Launch{"memset:chain_flags", nullptr, 0.0});
   return &tmp;
 }
 
@@ -1048,7 +1284,12 @@ int esr_profile_launches(esr_handle* h, const void* in_nchw, void* out_nchw, int
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t gexec = nullptr;
     cudaError_t err = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
-    for (int r = 0; r < reps && err == cudaSuccess; ++r) err = pl->launches[i].fn(cs);
+    // a fused chain needs its halo flags re-armed before every run (the memset is the plan's first launch)
+    const bool is_chain = pl->launches[i].name.rfind("conv_chain", 0) == 0;
+    for (int r = 0; r < reps && err == cudaSuccess; ++r) {
+      if (is_chain) err = pl->launches[0].fn(cs);
+      if (err == cudaSuccess) err = pl->launches[i].fn(cs);
+    }
     cudaError_t err2 = cudaStreamEndCapture(cs, &graph);
     if (err == cudaSuccess) err = err2;
     if (err == cudaSuccess) err = cudaGraphInstantiate(&gexec, graph, 0);
@@ -1084,6 +1325,9 @@ int esr_set_option(esr_handle* h, const char* key, int value) {
   else if (k == "tc_dbg_flags") h->opt_dbg_flags = value;
   else if (k == "tc_acc_slots") h->opt_acc_slots = value == 4 ? 4 : 2;
   else if (k == "use_pdl") h->opt_pdl = value ? 1 : 0;
+  else if (k == "chain_enable") h->opt_chain = value ? 1 : 0;
+  else if (k == "chain_store_all") h->opt_chain_store_all = value ? 1 : 0;
+  else if (k == "chain_mask") h->opt_chain_mask = value;
   else return fail(h, ESR_E_INVALID, "unknown option: " + k);
   drop_plans(h);
   return ESR_OK;

@@ -244,6 +244,7 @@ struct GraphBuilder {
   struct TcPlane {
     int dy, dx;
     std::vector<float> w;  // [cinP][accP]
+    bool identity = false;
   };
   struct TcBuild {
     int cinP, accP;
@@ -293,6 +294,7 @@ struct GraphBuilder {
   // fp16, w + 1 would wipe out the low bits of w)
   void tc_add_identity(TcBuild& b, int C) {
     TcPlane& p = tc_plane(b, 0, 0, true);
+    p.identity = true;
     for (int c = 0; c < C; ++c) p.w[(size_t)c * b.accP + c] = 1.f;
   }
   // finishes the op: derives the MMA entry list from the non-zero structure, swizzles the B blocks
@@ -371,6 +373,14 @@ struct GraphBuilder {
     for (size_t si = 0; si < b.segs.size(); ++si)   // all-zero segment: still has to be initialised
       if (!seg_started[si]) emit(b.planes[0], 0, si, si + 1, -1);
     c.groups = std::move(groups);
+    c.accP = b.accP;
+    c.segs = b.segs;
+    c.bias = b.bias;
+    for (auto& pl : b.planes) {
+      TcDensePlane d;
+      d.dy = pl.dy; d.dx = pl.dx; d.identity = pl.identity; d.w = pl.w;
+      c.dense.push_back(std::move(d));
+    }
     if (group_bias_out) {
       group_bias_out->clear();
       for (auto& gd : c.groups)

@@ -324,6 +324,8 @@ MODELS = {
     18: dict(arch="bsrn", name="18_RFDNFINALB5", data_range=1.0, weights="team18_bsrn", fn=bsrn_forward),
     # id 22: the same RFDN graph at nf = 40 (models/team22_rep_rfdn.py:101-165, test_demo.py:175-181)
     22: dict(arch="rfdn", name="22_RFDN40", data_range=1.0, weights="team22_rep_rfdn", fn=rfdn_forward),
+    # id 26: IMDN with seven blocks (test_demo.py:203-209); imdn_forward takes the block count from the state dict
+    26: dict(arch="imdn", name="26_IMDN", data_range=1.0, weights="team26_imdn_nb7", fn=imdn_forward),
     # id 40: pruned RFDN, nf = 40, no inner residuals, ESA width 12 (test_demo.py:302-308)
     40: dict(arch="rfdn_pruned", name="40_RFDNPrune", data_range=255.0, weights="team40_rfdn_pruned", fn=rfdn_pruned_forward),
 }
@@ -373,6 +375,57 @@ def psnr(a, b, border=0, peak=255.0):
         b = b[..., border:-border, border:-border] if b.ndim == 4 else b[border:-border, border:-border]
     mse = np.mean((a - b) ** 2)
     return float("inf") if mse == 0 else 20 * math.log10(peak / math.sqrt(mse))
+
+
+# ---------------------------------------------------------------------------------------------
+# MATLAB-style bicubic resize (the DIV2K LR protocol), utils/utils_image.py:565-626 (cubic,
+# calculate_weights_indices) and :704-774 (imresize_np).  Restated per axis as a dense weight matrix:
+# output k sits at u = k / scale + 0.5 (1 - 1 / scale) (1-based), takes ceil(4 / scale) + 2 taps starting at
+# floor(u - 2 / scale) with the antialiasing kernel scale * cubic(scale * d), rows normalised to 1, and taps that
+# fall outside the image are mirrored about the border (the reference's symmetric padding).
+# ---------------------------------------------------------------------------------------------
+def _cubic(d):
+    a = np.abs(d)
+    return np.where(a <= 1, 1.5 * a ** 3 - 2.5 * a ** 2 + 1, np.where(a <= 2, -0.5 * a ** 3 + 2.5 * a ** 2 - 4 * a + 2, 0.0))
+
+
+def _resize_matrix(n_in, scale, antialiasing=True):
+    n_out = int(np.ceil(n_in * scale))
+    kw = 4.0 / scale if (scale < 1 and antialiasing) else 4.0
+    k = np.arange(1, n_out + 1, dtype=np.float64)
+    u = k / scale + 0.5 * (1 - 1 / scale)
+    left = np.floor(u - kw / 2)
+    P = int(np.ceil(kw)) + 2
+    idx = left[:, None] + np.arange(P)[None, :]                      # 1-based input positions
+    d = u[:, None] - idx
+    wgt = scale * _cubic(d * scale) if (scale < 1 and antialiasing) else _cubic(d)
+    wgt = wgt / wgt.sum(axis=1, keepdims=True)
+    idx = idx.astype(np.int64)
+    idx = np.where(idx < 1, 1 - idx, idx)                            # mirror (edge pixel repeated)
+    idx = np.where(idx > n_in, 2 * n_in + 1 - idx, idx)
+    M = np.zeros((n_out, n_in), dtype=np.float64)
+    np.add.at(M, (np.repeat(np.arange(n_out), P), (idx - 1).ravel()), wgt.ravel())
+    return M
+
+
+def imresize_np(img, scale, antialiasing=True):
+    """img: (H, W, C) or (H, W) float array in [0, 1]; returns float32 like the reference (no rounding)."""
+    a = np.asarray(img, dtype=np.float64)
+    squeeze = a.ndim == 2
+    if squeeze:
+        a = a[:, :, None]
+    Mh, Mw = _resize_matrix(a.shape[0], scale, antialiasing), _resize_matrix(a.shape[1], scale, antialiasing)
+    out = np.einsum("ih,hwc->iwc", Mh, a)
+    out = np.einsum("jw,iwc->ijc", Mw, out)
+    out = out.astype(np.float32)
+    return out[:, :, 0] if squeeze else out
+
+
+def shaped_input(seed, h, w, data_range):
+    """Seeded (1,3,h,w) input of the BASELINE-shape goldens (tests/golden/make_golden.py::shaped_input): uniform in
+    [0, data_range), rounded to fp16-representable values so the fp16 engine and the fp32 reference see the same tensor."""
+    rng = np.random.default_rng(int(seed))
+    return (rng.random((1, 3, h, w), dtype=np.float32) * np.float32(data_range)).astype(np.float16).astype(np.float32)
 
 
 def load_weights(path):

@@ -7,9 +7,12 @@ matplotlib, force map_location, chdir to the reference root) and writes, next to
 
   weights/<name>.npz      state-dicts of the four in-scope checkpoints as fp32 numpy arrays
   test_bmp.npz            utils/test.bmp as uint8 HWC RGB (via the reference's imread_uint)
+  test_bmp_lr.npz         the reference's imresize_np (MATLAB bicubic) of test.bmp: x1/4 (64x64), an odd crop, x2
   ref_<arch>_small.npz    seeded small inputs + FULL reference outputs (several odd sizes)
   ref_<arch>_256.npz      reference output on test.bmp (256x256): crops, strided subsample, stats
   ref_rfdn_tiled.npz      reference tiled forward (tile=32, overlap=8) on a 48x40 input
+  ref_<arch>_<H>x<W>.npz  BASELINE.json config shapes (RFDN 339x510 = configs[2], BSRN 270x480 = configs[4]): numpy-seeded
+                          input (regenerated from the seed at test time), crops + strided subsample + sums of the output
 
     python tests/golden/make_golden.py 22         # only the listed model ids
 
@@ -41,9 +44,17 @@ torch.set_num_threads(os.cpu_count())
 
 MODELS = {-1: ("imdn", "imdn_baseline.pth"), 0: ("rfdn", "rfdn_baseline.pth"),
           4: ("rlfn", "team04_rlfn.pth"), 18: ("bsrn", "team18_bsrn.pth"),
-          22: ("rfdn40", "team22_rep_rfdn.pth"), 40: ("rfdn_pruned", "team40_rfdn_pruned.pth")}   # id 22 = RFDN at nf = 40 (test_demo.py:175-181): same graph, SURVEY row N1
+          22: ("rfdn40", "team22_rep_rfdn.pth"), 40: ("rfdn_pruned", "team40_rfdn_pruned.pth"),
+          26: ("imdn_nb7", "team26_imdn_nb7.pth")}   # id 22 = RFDN at nf = 40 (test_demo.py:175-181): same graph, SURVEY row N1
 SMALL_SIZES = [(15, 15), (24, 20), (33, 47), (64, 64)]
 CROPS = [(0, 0), (0, 992), (992, 0), (992, 992), (500, 500), (0, 480), (700, 0), (301, 777)]
+SHAPED = {0: (339, 510), 18: (270, 480)}   # model id -> LR shape of its BASELINE.json config
+
+
+def shaped_input(mid, h, w, data_range):
+    """The seeded input of the BASELINE-shape goldens (tests regenerate it with the same two lines)."""
+    rng = np.random.default_rng(1000 + mid)
+    return (rng.random((1, 3, h, w), dtype=np.float32) * np.float32(data_range)).astype(np.float16).astype(np.float32)
 
 
 def main():
@@ -52,6 +63,12 @@ def main():
     img = util.imread_uint(os.path.join(REF, "utils", "test.bmp"), n_channels=3)
     if not only:
         np.savez_compressed(os.path.join(HERE, "test_bmp.npz"), img=img)
+    if not only or -100 in only:
+        # the DIV2K LR protocol on the one natural image the reference ships: LR = imresize_np(HR / 255, 1/4)
+        # (utils/utils_image.py:704-774), also on an odd-sized crop; pins the oracle's restatement
+        hr = img.astype(np.float32) / 255.
+        np.savez_compressed(os.path.join(HERE, "test_bmp_lr.npz"), lr64=util.imresize_np(hr.copy(), 1 / 4),
+                            lr_odd=util.imresize_np(hr[:130, :77].copy(), 1 / 4), up2=util.imresize_np(hr[:40, :36].copy(), 2))
     for mid, (arch, fname) in MODELS.items():
         if only and mid not in only:
             continue
@@ -86,6 +103,22 @@ def main():
             big["fp32_vs_fp64_maxabs"] = np.float64(np.abs(y - y64).max())
         np.savez_compressed(os.path.join(HERE, f"ref_{arch}_256.npz"), **big)
         print(name, "ok; fp32-vs-fp64 max abs", big.get("fp32_vs_fp64_maxabs"))
+
+        if mid in SHAPED:
+            h, w = SHAPED[mid]
+            xs = shaped_input(mid, h, w, data_range)   # fp16-representable values: the fp16 engine sees the same input
+            with torch.no_grad():
+                ys = test_demo.forward(torch.from_numpy(xs), model, tile).numpy().copy()
+            Ho, Wo = 4 * h, 4 * w
+            cr = [(0, 0), (0, Wo - 32), (Ho - 32, 0), (Ho - 32, Wo - 32), (Ho // 2, Wo // 2), (4 * 127, 4 * 128 - 16), (4 * 255, 4 * 383)]
+            cr = [(min(a, Ho - 32), min(b, Wo - 32)) for a, b in cr]
+            np.savez_compressed(os.path.join(HERE, f"ref_{arch}_{h}x{w}.npz"), data_range=np.float32(data_range),
+                                seed=np.int64(1000 + mid), crops_yx=np.array(cr, dtype=np.int32),
+                                crops=np.stack([ys[0, :, a:a + 32, b:b + 32] for a, b in cr]), sub16=ys[0, :, ::16, ::16].copy(),
+                                sum_c=ys.astype(np.float64).sum(axis=(0, 2, 3)),
+                                sq_sum_c=(ys.astype(np.float64) ** 2).sum(axis=(0, 2, 3)),
+                                minmax=np.array([ys.min(), ys.max()], dtype=np.float32))
+            print(name, "shaped golden", h, w)
 
         if arch == "rfdn":
             g = torch.Generator().manual_seed(7)

@@ -8,7 +8,7 @@ import pytest
 from oracle import esr_oracle as O
 
 ARCHS = [(-1, "imdn"), (0, "rfdn"), (4, "rlfn"), (18, "bsrn")]
-GOLDEN = ARCHS + [(22, "rfdn40"), (40, "rfdn_pruned")]   # (model id, golden file tag): RFDN at nf = 40, pruned RFDN
+GOLDEN = ARCHS + [(22, "rfdn40"), (40, "rfdn_pruned"), (26, "imdn_nb7")]   # (model id, golden file tag): RFDN at nf = 40, pruned RFDN, IMDN nb = 7
 
 
 def _weights(golden_dir, mid):
@@ -100,3 +100,32 @@ def test_torch_port_matches_reference_small_inputs(golden_dir, mid, arch):
     yd = OT.forward(arch, OT.prepare(_weights(golden_dir, mid), torch.float64), z["x3"], torch.float64).numpy()
     yn = O.forward(arch, _weights(golden_dir, mid), z["x3"], dtype=np.float64)
     assert np.abs(yd - yn).max() / dr < 1e-11     # the two restatements agree in fp64
+
+
+def test_imresize_np_matches_reference(golden_dir):
+    """MATLAB-bicubic resize of the DIV2K LR protocol (utils/utils_image.py:704-774) on test.bmp: x1/4 of the whole
+    image, of an odd-sized crop, and a x2 enlargement (no antialiasing branch)."""
+    img = np.load(os.path.join(golden_dir, "test_bmp.npz"))["img"].astype(np.float32) / 255.
+    z = np.load(os.path.join(golden_dir, "test_bmp_lr.npz"))
+    for got, want in [(O.imresize_np(img, 1 / 4), z["lr64"]), (O.imresize_np(img[:130, :77], 1 / 4), z["lr_odd"]),
+                      (O.imresize_np(img[:40, :36], 2), z["up2"])]:
+        assert got.shape == want.shape and got.dtype == np.float32
+        assert np.abs(got - want).max() < 2e-6
+
+
+@pytest.mark.parametrize("mid,arch,shape", [(0, "rfdn", (339, 510)), (18, "bsrn", (270, 480))])
+def test_torch_port_matches_reference_at_baseline_shapes(golden_dir, mid, arch, shape):
+    """BASELINE.json configs[2] / configs[4] LR shapes: the port bench.py times (and the GPU tests use as the
+    full-image reference at these sizes) against crops / a strided subsample / channel sums of the reference's output."""
+    pytest.importorskip("torch")
+    from oracle import esr_oracle_torch as OT
+
+    z = np.load(os.path.join(golden_dir, f"ref_{arch}_{shape[0]}x{shape[1]}.npz"))
+    dr = float(z["data_range"])
+    x = O.shaped_input(int(z["seed"]), shape[0], shape[1], dr)
+    y = OT.forward(arch, OT.prepare(_weights(golden_dir, mid)), x).numpy()
+    assert y.shape == (1, 3, 4 * shape[0], 4 * shape[1])
+    for (a, b), crop in zip(z["crops_yx"], z["crops"]):
+        assert np.abs(y[0, :, a:a + 32, b:b + 32] - crop).max() / dr < 1e-5
+    assert np.abs(y[0, :, ::16, ::16] - z["sub16"]).max() / dr < 1e-5
+    np.testing.assert_allclose(y.astype(np.float64).sum(axis=(0, 2, 3)), z["sum_c"], rtol=2e-6)
