@@ -29,10 +29,10 @@
 // stacked B operand is one strided descriptor; the parts are replaced one by one while the last steps of the
 // previous layer still run (part +1 is dead after step 2, part 0 after step 1, part -1 after step 0).
 //
-// Warp roles (384 threads, 1 CTA / SM): warp 0 TMA producer (input rows, halo rows, weights, flag polling),
-// warp 1 MMA issuer + TMEM owner, warps 2..9 epilogue (TMEM -> bias / residual / activation -> fp16 -> ring slot,
-// staging or pixel-shuffle store; the two edge pixels also go to the neighbour CTAs' rings), warp 10 store warp
-// (TMA stores of halo rows / staged groups, flag release).
+// Warp roles (640 threads, 1 CTA / SM): warp 0 TMA producer (input rows, halo rows, weights, flag polling),
+// warp 1 MMA issuer + TMEM owner, warps 2..17 epilogue (TMEM -> bias / residual / activation -> fp16 -> ring slot,
+// staging or pixel-shuffle store; the two edge pixels also go to the neighbour CTAs' rings with st.async), warp 18
+// store warp (TMA stores of halo rows / staged groups, flag release), warp 19 relay ("slot read" to the neighbours).
 #pragma once
 #include "conv_tc.cuh"
 
@@ -44,10 +44,12 @@ constexpr int CH_SLOTS = CH_R + 2;
 constexpr int CH_SLOT_PX = 144;
 constexpr int CH_SLOT_BYTES = CH_SLOT_PX * 128;    // 18432
 constexpr int CH_PX0 = 8;                          // ring position of tile pixel 0
-constexpr int CH_THREADS = 384;
+constexpr int CH_EPI_WARPS = 16;
+constexpr int CH_THREADS = 32 * (CH_EPI_WARPS + 4);   // warp 0 producer, 1 MMA issuer, 2..17 epilogue, 18 store, 19 relay
 constexpr int CH_MAX_MAPS = 20;
 constexpr int CH_W_BYTES = 3 * 64 * 384;           // three dy parts of a 64-column layer
 constexpr int CH_CTR_BYTES = 32 * 128;
+constexpr int CH_IDENT_BYTES = 64 * 128;           // [64 x 64] fp16 identity, K-major SWIZZLE_128B (block residual as an MMA)
 
 struct ChLayer {
   int32_t np;           // accumulator columns per output row (multiple of 16, <= 64)
@@ -56,7 +58,7 @@ struct ChLayer {
   int32_t part_bytes;   // np * 384
   int32_t w_goff;       // byte offset of the layer's weights inside the chain blob: 3 parts, then the centre block
   int32_t ring_out;     // group 0 is written in place into the row ring (every layer but the last)
-  int32_t res_smem;     // add the layer's own input (centre pixel) before the activation (RFDB `+ input`)
+  int32_t res_smem;     // block residual `+ input` (RFDB): issued as an exact identity MMA on the centre tap
   int32_t n0;           // group 0: accumulator columns [0, n0)
   float slope0;
   int32_t mode0;        // last layer: 0 = staging + TMA store, 1 = fused PixelShuffle(4) store
@@ -77,14 +79,16 @@ struct ChLayer {
 struct ChainParams {
   int32_t B, H, W, n_layers;
   int32_t strips, nbands, n_items;     // item = one band of one image (all strips = one cluster)
-  int32_t ring_off, w_off, ctr_off, stage_off, stage_bytes;
+  int32_t ring_off, w_off, ctr_off, ident_off, stage_off, stage_bytes;
   int32_t tmem_cols, ctr_acc_col;      // consecutive layers of different width use disjoint accumulator regions: the
                                        // per-row "accumulator drained" hand-over only holds between equal layouts
   int32_t store_all;                   // debug: every ring row also goes to global memory
+  int32_t dbg_flags;                   // timing experiments (results are wrong): 1 no MMAs, 2 epilogue only synchronises, 4 no TMA stores
   int32_t ps_fp32;
   void* ps_out;
   int32_t* flags;                      // [n_items][strips][n_layers], zeroed before the launch
   const uint8_t* wblob;
+  const uint8_t* ident;                // device copy of the identity block
   long long* dbg;
   ChLayer L[CH_MAX_LAYERS];
 };
@@ -104,6 +108,12 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
 }
 __device__ __forceinline__ void st_cluster_v4(uint32_t addr, const uint4& v) {
   asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// 16-byte store into a peer CTA's shared memory that completes 16 transaction bytes on a peer mbarrier (no fence
+// and no separate arrive in the sending warp)
+__device__ __forceinline__ void st_async_v4(uint32_t cluster_addr, const uint4& v, uint32_t cluster_mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+               ::"r"(cluster_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(cluster_mbar) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
@@ -156,7 +166,7 @@ __device__ __forceinline__ void umma_f16_ss_hi(uint32_t tmem_d, uint32_t a_lo, u
 __global__ void __launch_bounds__(CH_THREADS, 1)
 conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ ChainParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t tma_full[CH_SLOTS], sd[CH_SLOTS], ready[CH_R], wrote[CH_R], nfree[CH_R], wfull[4], sfree[2], ring_read;
+  __shared__ uint64_t tma_full[CH_SLOTS], sd[CH_SLOTS], ready[CH_R], wrote[CH_R], nfree[CH_R], wfull[4], sfree[2], ring_read, ident_bar;
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float bias_s[CH_MAX_LAYERS][128];   // [0,64): group 0, [64,128): group 1
 
@@ -178,20 +188,21 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
   if (warp == 0 && elect_one()) {
     for (int i = 0; i < CH_SLOTS; ++i) { mbar_init(&tma_full[i], 1); mbar_init(&sd[i], 1); }
     for (int j = 0; j < CH_R; ++j) {
-      mbar_init(&ready[j], TC_EPI_WARPS + 2 * n_side);
-      mbar_init(&wrote[j], TC_EPI_WARPS);
+      mbar_init(&ready[j], CH_EPI_WARPS);
+      mbar_init(&wrote[j], CH_EPI_WARPS);
       mbar_init(&nfree[j], n_side > 0 ? n_side : 1);
     }
     for (int i = 0; i < 4; ++i) mbar_init(&wfull[i], 1);
     mbar_init(&sfree[0], 1); mbar_init(&sfree[1], 1);
     mbar_init(&ring_read, 1);
+    mbar_init(&ident_bar, 1);
     fence_mbar_init();
     for (int i = 0; i < CH_MAX_MAPS; ++i) tma_prefetch_desc(&maps.m[i]);
   }
   if (warp == 1) tmem_alloc(&tmem_base_s, (uint32_t)p.tmem_cols);
-  if (warp >= 2 && warp < 2 + TC_EPI_WARPS) {
+  if (warp >= 2 && warp < 2 + CH_EPI_WARPS) {
     const int tid = threadIdx.x - 64;
-    for (int i = tid; i < nL * 128; i += 32 * TC_EPI_WARPS) {
+    for (int i = tid; i < nL * 128; i += 32 * CH_EPI_WARPS) {
       const int l = i >> 7, c = i & 127;
       const ChLayer& Lr = p.L[l];
       float v = 0.f;
@@ -210,6 +221,8 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (elect_one()) {
+      mbar_arrive_expect_tx(&ident_bar, (uint32_t)CH_IDENT_BYTES);     // constant: does not depend on the previous kernel
+      bulk_load_1d(smem + p.ident_off, p.ident, (uint32_t)CH_IDENT_BYTES, &ident_bar);
       griddep_wait();
       uint32_t g = 0, ctr_cnt = 0, ring_cnt = 0;
       for (int item = (int)cid; item < n_items; item += (int)ncl) {
@@ -226,55 +239,57 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
           int need_step[3];
           {
             const int ob = g > 0 ? p.L[l == 0 ? nL - 1 : l - 1].part_bytes : 1;
-            for (int pp = 0; pp < 3; ++pp) need_step[pp] = g > 0 ? 2 - min(2, ((pp + 1) * Lr.part_bytes - 1) / ob) : R + 1;
+            for (int pp = 0; pp < 3; ++pp) need_step[pp] = g > 0 ? 2 - min(2, ((pp + 1) * Lr.part_bytes - 1) / ob) : R + 1 - pp;
           }
           bool part_loaded[3] = {false, false, false};
           if (l == 0 && g > 0) mbar_wait(&ring_read, (ring_cnt - 1) & 1u);   // TMA stores out of the ring slots have read them
+          auto load_row = [&](int i) {
+            // the slot is also read back by the previous layer's epilogue where that layer adds a residual from the
+            // ring (none does at present: the block residual is an identity MMA)
+            if (!flags_ok) {
+              // halo rows of the band above: its stores of layer l-1 (strips s-1, s, s+1: the halo row includes the
+              // corner pixels) must have reached global memory
+              const int* f = p.flags + ((size_t)(item - 1) * strips) * nL + (l - 1);
+              const long long t0 = clock64();
+              for (int s2 = max(strip - 1, 0); s2 <= min(strip + 1, strips - 1); ++s2) {
+                while (ld_acquire_gpu(f + (size_t)s2 * nL) == 0) {
+                  if (clock64() - t0 > 4000000000LL) {
+                    printf("esr chain: flag timeout block %d item %d layer %d strip %d\n", blockIdx.x, item, l, s2);
+                    __trap();
+                  }
+                }
+              }
+              fence_proxy_async_all();
+              flags_ok = true;
+            }
+            const CUtensorMap* m128 = &maps.m[Lr.map_in];
+            const CUtensorMap* m8 = &maps.m[Lr.map_in + 1];
+            uint8_t* dst = smem + p.ring_off + i * CH_SLOT_BYTES;
+            mbar_arrive_expect_tx(&tma_full[i], (uint32_t)CH_SLOT_BYTES);
+            tma_load_4d(m128, &tma_full[i], dst + CH_PX0 * 128, 0, x0, row0 + i, img);
+            tma_load_4d(m8, &tma_full[i], dst, 0, x0 - 8, row0 + i, img);
+            tma_load_4d(m8, &tma_full[i], dst + (CH_PX0 + TC_TILE_PX) * 128, 0, x0 + TC_TILE_PX, row0 + i, img);
+          };
           for (int i = R + 1; i >= 0; --i) {
             // slot i, and the weight part whose last reader was step i, are free once step i of the previous
             // layer has completed
             if (g > 0) mbar_wait(&sd[i], (g - 1) & 1u);
-            // ... and, where the previous layer's epilogue reads its input row back (block residual from the ring:
-            // output row i-1 reads slot i), once that epilogue is through
-            if (g > 0 && i >= 1 && i <= R && (l == 0 || i < 2) && p.L[l == 0 ? nL - 1 : l - 1].res_smem)
-              mbar_wait(&wrote[i - 1], (g - 1) & 1u);
             for (int part = 0; part < 3; ++part) {   // part 0: dy = +1 (needed first), 1: dy = 0, 2: dy = -1
               if (part_loaded[part] || need_step[part] < i) continue;
               part_loaded[part] = true;
               mbar_arrive_expect_tx(&wfull[part], (uint32_t)Lr.part_bytes);
               bulk_load_1d(smem + p.w_off + part * Lr.part_bytes, wsrc + part * Lr.part_bytes, (uint32_t)Lr.part_bytes, &wfull[part]);
             }
-            if (i == (g > 0 ? 1 : R + 1) && Lr.ctr_n > 0) {   // the centre block's last reader is step 1
+            if (i == (g > 0 ? 1 : R) && Lr.ctr_n > 0) {   // the centre block's last reader is step 1
               mbar_arrive_expect_tx(&wfull[3], (uint32_t)(Lr.ctr_n * 128));
               bulk_load_1d(smem + p.ctr_off, wsrc + 3 * Lr.part_bytes, (uint32_t)(Lr.ctr_n * 128), &wfull[3]);
               ++ctr_cnt;
             }
-            if (l == 0 || i < 2) {
-              if (!flags_ok) {
-                // halo rows of the band above: its stores of layer l-1 (strips s-1, s, s+1: the halo row includes the
-                // corner pixels) must have reached global memory
-                const int* f = p.flags + ((size_t)(item - 1) * strips) * nL + (l - 1);
-                const long long t0 = clock64();
-                for (int s = max(strip - 1, 0); s <= min(strip + 1, strips - 1); ++s) {
-                  while (ld_acquire_gpu(f + (size_t)s * nL) == 0) {
-                    if (clock64() - t0 > 4000000000LL) {
-                      printf("esr chain: flag timeout block %d item %d layer %d strip %d\n", blockIdx.x, item, l, s);
-                      __trap();
-                    }
-                  }
-                }
-                fence_proxy_async_all();
-                flags_ok = true;
-              }
-              const CUtensorMap* m128 = &maps.m[Lr.map_in];
-              const CUtensorMap* m8 = &maps.m[Lr.map_in + 1];
-              uint8_t* dst = smem + p.ring_off + i * CH_SLOT_BYTES;
-              mbar_arrive_expect_tx(&tma_full[i], (uint32_t)CH_SLOT_BYTES);
-              tma_load_4d(m128, &tma_full[i], dst + CH_PX0 * 128, 0, x0, row0 + i, img);
-              tma_load_4d(m8, &tma_full[i], dst, 0, x0 - 8, row0 + i, img);
-              tma_load_4d(m8, &tma_full[i], dst + (CH_PX0 + TC_TILE_PX) * 128, 0, x0 + TC_TILE_PX, row0 + i, img);
-            }
+            if (l == 0) load_row(i);     // the chain's input: every row comes from global memory
           }
+          // the halo rows of the later layers go last: they are needed last (steps 1 and 0), and the flag they wait
+          // for must not hold up the weights
+          if (l > 0) { load_row(1); load_row(0); }
           if (Lr.ring_out) ++ring_cnt;
         }
       }
@@ -285,16 +300,22 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
     // ================================ MMA issuer ==================================
     if (elect_one()) {
       uint32_t g = 0, item_cnt = 0, ctr_cnt = 0;
-      const uint32_t w_base = smem_base + p.w_off, ctr_base = smem_base + p.ctr_off;
+      const bool no_mma = (p.dbg_flags & 1) != 0;
+      const uint32_t w_base = smem_base + p.w_off, ctr_base = smem_base + p.ctr_off, ident_base = smem_base + p.ident_off;
+      mbar_wait(&ident_bar, 0);
       const uint32_t HI_A = 0x40004040u, HI_B3 = 0x400040C0u;   // SBO 1024 / 3072 bytes, version 1, SWIZZLE_128B
       for (int item = (int)cid; item < n_items; item += (int)ncl, ++item_cnt) {
         for (int l = 0; l < nL; ++l, ++g) {
           const ChLayer& Lr = p.L[l];
-          const int np = Lr.np, ks = Lr.ksteps, ctr_n = Lr.ctr_n;
+          const int np = Lr.np, ks = Lr.ksteps, ctr_n = Lr.ctr_n, acc_col = Lr.acc_col, ctr_acc_col = p.ctr_acc_col;
+          const bool res_ident = Lr.res_smem != 0;
           const uint32_t part_bytes = (uint32_t)Lr.part_bytes;
           for (int i = R + 1; i >= 0; --i) {
             if (l == 0 || i < 2) mbar_wait(&tma_full[i], (i < 2 ? g : item_cnt) & 1u);
-            if (g > 0 && i >= 2) mbar_wait_cl(&ready[i - 2], (g - 1) & 1u);   // input row written (own + side pixels), accumulator drained
+            // input row written (own + side pixels), accumulator drained.  The side pixels arrive as st.async
+            // transactions on this barrier (async proxy, like a multicast TMA load): a plain CTA-scope wait orders them;
+            // the cluster-scope acquire form costs an L1 invalidate (~0.5k cycles) per step
+            if (g > 0 && i >= 2) mbar_wait(&ready[i - 2], (g - 1) & 1u);
             if (i == R + 1) mbar_wait(&wfull[0], g & 1u);
             if (i == R) { mbar_wait(&wfull[1], g & 1u); if (ctr_n > 0) mbar_wait(&wfull[3], ctr_cnt & 1u); }
             if (i == R - 1) mbar_wait(&wfull[2], g & 1u);
@@ -303,12 +324,12 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
             const int part0 = i >= 2 ? 0 : (i == 1 ? 1 : 2);
             const uint32_t a_base = ring_base + (uint32_t)i * CH_SLOT_BYTES + (CH_PX0 - 1) * 128;
             const uint32_t b_base = w_base + (uint32_t)part0 * part_bytes;
-            const uint32_t d0 = tmem_base + (uint32_t)(Lr.acc_col + jlo * np);
+            const uint32_t d0 = tmem_base + (uint32_t)(acc_col + jlo * np);
             const uint32_t id_all = umma_idesc_f16((uint32_t)(np * nj)), id_one = umma_idesc_f16((uint32_t)np);
             const uint32_t id_rest = umma_idesc_f16((uint32_t)(np * (nj > 1 ? nj - 1 : 1)));
             const bool first = i >= 2;     // output row i-2 receives its first contribution in this step
 #pragma unroll 1
-            for (int dxi = 0; dxi < 3; ++dxi) {
+            for (int dxi = 0; dxi < (no_mma ? 0 : 3); ++dxi) {
               const uint32_t a_lo0 = 0x10000u | (((a_base + (uint32_t)dxi * 128u) & 0x3FFFFu) >> 4);
               const uint32_t b_lo0 = 0x10000u | (((b_base + (uint32_t)dxi * 1024u) & 0x3FFFFu) >> 4);
               for (int k = 0; k < ks; ++k) {
@@ -321,12 +342,19 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
                 }
               }
             }
-            if (ctr_n > 0 && i >= 1 && i <= R) {   // centre-tap-only block (distillation 1x1) of output row i-1
-              const uint32_t dc = tmem_base + (uint32_t)(p.ctr_acc_col + (i - 1) * 32);
+            if (ctr_n > 0 && i >= 1 && i <= R && !no_mma) {   // centre-tap-only block (distillation 1x1) of output row i-1
+              const uint32_t dc = tmem_base + (uint32_t)(ctr_acc_col + (i - 1) * 32);
               const uint32_t a_lo0 = 0x10000u | (((a_base + 128u) & 0x3FFFFu) >> 4);
               const uint32_t b_lo0 = 0x10000u | ((ctr_base & 0x3FFFFu) >> 4);
               const uint32_t idc = umma_idesc_f16((uint32_t)ctr_n);
               for (int k = 0; k < ks; ++k) umma_f16_ss_hi(dc, a_lo0 + 2u * k, HI_A, b_lo0 + 2u * k, HI_A, idc, k > 0 ? 1u : 0u);
+            }
+            if (res_ident && i >= 1 && i <= R && !no_mma) {   // block residual `+ input`: exact identity tap onto output row i-1 (centre pixel)
+              const uint32_t dr = tmem_base + (uint32_t)(acc_col + (i - 1) * np);
+              const uint32_t a_lo0 = 0x10000u | (((a_base + 128u) & 0x3FFFFu) >> 4);
+              const uint32_t b_lo0 = 0x10000u | ((ident_base & 0x3FFFFu) >> 4);
+              const uint32_t idi = umma_idesc_f16((uint32_t)np);
+              for (int k = 0; k < ks; ++k) umma_f16_ss_hi(dr, a_lo0 + 2u * k, HI_A, b_lo0 + 2u * k, HI_A, idi, 1u);
             }
             umma_commit(&sd[i]);
             if (g < 8) CH_STAMP(1, g * 6 + i);
@@ -336,142 +364,143 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
       }
     }
     __syncwarp();
-  } else if (warp < 2 + TC_EPI_WARPS) {
+  } else if (warp < 2 + CH_EPI_WARPS) {
     // ================================ epilogue ====================================
+    // 16 warps: TMEM lane quadrant q = warp % 4 (hardware rule), `sub` = which 16-column unit of the accumulator row
+    // this warp converts (plus the same unit of the centre block's accumulator for sub < 2).  Everything a tile
+    // needs is hoisted into registers per layer: the parameter bank is re-read after every asm volatile otherwise.
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int sub = (warp - 2) >> 2;
     const int m = q * 32 + lane;
     const int pos = CH_PX0 + m;                 // ring position of this thread's pixel
-    const bool edgeL = hasL && m == 0, edgeR = hasR && m == TC_TILE_PX - 1;
+    const bool edgeL = hasL && m == 0, edgeR = hasR && m == TC_TILE_PX - 1, edge = edgeL || edgeR;
     const int x = x0 + m;
     void* const ps_out = p.ps_out;
     const int ps_fp32 = p.ps_fp32;
+    const int ring_off = p.ring_off, stage_off = p.stage_off, stage_bytes = p.stage_bytes, ctr_acc_col = p.ctr_acc_col;
+    // byte offsets of this thread's two 16-byte pieces inside a ring slot, and of the neighbour's halo position
+    const uint32_t roff0 = (uint32_t)(pos * 128 + (((2 * sub) ^ (pos & 7)) << 4)), roff1 = (uint32_t)(pos * 128 + (((2 * sub + 1) ^ (pos & 7)) << 4));
+    const int rpos = edgeL ? (CH_PX0 + TC_TILE_PX) : (CH_PX0 - 1);
+    const uint32_t xoff0 = (uint32_t)(rpos * 128 + (((2 * sub) ^ (rpos & 7)) << 4)), xoff1 = (uint32_t)(rpos * 128 + (((2 * sub + 1) ^ (rpos & 7)) << 4));
+    const uint32_t nb_rank = edgeL ? rank - 1 : rank + 1;
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    const bool epi_skip = (p.dbg_flags & 2) != 0;
     griddep_wait();
     uint32_t g = 0, stage_cnt = 0, ring_cnt = 0;
     for (int item = (int)cid; item < n_items; item += (int)ncl) {
       const int img = item / nbands, band = item - img * nbands, y0 = band * R;
       for (int l = 0; l < nL; ++l, ++g) {
         const ChLayer& Lr = p.L[l];
-        const int np = Lr.np, n0 = Lr.n0, n1 = Lr.n1, ring_out = Lr.ring_out;
-        const float slope0 = Lr.slope0, slope1 = Lr.slope1;
-        const bool has_gres = Lr.res != nullptr;
+        const int np = Lr.np, n0 = Lr.n0, n1 = Lr.n1;
+        const bool ring_out = Lr.ring_out != 0;
         const bool staged = (n1 > 0) || (!ring_out && Lr.mode0 == 0);
-        // the (up to) three 16-column units of this thread: accumulator units `half` and `half + 2`, centre unit `half`
-        // kind: 0 none, 1 group 0, 2 group 1, 3 zero fill of the ring lanes beyond n0
-        int ukind[3], uc0[3], ucol[3];
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          const int c = (half + 2 * s) * 16;
-          ucol[s] = c;
-          if (c < n0) { ukind[s] = 1; uc0[s] = c; }
-          else if (!Lr.g1_ctr && n1 > 0 && c >= Lr.col1 && c < Lr.col1 + n1) { ukind[s] = 2; uc0[s] = c - Lr.col1; }
-          else if (ring_out) { ukind[s] = 3; uc0[s] = c; }
-          else { ukind[s] = 0; uc0[s] = 0; }
-        }
-        ukind[2] = (Lr.g1_ctr && half * 16 < n1) ? 2 : 0;
-        uc0[2] = half * 16;
-        ucol[2] = half * 16;
+        const int c = sub * 16;
+        // unit A = accumulator columns [c, c+16): kind 0 none, 1 group 0, 2 group 1 (IMDN: columns of the same conv)
+        int kindA = 0, c0A = 0;
+        if (c < n0) { kindA = 1; c0A = c; }
+        else if (!Lr.g1_ctr && n1 > 0 && c >= Lr.col1 && c < Lr.col1 + n1) { kindA = 2; c0A = c - Lr.col1; }
+        const bool zfillA = ring_out && kindA != 1;            // ring lanes this layer does not produce are written as zeros
+        const bool ringA = ring_out && kindA == 1;
+        const bool kindB = Lr.g1_ctr && c < n1;                // unit B = the centre block's columns [c, c+16): always group 1
+        const uint32_t tcolA = (uint32_t)(Lr.acc_col + c), tcolB = (uint32_t)(ctr_acc_col + c);
+        const float* const biasA = &bias_s[l][(kindA == 2 ? 64 : 0) + c0A];
+        const float* const biasB = &bias_s[l][64 + c];
+        const float slopeA = kindA == 2 ? Lr.slope1 : Lr.slope0, slopeB = Lr.slope1;
+        const int resA = (kindA == 1 && Lr.res != nullptr) ? 2 : 0;   // (the block residual arrives through the accumulator)
+        const int res_after = Lr.res_after;
+        const __half* const gres = Lr.res;
+        const int gres_stride = Lr.res_stride, gres_coff = Lr.res_coff + c0A;
+        // staged destinations (unit A when it is not a ring unit, unit B always)
+        const int ncolsA = kindA == 1 ? n0 : n1, swzmA = kindA == 1 ? Lr.swz0 : Lr.swz1, modeA = kindA == 1 ? Lr.mode0 : 0;
+        const int swzA = swzmA == 1 ? (m & 7) : (swzmA == 2 ? ((m >> 1) & 3) : (swzmA == 3 ? ((m >> 2) & 1) : 0));
+        const int swzB = Lr.swz1 == 1 ? (m & 7) : (Lr.swz1 == 2 ? ((m >> 1) & 3) : (Lr.swz1 == 3 ? ((m >> 2) & 1) : 0));
+        const uint32_t strowA = (uint32_t)(m * ncolsA * 2), strowB = (uint32_t)(m * n1 * 2);
         for (int j = R - 1; j >= 0; --j) {
           const int y = y0 - l + j;
           const bool valid = y >= 0 && y < H && x < W;
-          const long long pix = ((long long)img * H + y) * W + x;
-          uint4 rg[2][2];
-          if (has_gres) {
-#pragma unroll
-            for (int s = 0; s < 2; ++s) {
-              rg[s][0] = make_uint4(0, 0, 0, 0); rg[s][1] = make_uint4(0, 0, 0, 0);
-              if (valid && ukind[s] == 1) {
-                const uint4* rp = reinterpret_cast<const uint4*>(Lr.res + pix * Lr.res_stride + Lr.res_coff + uc0[s]);
-                rg[s][0] = rp[0]; rg[s][1] = rp[1];
-              }
-            }
+          uint4 u0 = make_uint4(0, 0, 0, 0), u1 = u0;
+          if (resA == 2 && valid) {     // residual from global memory (LR_conv + fea): fetched before the accumulator is ready
+            const uint4* rp = reinterpret_cast<const uint4*>(gres + (((long long)img * H + y) * W + x) * gres_stride + gres_coff);
+            u0 = rp[0]; u1 = rp[1];
           }
           mbar_wait(&sd[j], g & 1u);
           tc_fence_after_sync();
-          if (warp == 2 && lane == 0 && n_side > 0) {   // my slot j+2 has been read: the neighbours may drop their edge pixels into it
-            if (hasL) mbar_arrive_remote(mapa_u32(smem_u32(&nfree[j]), rank - 1));
-            if (hasR) mbar_arrive_remote(mapa_u32(smem_u32(&nfree[j]), rank + 1));
-          }
-          uint32_t v[3][16];
-          const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-#pragma unroll
-          for (int s = 0; s < 2; ++s)
-            if (ukind[s] == 1 || ukind[s] == 2) tmem_ld16_nc(trow + (uint32_t)(Lr.acc_col + j * np + ucol[s]), v[s]);
-          if (ukind[2]) tmem_ld16_nc(trow + (uint32_t)(p.ctr_acc_col + j * 32 + ucol[2]), v[2]);
+          uint32_t va[16], vb[16];
+          if (kindA) tmem_ld16_nc(trow + tcolA + (uint32_t)(j * np), va);
+          if (kindB) tmem_ld16_nc(trow + tcolB + (uint32_t)(j * 32), vb);
           tmem_ld_wait();
           if (j == R - 1 && l > 0) mbar_wait(&ring_read, (ring_cnt - 1) & 1u);   // TMA stores out of the ring slots of the previous layer have read them
           const uint32_t buf = stage_cnt & 1u;
           if (staged) mbar_wait(&sfree[buf], ((stage_cnt >> 1) & 1u) ^ 1u);
-          if ((edgeL || edgeR) && n_side > 0) mbar_wait_cl(&nfree[j], g & 1u);
-          uint8_t* const slot_out = smem + p.ring_off + (j + 2) * CH_SLOT_BYTES;
-          const uint8_t* const slot_in = smem + p.ring_off + (j + 1) * CH_SLOT_BYTES;
-          uint8_t* const stage = smem + p.stage_off + buf * p.stage_bytes;
-#pragma unroll
-          for (int s = 0; s < 3; ++s) {
-            const int kind = ukind[s];
-            if (kind == 0) continue;
+          if (edge && ring_out) mbar_wait(&nfree[j], ring_cnt & 1u);            // the neighbour has read the slot my edge pixel goes into (a permission, no data)
+          uint8_t* const slot_out = smem + ring_off + (j + 2) * CH_SLOT_BYTES;
+          uint8_t* const stage = smem + stage_off + buf * stage_bytes;
+          if ((kindA || zfillA) && !epi_skip) {
             float f[16];
-            const int c0 = uc0[s];
-            if (kind == 3) {
-#pragma unroll
-              for (int e = 0; e < 16; ++e) f[e] = 0.f;
-            } else {
-              const bool g0 = kind == 1;
-              uint4 u0 = make_uint4(0, 0, 0, 0), u1 = u0;
-              bool has_res = false;
-              if (g0 && Lr.res_smem) {
-                const int ch = c0 >> 3;
-                u0 = *reinterpret_cast<const uint4*>(slot_in + pos * 128 + (((ch) ^ (pos & 7)) << 4));
-                u1 = *reinterpret_cast<const uint4*>(slot_in + pos * 128 + (((ch + 1) ^ (pos & 7)) << 4));
-                has_res = true;
-              } else if (g0 && has_gres) {
-                u0 = rg[s][0]; u1 = rg[s][1];
-                has_res = true;
-              }
-              tc_epi_math16(v[s], &bias_s[l][(g0 ? 0 : 64) + c0], false, g0 ? slope0 : slope1, has_res, u0, u1,
-                            g0 ? Lr.res_after : 0, f);
+            if (kindA) {
+              tc_epi_math16(va, biasA, false, slopeA, resA != 0, u0, u1, res_after, f);
             }
-            if (kind == 3 || (kind == 1 && ring_out)) {
-              uint4 o[2];
+            if (ringA || zfillA) {
+              uint4 o0, o1;
+              __half2* h0 = reinterpret_cast<__half2*>(&o0);
+              __half2* h1 = reinterpret_cast<__half2*>(&o1);
+              const bool nz = valid && ringA;
 #pragma unroll
-              for (int hs = 0; hs < 2; ++hs) {
-                __half2* h2 = reinterpret_cast<__half2*>(&o[hs]);
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-                  h2[e] = valid ? __floats2half2_rn(f[hs * 8 + 2 * e], f[hs * 8 + 2 * e + 1]) : __floats2half2_rn(0.f, 0.f);
-                const int ch = (c0 >> 3) + hs;
-                *reinterpret_cast<uint4*>(slot_out + pos * 128 + ((ch ^ (pos & 7)) << 4)) = o[hs];
+              for (int e = 0; e < 4; ++e) {
+                h0[e] = nz ? __floats2half2_rn(f[2 * e], f[2 * e + 1]) : __floats2half2_rn(0.f, 0.f);
+                h1[e] = nz ? __floats2half2_rn(f[8 + 2 * e], f[8 + 2 * e + 1]) : __floats2half2_rn(0.f, 0.f);
               }
-              if (edgeL || edgeR) {
-                const int rpos = edgeL ? (CH_PX0 + TC_TILE_PX) : (CH_PX0 - 1);
-                const uint32_t rbase = mapa_u32(smem_u32(slot_out) + (uint32_t)rpos * 128u, edgeL ? rank - 1 : rank + 1);
-#pragma unroll
-                for (int hs = 0; hs < 2; ++hs) st_cluster_v4(rbase + (uint32_t)((((c0 >> 3) + hs) ^ (rpos & 7)) << 4), o[hs]);
+              *reinterpret_cast<uint4*>(slot_out + roff0) = o0;
+              *reinterpret_cast<uint4*>(slot_out + roff1) = o1;
+              if (edge) {   // the same 32 bytes into the neighbour's halo position; the store itself signals its ready[j]
+                const uint32_t rslot = mapa_u32(smem_u32(slot_out), nb_rank), rbar = mapa_u32(smem_u32(&ready[j]), nb_rank);
+                st_async_v4(rslot + xoff0, o0, rbar);
+                st_async_v4(rslot + xoff1, o1, rbar);
               }
-            } else {
-              const bool g0 = kind == 1;
-              const int ncols = g0 ? n0 : n1;
-              const int swzm = g0 ? Lr.swz0 : Lr.swz1;
-              const int mode = g0 ? Lr.mode0 : 0;
-              const int swz = swzm == 1 ? (m & 7) : (swzm == 2 ? ((m >> 1) & 3) : (swzm == 3 ? ((m >> 2) & 1) : 0));
-              tc_epi_store16(f, mode, stage + m * (ncols * 2), c0, swz, valid, ps_out, ps_fp32, img, y, x, H, W);
             }
+            if (kindA && !ringA)
+              tc_epi_store16(f, modeA, stage + strowA, c0A, swzA, valid, ps_out, ps_fp32, img, y, x, H, W);
+          }
+          if (kindB && !epi_skip) {
+            float f[16];
+            const uint4 z = make_uint4(0, 0, 0, 0);
+            tc_epi_math16(vb, biasB, false, slopeB, false, z, z, 0, f);
+            tc_epi_store16(f, 0, stage + strowB, c, swzB, valid, ps_out, ps_fp32, img, y, x, H, W);
           }
           tc_fence_before_sync();
-          if (edgeL || edgeR) {
-            fence_proxy_async_all();
-            mbar_arrive_remote(mapa_u32(smem_u32(&ready[j]), edgeL ? rank - 1 : rank + 1));
-          }
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) { mbar_arrive(&ready[j]); mbar_arrive(&wrote[j]); }
+          if (lane == 0) {
+            // ready[j]: CH_EPI_WARPS arrivals + (ring layers) 128 bytes of edge pixels from every side neighbour
+            if (warp == 2 && ring_out && n_side > 0 && !epi_skip) mbar_arrive_expect_tx(&ready[j], (uint32_t)(128 * n_side));
+            else mbar_arrive(&ready[j]);
+            mbar_arrive(&wrote[j]);
+          }
           if (staged) ++stage_cnt;
           if (threadIdx.x == 64 && g < 8) CH_STAMP(2, g * 4 + j);
         }
         if (ring_out) ++ring_cnt;
       }
     }
-  } else if (warp == 2 + TC_EPI_WARPS) {
+  } else if (warp == 3 + CH_EPI_WARPS) {
+    // ================================ relay warp ==================================
+    // tells the side neighbours that this CTA's MMAs have read ring slot j+2 (step j, and with it step j+2, has
+    // completed): they may now drop the edge pixels of their output row j into it
+    if (n_side > 0 && elect_one()) {
+      uint32_t g = 0;
+      for (int item = (int)cid; item < n_items; item += (int)ncl)
+        for (int l = 0; l < nL; ++l, ++g) {
+          const bool ring_out = p.L[l].ring_out != 0;
+          for (int j = R - 1; j >= 0; --j) {
+            mbar_wait(&sd[j], g & 1u);     // every phase is waited for (a parity wait is only valid one phase deep)
+            if (!ring_out) continue;
+            if (hasL) mbar_arrive_remote(mapa_u32(smem_u32(&nfree[j]), rank - 1));
+            if (hasR) mbar_arrive_remote(mapa_u32(smem_u32(&nfree[j]), rank + 1));
+          }
+        }
+    }
+    __syncwarp();
+  } else if (warp == 2 + CH_EPI_WARPS) {
     // ================================ store warp ==================================
     if (elect_one()) {
       uint32_t g = 0, stage_cnt = 0;
@@ -479,17 +508,21 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
         const int img = item / nbands, band = item - img * nbands, y0 = band * R;
         for (int l = 0; l < nL; ++l, ++g) {
           const ChLayer& Lr = p.L[l];
-          const bool staged = (Lr.n1 > 0) || (!Lr.ring_out && Lr.mode0 == 0);
+          const bool ring_out = Lr.ring_out != 0, g0_staged = !ring_out && Lr.mode0 == 0, g1_staged = Lr.n1 > 0;
+          const bool staged = g1_staged || g0_staged;
+          const CUtensorMap* const map_out = &maps.m[Lr.map_out];
+          const CUtensorMap* const map_g1 = &maps.m[Lr.map_g1];
+          const int store_all = p.store_all, ring_off = p.ring_off, stage_off = p.stage_off, stage_bytes = p.stage_bytes;
           for (int j = R - 1; j >= 0; --j) {
             const int y = y0 - l + j;
             const bool row_valid = y >= 0 && y < H;
             mbar_wait(&wrote[j], g & 1u);
             const uint32_t buf = stage_cnt & 1u;
-            if (row_valid) {
-              if (Lr.ring_out && (p.store_all || j >= R - 2))
-                tma_store_4d(&maps.m[Lr.map_out], smem + p.ring_off + (j + 2) * CH_SLOT_BYTES + CH_PX0 * 128, 0, x0, y, img);
-              if (!Lr.ring_out && Lr.mode0 == 0) tma_store_4d(&maps.m[Lr.map_out], smem + p.stage_off + buf * p.stage_bytes, 0, x0, y, img);
-              if (Lr.n1 > 0) tma_store_4d(&maps.m[Lr.map_g1], smem + p.stage_off + buf * p.stage_bytes, 0, x0, y, img);
+            if (row_valid && !(p.dbg_flags & 4)) {
+              if (ring_out && (store_all || j >= R - 2))
+                tma_store_4d(map_out, smem + ring_off + (j + 2) * CH_SLOT_BYTES + CH_PX0 * 128, 0, x0, y, img);
+              if (g0_staged) tma_store_4d(map_out, smem + stage_off + buf * stage_bytes, 0, x0, y, img);
+              if (g1_staged) tma_store_4d(map_g1, smem + stage_off + buf * stage_bytes, 0, x0, y, img);
             }
             tma_store_commit();
             if (staged) {
@@ -497,16 +530,16 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
               mbar_arrive(&sfree[buf]);
               ++stage_cnt;
             }
-            if (Lr.ring_out && j == R - 2) {
+            if (ring_out && j == R - 2) {
               // rows R-1 and R-2 (the halo of the band below) are on their way: publish them
               tma_store_wait_all<0>();
               fence_proxy_async_all();
               __threadfence();
               st_release_gpu(p.flags + ((size_t)item * strips + strip) * nL + l, 1);
-              if (!p.store_all) mbar_arrive(&ring_read);   // ... and the ring slots they came from may be overwritten
+              if (!store_all) mbar_arrive(&ring_read);   // ... and the ring slots they came from may be overwritten
             }
           }
-          if (Lr.ring_out && p.store_all) {
+          if (ring_out && store_all) {
             tma_store_wait_read<0>();
             mbar_arrive(&ring_read);
           }

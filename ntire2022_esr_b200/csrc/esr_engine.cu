@@ -50,6 +50,7 @@ struct DevGraph {            // a Graph plus its device-side parameters
   std::vector<Table> tables;
   float* d_params = nullptr;   // all tables (w, b) back to back
   uint8_t* d_blobs = nullptr;  // all tcgen05 weight blobs
+  uint8_t* d_ident = nullptr;  // [64 x 64] fp16 identity block (K-major SWIZZLE_128B) for the fused chains
   bool built = false;
 };
 
@@ -164,6 +165,13 @@ static std::string build_dev_graph(Engine& e, int gid) {
       for (auto& ch : dg.g.chains) std::copy(ch.blob.begin(), ch.blob.end(), hb.begin() + ch.off_blob);
       if (cudaMalloc(&dg.d_blobs, nblob) != cudaSuccess) return "cudaMalloc(blobs) failed";
       if (cudaMemcpy(dg.d_blobs, hb.data(), nblob, cudaMemcpyHostToDevice) != cudaSuccess) return "cudaMemcpy(blobs) failed";
+    }
+    if (tc) {
+      std::vector<uint8_t> id(CH_IDENT_BYTES, 0);
+      const __half one = __float2half_rn(1.f);
+      for (uint32_t n = 0; n < 64; ++n) memcpy(id.data() + sw128_offset(n, n), &one, 2);
+      if (cudaMalloc(&dg.d_ident, CH_IDENT_BYTES) != cudaSuccess) return "cudaMalloc(ident) failed";
+      if (cudaMemcpy(dg.d_ident, id.data(), CH_IDENT_BYTES, cudaMemcpyHostToDevice) != cudaSuccess) return "cudaMemcpy(ident) failed";
     }
   }
   dg.built = true;
@@ -419,6 +427,7 @@ static int plan_chain(Engine* e, const DevGraph& dg, const ChainDecl& ch, const 
   p.nbands = (H + nL - 1 + CH_R - 1) / CH_R;
   p.n_items = B * p.nbands;
   p.store_all = e->opt_chain_store_all;
+  p.dbg_flags = e->opt_dbg_flags;
   p.ps_fp32 = 0;
   p.ps_out = pl.out;
   p.flags = reinterpret_cast<int32_t*>(ws + flags_off);
@@ -524,7 +533,9 @@ static int plan_chain(Engine* e, const DevGraph& dg, const ChainDecl& ch, const 
   p.ring_off = 0;
   p.w_off = CH_SLOTS * CH_SLOT_BYTES;
   p.ctr_off = p.w_off + CH_W_BYTES;
-  p.stage_off = p.ctr_off + CH_CTR_BYTES;
+  p.ident_off = p.ctr_off + CH_CTR_BYTES;
+  p.stage_off = p.ident_off + CH_IDENT_BYTES;
+  p.ident = dg.d_ident;
   p.stage_bytes = (TC_TILE_PX * std::max(stage_cols, 16) * 2 + 1023) / 1024 * 1024;
   const size_t smem = (size_t)p.stage_off + 2 * (size_t)p.stage_bytes + 1024;
   if (smem > kMaxSmem) return fail(e, ESR_E_INVALID, "chain: shared memory budget exceeded");
@@ -1403,6 +1414,7 @@ void esr_destroy(esr_handle* h) {
     for (auto& dg : h->graphs) {
       if (dg.d_params) cudaFree(dg.d_params);
       if (dg.d_blobs) cudaFree(dg.d_blobs);
+      if (dg.d_ident) cudaFree(dg.d_ident);
     }
     cudaDeviceSynchronize();
     for (auto& sl : h->hslot) {

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--store_all", type=int, default=0)
     ap.add_argument("--mask", type=int, default=-1)
     ap.add_argument("--timeline", type=int, default=0)
+    ap.add_argument("--dbg", type=int, default=0)
     ap.add_argument("--shapes", type=int, nargs="*", default=None)
     a = ap.parse_args()
     import torch
@@ -100,6 +101,7 @@ def main():
             eng.set_option("chain_enable", 1)
             eng.set_option("use_graph", 0)
             eng.set_option("tc_timeline", 1)
+            eng.set_option("tc_dbg_flags", a.dbg)
             for _ in range(3):
                 eng.forward(xt)
             torch.cuda.synchronize()
