@@ -90,6 +90,7 @@ struct ChainParams {
   const uint8_t* wblob;
   const uint8_t* ident;                // device copy of the identity block
   long long* dbg;
+  long long* dbg_blocks;               // optional: [gridDim.x][4] globaltimer stamps (kernel entry, set-up done, roles done, exit)
   ChLayer L[CH_MAX_LAYERS];
 };
 struct ChainMaps { CUtensorMap m[CH_MAX_MAPS]; };
@@ -158,6 +159,11 @@ __device__ __forceinline__ void umma_f16_ss_hi(uint32_t tmem_d, uint32_t a_lo, u
       ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(a_hi), "r"(b_hi));
 }
 
+__device__ __forceinline__ long long global_timer_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 #define CH_STAMP(role, idx)                                                                        \
   do {                                                                                             \
     if (dbg != nullptr && blockIdx.x == 0 && (idx) < 64) dbg[(role) * 64 + (idx)] = clock64();      \
@@ -172,6 +178,7 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   long long* const dbg = p.dbg;
+  if (p.dbg_blocks != nullptr && threadIdx.x == 0) p.dbg_blocks[blockIdx.x * 4 + 0] = global_timer_ns();
   const uint32_t raw_u32 = smem_u32(smem_raw);
   const uint32_t pad = (1024u - (raw_u32 & 1023u)) & 1023u;
   uint8_t* const smem = smem_raw + pad;
@@ -217,6 +224,7 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
   tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_s;
   if (threadIdx.x == 0) CH_STAMP(0, 0);
+  if (p.dbg_blocks != nullptr && threadIdx.x == 0) p.dbg_blocks[blockIdx.x * 4 + 1] = global_timer_ns();
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -298,69 +306,113 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
     __syncwarp();
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
+    // One thread issues every MMA.  It measures ~100 cycles per instruction when the loop is branchy, and the tensor
+    // pipe's queue is short, so (a) the MMAs of a step are issued from straight-line code and (b) the barrier waits of
+    // the NEXT step are taken in the middle of the current step's MMAs: the pipe never drains while this thread polls.
     if (elect_one()) {
-      uint32_t g = 0, item_cnt = 0, ctr_cnt = 0;
       const bool no_mma = (p.dbg_flags & 1) != 0;
       const uint32_t w_base = smem_base + p.w_off, ctr_base = smem_base + p.ctr_off, ident_base = smem_base + p.ident_off;
+      const int ctr_acc_col = p.ctr_acc_col;
       mbar_wait(&ident_bar, 0);
       const uint32_t HI_A = 0x40004040u, HI_B3 = 0x400040C0u;   // SBO 1024 / 3072 bytes, version 1, SWIZZLE_128B
-      for (int item = (int)cid; item < n_items; item += (int)ncl, ++item_cnt) {
-        for (int l = 0; l < nL; ++l, ++g) {
+      // position in the (band, layer, step) sequence
+      int it_item = (int)cid, it_l = 0, it_i = R + 1;
+      uint32_t it_g = 0, it_items = 0, it_ctr = 0;
+      bool it_valid = it_item < n_items;
+      auto wait_step = [&](int l, int i, uint32_t g, uint32_t items, uint32_t ctrc) {
+        if (l == 0 || i < 2) mbar_wait(&tma_full[i], (i < 2 ? g : items) & 1u);
+        // input row written (own + side pixels), accumulator drained.  The side pixels arrive as st.async transactions
+        // on this barrier (async proxy, like a multicast TMA load): a plain CTA-scope wait orders them
+        if (g > 0 && i >= 2) mbar_wait(&ready[i - 2], (g - 1) & 1u);
+        if (i == R + 1) mbar_wait(&wfull[0], g & 1u);
+        if (i == R) { mbar_wait(&wfull[1], g & 1u); if (p.L[l].ctr_n > 0) mbar_wait(&wfull[3], ctrc & 1u); }
+        if (i == R - 1) mbar_wait(&wfull[2], g & 1u);
+      };
+      if (it_valid) wait_step(0, R + 1, 0, 0, 0);
+      // the current layer's constants live in registers and change only at a layer boundary (an indexed read of the
+      // parameter bank per step costs the single issuing thread tens of cycles each)
+      int np = 0, ks = 0, ctr_n = 0, acc_col = 0, part_bytes = 0, cur_l = -1;
+      bool res_ident = false;
+      while (it_valid) {
+        const int l = it_l, i = it_i;
+        const uint32_t g = it_g;
+        if (l != cur_l) {
           const ChLayer& Lr = p.L[l];
-          const int np = Lr.np, ks = Lr.ksteps, ctr_n = Lr.ctr_n, acc_col = Lr.acc_col, ctr_acc_col = p.ctr_acc_col;
-          const bool res_ident = Lr.res_smem != 0;
-          const uint32_t part_bytes = (uint32_t)Lr.part_bytes;
-          for (int i = R + 1; i >= 0; --i) {
-            if (l == 0 || i < 2) mbar_wait(&tma_full[i], (i < 2 ? g : item_cnt) & 1u);
-            // input row written (own + side pixels), accumulator drained.  The side pixels arrive as st.async
-            // transactions on this barrier (async proxy, like a multicast TMA load): a plain CTA-scope wait orders them;
-            // the cluster-scope acquire form costs an L1 invalidate (~0.5k cycles) per step
-            if (g > 0 && i >= 2) mbar_wait(&ready[i - 2], (g - 1) & 1u);
-            if (i == R + 1) mbar_wait(&wfull[0], g & 1u);
-            if (i == R) { mbar_wait(&wfull[1], g & 1u); if (ctr_n > 0) mbar_wait(&wfull[3], ctr_cnt & 1u); }
-            if (i == R - 1) mbar_wait(&wfull[2], g & 1u);
-            tc_fence_after_sync();
-            const int jlo = max(i - 2, 0), jhi = min(i, R - 1), nj = jhi - jlo + 1;
-            const int part0 = i >= 2 ? 0 : (i == 1 ? 1 : 2);
-            const uint32_t a_base = ring_base + (uint32_t)i * CH_SLOT_BYTES + (CH_PX0 - 1) * 128;
-            const uint32_t b_base = w_base + (uint32_t)part0 * part_bytes;
-            const uint32_t d0 = tmem_base + (uint32_t)(acc_col + jlo * np);
-            const uint32_t id_all = umma_idesc_f16((uint32_t)(np * nj)), id_one = umma_idesc_f16((uint32_t)np);
-            const uint32_t id_rest = umma_idesc_f16((uint32_t)(np * (nj > 1 ? nj - 1 : 1)));
-            const bool first = i >= 2;     // output row i-2 receives its first contribution in this step
-#pragma unroll 1
-            for (int dxi = 0; dxi < (no_mma ? 0 : 3); ++dxi) {
-              const uint32_t a_lo0 = 0x10000u | (((a_base + (uint32_t)dxi * 128u) & 0x3FFFFu) >> 4);
-              const uint32_t b_lo0 = 0x10000u | (((b_base + (uint32_t)dxi * 1024u) & 0x3FFFFu) >> 4);
-              for (int k = 0; k < ks; ++k) {
-                const uint32_t a_lo = a_lo0 + 2u * k, b_lo = b_lo0 + 2u * k;
-                if (first && dxi == 0 && k == 0) {
-                  umma_f16_ss_hi(d0, a_lo, HI_A, b_lo, HI_B3, id_one, 0u);
-                  if (nj > 1) umma_f16_ss_hi(d0 + (uint32_t)np, a_lo, HI_A, b_lo + (part_bytes >> 4), HI_B3, id_rest, 1u);
-                } else {
-                  umma_f16_ss_hi(d0, a_lo, HI_A, b_lo, HI_B3, id_all, 1u);
-                }
-              }
-            }
-            if (ctr_n > 0 && i >= 1 && i <= R && !no_mma) {   // centre-tap-only block (distillation 1x1) of output row i-1
-              const uint32_t dc = tmem_base + (uint32_t)(ctr_acc_col + (i - 1) * 32);
-              const uint32_t a_lo0 = 0x10000u | (((a_base + 128u) & 0x3FFFFu) >> 4);
-              const uint32_t b_lo0 = 0x10000u | ((ctr_base & 0x3FFFFu) >> 4);
-              const uint32_t idc = umma_idesc_f16((uint32_t)ctr_n);
-              for (int k = 0; k < ks; ++k) umma_f16_ss_hi(dc, a_lo0 + 2u * k, HI_A, b_lo0 + 2u * k, HI_A, idc, k > 0 ? 1u : 0u);
-            }
-            if (res_ident && i >= 1 && i <= R && !no_mma) {   // block residual `+ input`: exact identity tap onto output row i-1 (centre pixel)
-              const uint32_t dr = tmem_base + (uint32_t)(acc_col + (i - 1) * np);
-              const uint32_t a_lo0 = 0x10000u | (((a_base + 128u) & 0x3FFFFu) >> 4);
-              const uint32_t b_lo0 = 0x10000u | ((ident_base & 0x3FFFFu) >> 4);
-              const uint32_t idi = umma_idesc_f16((uint32_t)np);
-              for (int k = 0; k < ks; ++k) umma_f16_ss_hi(dr, a_lo0 + 2u * k, HI_A, b_lo0 + 2u * k, HI_A, idi, 1u);
-            }
-            umma_commit(&sd[i]);
-            if (g < 8) CH_STAMP(1, g * 6 + i);
-          }
-          if (ctr_n > 0) ++ctr_cnt;
+          np = Lr.np; ks = Lr.ksteps; ctr_n = Lr.ctr_n; acc_col = Lr.acc_col; part_bytes = Lr.part_bytes;
+          res_ident = Lr.res_smem != 0;
+          cur_l = l;
         }
+        const uint32_t pb16 = (uint32_t)part_bytes >> 4;
+        tc_fence_after_sync();
+        if (g < 5) CH_STAMP(3, g * 12 + i * 2);
+        const int jlo = max(i - 2, 0), jhi = min(i, R - 1), nj = jhi - jlo + 1;
+        const int part0 = i >= 2 ? 0 : (i == 1 ? 1 : 2);
+        const uint32_t a_base = ring_base + (uint32_t)i * CH_SLOT_BYTES + (CH_PX0 - 1) * 128;
+        const uint32_t A0 = 0x10000u | ((a_base & 0x3FFFFu) >> 4);                               // + 8 per dx, + 2 per K step
+        const uint32_t B0 = 0x10000u | (((w_base + (uint32_t)(part0 * part_bytes)) & 0x3FFFFu) >> 4);   // + 64 per dx, + 2 per K step
+        const uint32_t d0 = tmem_base + (uint32_t)(acc_col + jlo * np);
+        const uint32_t id_all = umma_idesc_f16((uint32_t)(np * nj)), id_one = umma_idesc_f16((uint32_t)np);
+        const uint32_t id_rest = umma_idesc_f16((uint32_t)(np * (nj > 1 ? nj - 1 : 1)));
+        if (!no_mma) {
+          // dx = -1 and dx = 0 taps; the very first MMA of a step with i >= 2 initialises output row i-2
+          if (i >= 2) {
+            umma_f16_ss_hi(d0, A0, HI_A, B0, HI_B3, id_one, 0u);
+            if (nj > 1) umma_f16_ss_hi(d0 + (uint32_t)np, A0, HI_A, B0 + pb16, HI_B3, id_rest, 1u);
+          } else {
+            umma_f16_ss_hi(d0, A0, HI_A, B0, HI_B3, id_all, 1u);
+          }
+          if (ks > 1) umma_f16_ss_hi(d0, A0 + 2, HI_A, B0 + 2, HI_B3, id_all, 1u);
+          if (ks > 2) umma_f16_ss_hi(d0, A0 + 4, HI_A, B0 + 4, HI_B3, id_all, 1u);
+          if (ks > 3) umma_f16_ss_hi(d0, A0 + 6, HI_A, B0 + 6, HI_B3, id_all, 1u);
+          umma_f16_ss_hi(d0, A0 + 8, HI_A, B0 + 64, HI_B3, id_all, 1u);
+          if (ks > 1) umma_f16_ss_hi(d0, A0 + 10, HI_A, B0 + 66, HI_B3, id_all, 1u);
+          if (ks > 2) umma_f16_ss_hi(d0, A0 + 12, HI_A, B0 + 68, HI_B3, id_all, 1u);
+          if (ks > 3) umma_f16_ss_hi(d0, A0 + 14, HI_A, B0 + 70, HI_B3, id_all, 1u);
+        }
+        // advance, and take the next step's waits while the MMAs above execute
+        {
+          if (--it_i < 0) {
+            it_i = R + 1;
+            if (ctr_n > 0) ++it_ctr;
+            ++it_g;
+            if (++it_l == nL) {
+              it_l = 0;
+              ++it_items;
+              it_item += (int)ncl;
+              it_valid = it_item < n_items;
+            }
+          }
+          if (it_valid) wait_step(it_l, it_i, it_g, it_items, it_ctr);
+        }
+        if (!no_mma) {
+          umma_f16_ss_hi(d0, A0 + 16, HI_A, B0 + 128, HI_B3, id_all, 1u);
+          if (ks > 1) umma_f16_ss_hi(d0, A0 + 18, HI_A, B0 + 130, HI_B3, id_all, 1u);
+          if (ks > 2) umma_f16_ss_hi(d0, A0 + 20, HI_A, B0 + 132, HI_B3, id_all, 1u);
+          if (ks > 3) umma_f16_ss_hi(d0, A0 + 22, HI_A, B0 + 134, HI_B3, id_all, 1u);
+          if (i >= 1 && i <= R) {
+            const uint32_t Ac = A0 + 8;   // centre tap
+            if (ctr_n > 0) {              // centre-tap-only block (distillation 1x1) of output row i-1
+              const uint32_t dc = tmem_base + (uint32_t)(ctr_acc_col + (i - 1) * 32);
+              const uint32_t Bc = 0x10000u | ((ctr_base & 0x3FFFFu) >> 4);
+              const uint32_t idc = umma_idesc_f16((uint32_t)ctr_n);
+              umma_f16_ss_hi(dc, Ac, HI_A, Bc, HI_A, idc, 0u);
+              if (ks > 1) umma_f16_ss_hi(dc, Ac + 2, HI_A, Bc + 2, HI_A, idc, 1u);
+              if (ks > 2) umma_f16_ss_hi(dc, Ac + 4, HI_A, Bc + 4, HI_A, idc, 1u);
+              if (ks > 3) umma_f16_ss_hi(dc, Ac + 6, HI_A, Bc + 6, HI_A, idc, 1u);
+            }
+            if (res_ident) {              // block residual `+ input`: exact identity tap onto output row i-1
+              const uint32_t dr = tmem_base + (uint32_t)(acc_col + (i - 1) * np);
+              const uint32_t Bi = 0x10000u | ((ident_base & 0x3FFFFu) >> 4);
+              umma_f16_ss_hi(dr, Ac, HI_A, Bi, HI_A, id_one, 1u);
+              if (ks > 1) umma_f16_ss_hi(dr, Ac + 2, HI_A, Bi + 2, HI_A, id_one, 1u);
+              if (ks > 2) umma_f16_ss_hi(dr, Ac + 4, HI_A, Bi + 4, HI_A, id_one, 1u);
+              if (ks > 3) umma_f16_ss_hi(dr, Ac + 6, HI_A, Bi + 6, HI_A, id_one, 1u);
+            }
+          }
+        }
+        if (g < 5) CH_STAMP(3, g * 12 + i * 2 + 1);
+        umma_commit(&sd[i]);
+        if (g < 8) CH_STAMP(1, g * 6 + i);
       }
     }
     __syncwarp();
@@ -551,9 +603,14 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
   }
   tc_fence_before_sync();
   __syncthreads();
-  cluster_sync_all();     // no CTA may leave while a peer can still write into its shared memory
+  if (p.dbg_blocks != nullptr && threadIdx.x == 0) p.dbg_blocks[blockIdx.x * 4 + 2] = global_timer_ns();
+  // Every remote access to this CTA's shared memory has been consumed by now (the side pixels through ready[], the
+  // "slot read" arrivals through nfree[]); the cluster barrier is only insurance and carries no data, so the relaxed
+  // form is enough.  (The release / acquire form measured 4-8 us here: it drains the CTA's outstanding global writes.)
+  if (!(p.dbg_flags & 8)) asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   if (threadIdx.x == 0) CH_STAMP(0, 1);
+  if (p.dbg_blocks != nullptr && threadIdx.x == 0) p.dbg_blocks[blockIdx.x * 4 + 3] = global_timer_ns();
 }
 
 }  // namespace esr

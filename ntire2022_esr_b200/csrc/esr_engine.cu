@@ -441,6 +441,7 @@ static int plan_chain(Engine* e, const DevGraph& dg, const ChainDecl& ch, const 
     int idx = 0;
     for (auto& l : pl.launches) idx += l.name.rfind("conv_chain", 0) == 0 ? 1 : 0;
     if (idx < 8) p.dbg = e->d_timeline + (size_t)(224 + 2 * idx) * 128;   // chain records: two 128-stamp slots each, from slot 224
+    if (idx < 8) p.dbg_blocks = e->d_timeline + (size_t)(100 + 5 * idx) * 128;   // per-block globaltimer stamps: 148 x 4 = 592 longs
   }
   int nmaps = 0;
   auto add_map = [&](void* base, int Cs, int c_extent, int box_c, int box_w, int swz) -> int {

@@ -107,6 +107,18 @@ def main():
             torch.cuda.synchronize()
             tl = eng.debug_timeline(240).reshape(240 * 128)
             for ci in range(a.timeline):
+                bt = tl[(100 + 5 * ci) * 128:(100 + 5 * ci) * 128 + 148 * 4].reshape(148, 4)
+                bt = bt[bt[:, 0] > 0]
+                if len(bt):
+                    z = bt[:, 0].min()
+                    print(f"TLB chain {ci}: {len(bt)} blocks; entry {int(bt[:, 0].min() - z)}..{int(bt[:, 0].max() - z)} ns, set-up done "
+                          f"{int(bt[:, 1].min() - z)}..{int(bt[:, 1].max() - z)}, roles done {int(bt[:, 2].min() - z)}..{int(bt[:, 2].max() - z)} "
+                          f"(median {int(np.median(bt[:, 2]) - z)}), exit {int(bt[:, 3].min() - z)}..{int(bt[:, 3].max() - z)}")
+                    for bi in (0, 1, 2, 3, 60, 61, 128, 129):
+                        if bi < len(bt):
+                            print(f"   block {bi}: entry {int(bt[bi, 0] - z)} setup {int(bt[bi, 1] - z)} roles {int(bt[bi, 2] - z)} exit {int(bt[bi, 3] - z)}")
+                    order = np.argsort(bt[:, 2])
+                    print("   roles-done time by block (sorted, every 16th):", [(int(o), int(bt[o, 2] - z)) for o in order[::16]])
                 t = tl[(224 + 2 * ci) * 128:(226 + 2 * ci) * 128]
                 t0 = t[0]
                 print(f"TLC chain {ci}: kernel start 0 end {int(t[1] - t0)} cycles")
@@ -117,6 +129,12 @@ def main():
                         continue
                     print(f"   layer {g}: mma step commit (i=5..0): " + " ".join(f"{int(v - t0):7d}" for v in mm[::-1]) +
                           "   epilogue done (j=3..0): " + " ".join(f"{int(v - t0):7d}" for v in ep[::-1]), flush=True)
+                for g in range(4):
+                    w = t[192 + g * 12: 192 + g * 12 + 12]
+                    if w.max() == 0:
+                        continue
+                    print(f"      issuer layer {g} (i=5..0) waits done / mma issued: " +
+                          "  ".join(f"{int(w[2 * i] - t0)}/{int(w[2 * i + 1] - t0)}" for i in (5, 4, 3, 2, 1, 0)), flush=True)
     print(f"WORST {worst:.3e}")
 
 
