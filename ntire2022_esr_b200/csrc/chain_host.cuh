@@ -106,6 +106,29 @@ inline void chain_pack_layer(const TcConv& c, ChainLayerDecl& d, std::vector<uin
   for (int cc = 0; cc < d.n1; ++cc) bias[64 + cc] = c.bias[b1 + cc];
 }
 
+// Can this layer run as the pointwise last stage of a chain?  One MMA per (K chunk, K step) over all its columns,
+// 64-channel output groups (staged in ring slots) plus at most one 16-channel group (staging buffer).
+inline bool chain_pw_ok(const TcConv& c) {
+  if (c.halo != 0 || c.nchunks < 1 || c.nchunks > 2 || c.groups.empty() || c.groups.size() > 3) return false;
+  const int n = (c.acc_cols + 15) / 16 * 16;
+  if (n > 144 || (int)c.entries.size() != c.nchunks) return false;
+  for (int ch = 0; ch < c.nchunks; ++ch) {
+    const TcPlaneEntry& e = c.entries[ch];
+    if (e.dy != 0 || e.dx != 0 || e.chunk != ch || e.n != n || e.dcol != 0 || e.b_off != (size_t)ch * n * 128) return false;
+    if (c.chunk_c0[ch] != c.chunk_c0[0] + 64 * ch) return false;
+  }
+  int n64 = 0, n16 = 0, col = 0;
+  for (size_t gi = 0; gi < c.groups.size(); ++gi) {
+    const TcGroupDecl& gd = c.groups[gi];
+    if (gd.col0 != col || gd.mode != 0 || gd.off_bias9 >= 0) return false;
+    if (gd.act != ACT_NONE && gd.act != ACT_RELU && gd.act != ACT_LRELU) return false;
+    if (gd.res != BUF_NONE && gi != 0) return false;
+    if (gd.ncols == 64) ++n64; else if (gd.ncols == 16) ++n16; else return false;
+    col += gd.ncols;
+  }
+  return n64 <= 2 && n16 <= 1 && col <= n;
+}
+
 // Scans the op list for maximal runs of chainable layers where each layer feeds the next one.
 inline void find_chains(Graph& g) {
   g.chains.clear();
@@ -138,7 +161,18 @@ inline void find_chains(Graph& g) {
     if (ch.layers.size() >= 2) {
       ch.n_ops = (int)ch.layers.size();
       for (auto& d : ch.layers) chain_pack_layer(g.tc[d.tc], d, ch.blob);
-      i = ch.first_op + ch.n_ops;
+      // a pointwise layer right behind the chain (RFDB c5 + ESA entry, IMDB conv1x1) becomes its last stage
+      const size_t nxt = (size_t)ch.first_op + ch.n_ops;
+      if (nxt < g.ops.size() && g.ops[nxt].kind == OP_CONV_TC && g.tc[ch.layers.back().tc].groups[0].mode == 0 &&
+          chain_pw_ok(g.tc[g.ops[nxt].tc])) {
+        const TcConv& pc = g.tc[g.ops[nxt].tc];
+        ch.pw_tc = g.ops[nxt].tc;
+        ch.pw_bias_goff = (ch.blob.size() + 127) / 128 * 128;
+        ch.blob.resize(ch.pw_bias_goff + 160 * sizeof(float), 0);
+        float* pb = reinterpret_cast<float*>(ch.blob.data() + ch.pw_bias_goff);
+        for (int cc = 0; cc < pc.accP && cc < 160; ++cc) pb[cc] = pc.bias[cc];
+      }
+      i = ch.first_op + ch.n_ops;     // (the pointwise op stays in the op list: whether it is fused is a per-call option)
       g.chains.push_back(std::move(ch));
     } else {
       ++i;

@@ -76,6 +76,37 @@ struct ChLayer {
   const __half* res;    // residual from global memory (LR_conv + fea), nullptr = none
 };
 
+// Optional last stage of a chain: a pointwise (1x1) convolution over the rows the last 3x3 layer has just produced
+// (RFDB: c5 with the ESA entry columns over [d1|d2|d3|r4]; IMDB: conv1x1 over the distilled features).  Its input comes
+// back from global memory (the chain's own staged stores + those of the band above, behind the same flags), its
+// 64-channel output groups are staged in ring slots that are free by then.
+struct ChPw {
+  int32_t enabled;
+  int32_t nchunks;        // 64-channel K chunks of the input buffer (1 or 2)
+  int32_t ksteps;         // K steps per chunk
+  int32_t n;              // accumulator columns (multiple of 16, <= 144)
+  int32_t acc_col;        // rows alternate between TMEM columns acc_col and acc_col + n
+  int32_t w_soff;         // byte offset of the weights inside the shared-memory weight area
+  int32_t w_bytes;        // nchunks * n * 128
+  int32_t w_early;        // 1: that range is dead during the last 3x3 layer (the weights arrive one layer ahead)
+  int32_t map_in;         // tensor map (box 64 ch x 128 px) over the input buffer
+  int32_t chunk_c0[2];    // channel coordinate of each chunk
+  int32_t ngroups;
+  int32_t g_col0[3], g_ncols[3], g_map[3];
+  int32_t g_stage[3];     // 0 / 1: first / second 64-channel group, 2: the 16-channel group (ordinary staging buffer).
+  int32_t nbuf;           // 64-channel groups are staged in ring slots 1 and 0.  nbuf = 2: rows alternate between two
+  int32_t n64;            // buffers per group - one group: slot 1 / slot 0; two groups: slot 1 / weight area [0, 16K) and
+                          // slot 0 / weight area [16K, 32K) (free while the pointwise weights sit behind them)
+  float g_slope[3];
+  int32_t res_stride, res_coff, res_after;
+  int32_t from_smem;      // 1: the last 3x3 layer's group 0 is a channel range of this stage's input: its epilogue writes it
+  int32_t fs_chunk;       //    straight into the A slot (chunk fs_chunk, channels fs_lane0 ..) instead of going through memory
+  int32_t fs_lane0;
+  int32_t bias_goff;      // byte offset of 160 bias floats (per accumulator column) inside the chain blob
+  const __half* res;      // residual of group 0 from global memory, nullptr = none
+  const uint8_t* w;       // device pointer: chunk c at w + c * n * 128 (K-major SWIZZLE_128B)
+};
+
 struct ChainParams {
   int32_t B, H, W, n_layers;
   int32_t strips, nbands, n_items;     // item = one band of one image (all strips = one cluster)
@@ -87,11 +118,13 @@ struct ChainParams {
   int32_t ps_fp32;
   void* ps_out;
   int32_t* flags;                      // [n_items][strips][n_layers], zeroed before the launch
+  int32_t* item_counter;               // bands beyond the first wave are handed out in order through this counter (zeroed with the flags)
   const uint8_t* wblob;
   const uint8_t* ident;                // device copy of the identity block
   long long* dbg;
   long long* dbg_blocks;               // optional: [gridDim.x][4] globaltimer stamps (kernel entry, set-up done, roles done, exit)
   ChLayer L[CH_MAX_LAYERS];
+  ChPw pw;
 };
 struct ChainMaps { CUtensorMap m[CH_MAX_MAPS]; };
 
@@ -169,12 +202,18 @@ __device__ __forceinline__ long long global_timer_ns() {
     if (dbg != nullptr && blockIdx.x == 0 && (idx) < 64) dbg[(role) * 64 + (idx)] = clock64();      \
   } while (0)
 
+// kPw: compiled with / without the optional pointwise last stage (its code costs the common instantiation registers)
+template <bool kPw>
 __global__ void __launch_bounds__(CH_THREADS, 1)
 conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ ChainParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t tma_full[CH_SLOTS], sd[CH_SLOTS], ready[CH_R], wrote[CH_R], nfree[CH_R], wfull[4], sfree[2], ring_read, ident_bar;
+  __shared__ uint64_t tma_full[CH_SLOTS], sd[CH_SLOTS], ready[CH_R], wrote[CH_R], nfree[CH_R], wfull[4], sfree[2], ring_read, ident_bar,
+      pw_afull[2], pw_wfull, pw_drow[CH_R], pw_sfree[2], pw_done, pw_dpre;
+  __shared__ uint64_t sched_bar[2];
+  __shared__ int sched_item[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float bias_s[CH_MAX_LAYERS][128];   // [0,64): group 0, [64,128): group 1
+  __shared__ __align__(16) float pw_bias_s[160];               // pointwise stage: per accumulator column
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   long long* const dbg = p.dbg;
@@ -186,11 +225,24 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
 
   const int R = CH_R;
   const int H = p.H, W = p.W, nL = p.n_layers, strips = p.strips, nbands = p.nbands, n_items = p.n_items;
+  const bool has_pw = kPw && p.pw.enabled != 0;
+  const int nG = nL + (has_pw ? 1 : 0);      // stages per band: the 3x3 layers (+ the pointwise stage)
   const uint32_t rank = cluster_ctarank(), cid = cluster_id_x(), ncl = cluster_nid_x();
   const int strip = (int)rank, x0 = strip * TC_TILE_PX;
   const bool hasL = strip > 0, hasR = strip + 1 < strips;
   const int n_side = (hasL ? 1 : 0) + (hasR ? 1 : 0);
   const uint32_t ring_base = smem_base + p.ring_off;
+  // Band scheduling.  The first band of cluster c is band c; when there are more bands than clusters the rest are
+  // handed out in increasing order through a global counter (the leader CTA's producer fetches the k+1-th band while
+  // the k-th is loading and posts it into every CTA of the cluster).  A band only depends on lower-numbered bands, and
+  // a lower-numbered band is always held by a running (or finished) cluster, so the kernel makes progress with any
+  // number of co-resident clusters - also next to kernels of other streams.
+  const bool dyn_sched = n_items > (int)ncl;
+  auto next_item = [&](uint32_t k) -> int {   // k-th band of this cluster, k >= 1
+    if (!dyn_sched) return n_items;
+    mbar_wait_cl(&sched_bar[k & 1u], ((k - 1) >> 1) & 1u);
+    return *reinterpret_cast<volatile int*>(&sched_item[k & 1u]);
+  };
 
   if (warp == 0 && elect_one()) {
     for (int i = 0; i < CH_SLOTS; ++i) { mbar_init(&tma_full[i], 1); mbar_init(&sd[i], 1); }
@@ -203,6 +255,13 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
     mbar_init(&sfree[0], 1); mbar_init(&sfree[1], 1);
     mbar_init(&ring_read, 1);
     mbar_init(&ident_bar, 1);
+    mbar_init(&sched_bar[0], 1); mbar_init(&sched_bar[1], 1);
+    mbar_init(&pw_afull[0], 1); mbar_init(&pw_afull[1], 1);
+    mbar_init(&pw_wfull, 1);
+    for (int j = 0; j < CH_R; ++j) mbar_init(&pw_drow[j], 1);
+    mbar_init(&pw_sfree[0], 1); mbar_init(&pw_sfree[1], 1);
+    mbar_init(&pw_done, 1);
+    mbar_init(&pw_dpre, 1);
     fence_mbar_init();
     for (int i = 0; i < CH_MAX_MAPS; ++i) tma_prefetch_desc(&maps.m[i]);
   }
@@ -217,6 +276,8 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
       else if (c - 64 < Lr.n1) v = reinterpret_cast<const float*>(p.wblob + Lr.w_goff + 3 * Lr.part_bytes + CH_CTR_BYTES)[c];
       bias_s[l][c] = v;
     }
+    if (p.pw.enabled)
+      for (int i = tid; i < 160; i += 32 * CH_EPI_WARPS) pw_bias_s[i] = reinterpret_cast<const float*>(p.wblob + p.pw.bias_goff)[i];
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -232,9 +293,15 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
       mbar_arrive_expect_tx(&ident_bar, (uint32_t)CH_IDENT_BYTES);     // constant: does not depend on the previous kernel
       bulk_load_1d(smem + p.ident_off, p.ident, (uint32_t)CH_IDENT_BYTES, &ident_bar);
       griddep_wait();
-      uint32_t g = 0, ctr_cnt = 0, ring_cnt = 0;
-      for (int item = (int)cid; item < n_items; item += (int)ncl) {
+      uint32_t g = 0, ctr_cnt = 0, ring_cnt = 0, items = 0;
+      for (int item = (int)cid; item < n_items; ++items, item = next_item(items)) {
         const int img = item / nbands, band = item - img * nbands, y0 = band * R;
+        if (has_pw && g > 0) {
+          // the pointwise stage of the previous band: its MMAs have read their ring slots, its stores have read the two
+          // staging slots, and its weights / accumulators are done with
+          mbar_wait(&sd[0], (g - 1) & 1u);
+          mbar_wait(&pw_done, (items - 1) & 1u);
+        }
         for (int l = 0; l < nL; ++l, ++g) {
           const ChLayer& Lr = p.L[l];
           const int row0 = y0 - l - 1;             // image row of input row 0 of this layer
@@ -248,6 +315,8 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
           {
             const int ob = g > 0 ? p.L[l == 0 ? nL - 1 : l - 1].part_bytes : 1;
             for (int pp = 0; pp < 3; ++pp) need_step[pp] = g > 0 ? 2 - min(2, ((pp + 1) * Lr.part_bytes - 1) / ob) : R + 1 - pp;
+            if (l == 0 && g > 0 && has_pw)   // the previous stage was the pointwise one (all of it has completed, see above)
+              for (int pp = 0; pp < 3; ++pp) need_step[pp] = R + 1 - pp;
           }
           bool part_loaded[3] = {false, false, false};
           if (l == 0 && g > 0) mbar_wait(&ring_read, (ring_cnt - 1) & 1u);   // TMA stores out of the ring slots have read them
@@ -295,10 +364,55 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
             }
             if (l == 0) load_row(i);     // the chain's input: every row comes from global memory
           }
+          if (l == 0 && dyn_sched && rank == 0) {
+            // leader: fetch this cluster's next band and post it to every CTA of the cluster
+            const int nxt = (int)ncl + atomicAdd(p.item_counter, 1);
+            const uint32_t slot = (items + 1) & 1u;
+            for (uint32_t r = 0; r < (uint32_t)strips; ++r) {
+              asm volatile("st.shared::cluster.b32 [%0], %1;" ::"r"(mapa_u32(smem_u32(&sched_item[slot]), r)), "r"(nxt) : "memory");
+              mbar_arrive_remote(mapa_u32(smem_u32(&sched_bar[slot]), r));
+            }
+          }
           // the halo rows of the later layers go last: they are needed last (steps 1 and 0), and the flag they wait
           // for must not hold up the weights
           if (l > 0) { load_row(1); load_row(0); }
           if (Lr.ring_out) ++ring_cnt;
+          if (has_pw && l == nL - 1 && p.pw.w_early) {   // the pointwise weights go where the wider layers' parts used to be
+            mbar_arrive_expect_tx(&pw_wfull, (uint32_t)p.pw.w_bytes);
+            bulk_load_1d(smem + p.w_off + p.pw.w_soff, p.pw.w, (uint32_t)p.pw.w_bytes, &pw_wfull);
+          }
+        }
+        if (has_pw) {
+          // ---- pointwise stage: rows j = R-1 .. 0 of the last 3x3 layer's output rows, K chunks into ring slot pairs
+          const ChPw& P = p.pw;
+          if (!P.w_early) {
+            mbar_wait(&sd[0], (g - 1) & 1u);
+            mbar_arrive_expect_tx(&pw_wfull, (uint32_t)P.w_bytes);
+            bulk_load_1d(smem + p.w_off + P.w_soff, P.w, (uint32_t)P.w_bytes, &pw_wfull);
+          }
+          const CUtensorMap* const mp = &maps.m[P.map_in];
+          if (P.from_smem) {   // everything this CTA stored in the layers before the last one has landed
+            mbar_wait(&pw_dpre, items & 1u);
+            fence_proxy_async_all();
+          }
+          for (int j = R - 1; j >= 0; --j) {
+            const int pr = (R - 1 - j) & 1;          // slot pair: 0 -> slots (5, 4), 1 -> slots (3, 2)
+            if (j >= R - 2) {   // first use: the last 3x3 layer's steps that read those slots
+              mbar_wait(&sd[5 - 2 * pr], (g - 1) & 1u);
+              mbar_wait(&sd[4 - 2 * pr], (g - 1) & 1u);
+            } else {            // second use: the MMAs of pointwise row j+2
+              mbar_wait(&sd[j + 2], g & 1u);
+            }
+            if (!P.from_smem) {
+              mbar_wait(&pw_drow[j], items & 1u);    // this CTA's stores up to row j of the last layer have landed
+              fence_proxy_async_all();
+            }
+            const int y = y0 - (nL - 1) + j;
+            mbar_arrive_expect_tx(&pw_afull[pr], (uint32_t)(P.nchunks * TC_TILE_PX * 128));
+            for (int c = 0; c < P.nchunks; ++c)
+              tma_load_4d(mp, &pw_afull[pr], smem + p.ring_off + (5 - 2 * pr - c) * CH_SLOT_BYTES + CH_PX0 * 128, P.chunk_c0[c], x0, y, img);
+          }
+          ++g;
         }
       }
       (void)ctr_cnt;
@@ -320,13 +434,25 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
       uint32_t it_g = 0, it_items = 0, it_ctr = 0;
       bool it_valid = it_item < n_items;
       auto wait_step = [&](int l, int i, uint32_t g, uint32_t items, uint32_t ctrc) {
-        if (l == 0 || i < 2) mbar_wait(&tma_full[i], (i < 2 ? g : items) & 1u);
+        if (l == nL) {   // pointwise stage: steps R+1, R are empty; step j < R = output row j
+          if (i >= R) return;
+          const int pr = (R - 1 - i) & 1;
+          if (i == R - 1) mbar_wait(&pw_wfull, items & 1u);
+          mbar_wait(&pw_afull[pr], i < R - 2 ? 1u : 0u);     // each slot pair is filled twice per band
+          if (p.pw.from_smem) mbar_wait(&ready[i], (g - 1) & 1u);   // ... and the last 3x3 layer's epilogue has added its channels
+          if (i < R - 2) mbar_wait(&ready[i + 2], g & 1u);    // row i+2 used the same accumulator: drained
+          return;
+        }
+        if (l == 0 && g > 0 && has_pw && i == R + 1)          // the pointwise accumulators overlap every row's columns
+          for (int j = 0; j < R; ++j) mbar_wait(&ready[j], (g - 1) & 1u);
+        const uint32_t g3 = g - items * (uint32_t)(nG - nL);   // 3x3 layers so far (the weight / halo-row barriers skip the pointwise stage)
+        if (l == 0 || i < 2) mbar_wait(&tma_full[i], (i < 2 ? g3 : items) & 1u);
         // input row written (own + side pixels), accumulator drained.  The side pixels arrive as st.async transactions
         // on this barrier (async proxy, like a multicast TMA load): a plain CTA-scope wait orders them
         if (g > 0 && i >= 2) mbar_wait(&ready[i - 2], (g - 1) & 1u);
-        if (i == R + 1) mbar_wait(&wfull[0], g & 1u);
-        if (i == R) { mbar_wait(&wfull[1], g & 1u); if (p.L[l].ctr_n > 0) mbar_wait(&wfull[3], ctrc & 1u); }
-        if (i == R - 1) mbar_wait(&wfull[2], g & 1u);
+        if (i == R + 1) mbar_wait(&wfull[0], g3 & 1u);
+        if (i == R) { mbar_wait(&wfull[1], g3 & 1u); if (p.L[l].ctr_n > 0) mbar_wait(&wfull[3], ctrc & 1u); }
+        if (i == R - 1) mbar_wait(&wfull[2], g3 & 1u);
       };
       if (it_valid) wait_step(0, R + 1, 0, 0, 0);
       // the current layer's constants live in registers and change only at a layer boundary (an indexed read of the
@@ -336,6 +462,33 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
       while (it_valid) {
         const int l = it_l, i = it_i;
         const uint32_t g = it_g;
+        if (l == nL) {
+          // ---- pointwise stage
+          tc_fence_after_sync();
+          if (i < R && !no_mma) {
+            const ChPw& P = p.pw;
+            const int pr = (R - 1 - i) & 1;
+            const uint32_t d = tmem_base + (uint32_t)(P.acc_col + (i & 1) * P.n);
+            const uint32_t idp = umma_idesc_f16((uint32_t)P.n);
+            for (int c = 0; c < P.nchunks; ++c) {
+              const uint32_t Ap = 0x10000u | (((ring_base + (uint32_t)(5 - 2 * pr - c) * CH_SLOT_BYTES + CH_PX0 * 128) & 0x3FFFFu) >> 4);
+              const uint32_t Bp = 0x10000u | (((w_base + (uint32_t)(P.w_soff + c * P.n * 128)) & 0x3FFFFu) >> 4);
+              for (int k = 0; k < P.ksteps; ++k) umma_f16_ss_hi(d, Ap + 2u * k, HI_A, Bp + 2u * k, HI_A, idp, (c | k) ? 1u : 0u);
+            }
+          }
+          umma_commit(&sd[i]);
+          if (g < 8) CH_STAMP(1, g * 6 + i);
+          if (--it_i < 0) {
+            it_i = R + 1;
+            ++it_g;
+            it_l = 0;
+            ++it_items;
+            it_item = next_item(it_items);
+            it_valid = it_item < n_items;
+          }
+          if (it_valid) wait_step(it_l, it_i, it_g, it_items, it_ctr);
+          continue;
+        }
         if (l != cur_l) {
           const ChLayer& Lr = p.L[l];
           np = Lr.np; ks = Lr.ksteps; ctr_n = Lr.ctr_n; acc_col = Lr.acc_col; part_bytes = Lr.part_bytes;
@@ -369,20 +522,27 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
           if (ks > 2) umma_f16_ss_hi(d0, A0 + 12, HI_A, B0 + 68, HI_B3, id_all, 1u);
           if (ks > 3) umma_f16_ss_hi(d0, A0 + 14, HI_A, B0 + 70, HI_B3, id_all, 1u);
         }
-        // advance, and take the next step's waits while the MMAs above execute
+        // advance, and take the next step's waits while the MMAs above execute - unless the next step opens a new
+        // stage: its weights may only be requested once THIS step has been committed (a wider layer after a narrower
+        // one waits for sd[0]), so waiting for them here would be a cycle
+        bool deferred_wait = false;
         {
           if (--it_i < 0) {
             it_i = R + 1;
             if (ctr_n > 0) ++it_ctr;
             ++it_g;
-            if (++it_l == nL) {
+            if (++it_l == nG) {
               it_l = 0;
               ++it_items;
-              it_item += (int)ncl;
+              it_item = next_item(it_items);
               it_valid = it_item < n_items;
             }
           }
-          if (it_valid) wait_step(it_l, it_i, it_g, it_items, it_ctr);
+          if (it_valid) {
+            // (equal widths: the next stage's first weight part was requested after step 2 - safe to wait for here)
+            if (it_i == R + 1 && (it_l == nL || (p.L[it_l].part_bytes - 1) / part_bytes >= 2)) deferred_wait = true;
+            else wait_step(it_l, it_i, it_g, it_items, it_ctr);
+          }
         }
         if (!no_mma) {
           umma_f16_ss_hi(d0, A0 + 16, HI_A, B0 + 128, HI_B3, id_all, 1u);
@@ -413,6 +573,7 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
         if (g < 5) CH_STAMP(3, g * 12 + i * 2 + 1);
         umma_commit(&sd[i]);
         if (g < 8) CH_STAMP(1, g * 6 + i);
+        if (deferred_wait) wait_step(it_l, it_i, it_g, it_items, it_ctr);
       }
     }
     __syncwarp();
@@ -438,14 +599,16 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
     const bool epi_skip = (p.dbg_flags & 2) != 0;
     griddep_wait();
-    uint32_t g = 0, stage_cnt = 0, ring_cnt = 0;
-    for (int item = (int)cid; item < n_items; item += (int)ncl) {
+    uint32_t g = 0, stage_cnt = 0, ring_cnt = 0, pw_rows = 0, items = 0;
+    for (int item = (int)cid; item < n_items; ++items, item = next_item(items)) {
       const int img = item / nbands, band = item - img * nbands, y0 = band * R;
       for (int l = 0; l < nL; ++l, ++g) {
         const ChLayer& Lr = p.L[l];
         const int np = Lr.np, n0 = Lr.n0, n1 = Lr.n1;
         const bool ring_out = Lr.ring_out != 0;
-        const bool staged = (n1 > 0) || (!ring_out && Lr.mode0 == 0);
+        const bool to_pw = has_pw && l == nL - 1 && p.pw.from_smem != 0;   // group 0 goes straight into the pointwise stage's A slot
+        const bool staged = (n1 > 0) || (!ring_out && Lr.mode0 == 0 && !to_pw);
+        const int pw_slot_c = p.pw.fs_chunk, pw_lane0 = p.pw.fs_lane0;
         const int c = sub * 16;
         // unit A = accumulator columns [c, c+16): kind 0 none, 1 group 0, 2 group 1 (IMDN: columns of the same conv)
         int kindA = 0, c0A = 0;
@@ -510,7 +673,22 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
                 st_async_v4(rslot + xoff1, o1, rbar);
               }
             }
-            if (kindA && !ringA)
+            if (kindA == 1 && to_pw) {
+              const int pr = (R - 1 - j) & 1;
+              mbar_wait(&pw_afull[pr], j < R - 2 ? 1u : 0u);     // the rest of that pixel row has arrived from global memory
+              uint8_t* const slot = smem + ring_off + (5 - 2 * pr - pw_slot_c) * CH_SLOT_BYTES;
+              uint4 o0, o1;
+              __half2* h0 = reinterpret_cast<__half2*>(&o0);
+              __half2* h1 = reinterpret_cast<__half2*>(&o1);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                h0[e] = valid ? __floats2half2_rn(f[2 * e], f[2 * e + 1]) : __floats2half2_rn(0.f, 0.f);
+                h1[e] = valid ? __floats2half2_rn(f[8 + 2 * e], f[8 + 2 * e + 1]) : __floats2half2_rn(0.f, 0.f);
+              }
+              const int ch = (pw_lane0 + c0A) >> 3;
+              *reinterpret_cast<uint4*>(slot + pos * 128 + ((ch ^ (pos & 7)) << 4)) = o0;
+              *reinterpret_cast<uint4*>(slot + pos * 128 + (((ch + 1) ^ (pos & 7)) << 4)) = o1;
+            } else if (kindA && !ringA)
               tc_epi_store16(f, modeA, stage + strowA, c0A, swzA, valid, ps_out, ps_fp32, img, y, x, H, W);
           }
           if (kindB && !epi_skip) {
@@ -533,16 +711,100 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
         }
         if (ring_out) ++ring_cnt;
       }
+      if (has_pw) {
+        // ---- pointwise stage: output row j = accumulator slot (j & 1); 16-column units u = sub, sub + 4, sub + 8.
+        // The unit descriptors are resolved into registers here (compile-time indexed), not inside the row loop.
+        const ChPw& P = p.pw;
+        const int n = P.n, nunits = n >> 4, acc_col = P.acc_col, ngr = P.ngroups;
+        const bool dbl = P.nbuf == 2, one64 = P.n64 <= 1;
+        const int w_off_s = p.w_off;
+        const __half* const gres = P.res;
+        const int gres_stride = P.res_stride, gres_coff = P.res_coff, res_after = P.res_after;
+        bool has16 = false;
+        for (int k = 0; k < ngr; ++k) has16 = has16 || P.g_stage[k] == 2;
+        bool uval[3], ures[3];
+        int ucol[3], uc0[3], ust[3];
+        float usl[3];
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+          const int u = sub + 4 * t, c = u * 16;
+          int k = 0;
+          if (ngr > 1 && c >= P.g_col0[1]) k = 1;
+          if (ngr > 2 && c >= P.g_col0[2]) k = 2;
+          const int col0 = k == 0 ? P.g_col0[0] : (k == 1 ? P.g_col0[1] : P.g_col0[2]);
+          const int nc = k == 0 ? P.g_ncols[0] : (k == 1 ? P.g_ncols[1] : P.g_ncols[2]);
+          ucol[t] = c;
+          uc0[t] = c - col0;
+          uval[t] = u < nunits && uc0[t] < nc;
+          ust[t] = k == 0 ? P.g_stage[0] : (k == 1 ? P.g_stage[1] : P.g_stage[2]);
+          usl[t] = k == 0 ? P.g_slope[0] : (k == 1 ? P.g_slope[1] : P.g_slope[2]);
+          ures[t] = k == 0 && gres != nullptr;
+        }
+        for (int j = R - 1; j >= 0; --j) {
+          const int y = y0 - (nL - 1) + j;
+          const bool valid = y >= 0 && y < H && x < W;
+          mbar_wait(&sd[j], g & 1u);
+          tc_fence_after_sync();
+          const uint32_t buf = stage_cnt & 1u;
+          const uint32_t pb = dbl ? (pw_rows & 1u) : 0u, pn = dbl ? (pw_rows >> 1) : pw_rows;   // staging buffer of this row, its use count
+          if (pn > 0) mbar_wait(&pw_sfree[pb], (pn - 1) & 1u);          // the TMA stores of its previous user have read it
+          if (has16) mbar_wait(&sfree[buf], ((stage_cnt >> 1) & 1u) ^ 1u);
+          uint8_t* const stage = smem + stage_off + buf * stage_bytes;
+          const uint32_t tacc = trow + (uint32_t)(acc_col + (j & 1) * n);
+#pragma unroll
+          for (int t = 0; t < 3; ++t) {
+            if (!uval[t]) continue;
+            uint4 u0 = make_uint4(0, 0, 0, 0), u1 = u0;
+            if (ures[t] && valid) {
+              const uint4* rp = reinterpret_cast<const uint4*>(gres + (((long long)img * H + y) * W + x) * gres_stride + gres_coff + uc0[t]);
+              u0 = rp[0]; u1 = rp[1];
+            }
+            uint32_t va[16];
+            tmem_ld16_nc(tacc + (uint32_t)ucol[t], va);
+            tmem_ld_wait();
+            if (epi_skip) continue;
+            float f[16];
+            tc_epi_math16(va, &pw_bias_s[ucol[t]], false, usl[t], ures[t], u0, u1, res_after, f);
+            if (ust[t] == 2) {
+              tc_epi_store16(f, 0, stage + m * 32, uc0[t], (m >> 2) & 1, valid, ps_out, ps_fp32, img, y, x, H, W);
+            } else {
+              // staging row m of this group's buffer for this row (ring slot: behind the 8 pad positions)
+              uint8_t* const sb = one64 ? smem + ring_off + (int)(1u - pb) * CH_SLOT_BYTES + CH_PX0 * 128
+                                        : (pb == 0 ? smem + ring_off + (1 - ust[t]) * CH_SLOT_BYTES + CH_PX0 * 128
+                                                   : smem + w_off_s + ust[t] * 16384);
+              uint4 o0, o1;
+              __half2* h0 = reinterpret_cast<__half2*>(&o0);
+              __half2* h1 = reinterpret_cast<__half2*>(&o1);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                h0[e] = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
+                h1[e] = __floats2half2_rn(f[8 + 2 * e], f[8 + 2 * e + 1]);
+              }
+              const int ch = uc0[t] >> 3;
+              *reinterpret_cast<uint4*>(sb + m * 128 + ((ch ^ (m & 7)) << 4)) = o0;
+              *reinterpret_cast<uint4*>(sb + m * 128 + (((ch + 1) ^ (m & 7)) << 4)) = o1;
+            }
+          }
+          tc_fence_before_sync();
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) { mbar_arrive(&ready[j]); mbar_arrive(&wrote[j]); }
+          if (has16) ++stage_cnt;
+          ++pw_rows;
+          if (threadIdx.x == 64 && g < 8) CH_STAMP(2, g * 4 + j);
+        }
+        ++g;
+      }
     }
   } else if (warp == 3 + CH_EPI_WARPS) {
     // ================================ relay warp ==================================
     // tells the side neighbours that this CTA's MMAs have read ring slot j+2 (step j, and with it step j+2, has
     // completed): they may now drop the edge pixels of their output row j into it
     if (n_side > 0 && elect_one()) {
-      uint32_t g = 0;
-      for (int item = (int)cid; item < n_items; item += (int)ncl)
-        for (int l = 0; l < nL; ++l, ++g) {
-          const bool ring_out = p.L[l].ring_out != 0;
+      uint32_t g = 0, items = 0;
+      for (int item = (int)cid; item < n_items; ++items, item = next_item(items))
+        for (int l = 0; l < nG; ++l, ++g) {
+          const bool ring_out = l < nL && p.L[l].ring_out != 0;
           for (int j = R - 1; j >= 0; --j) {
             mbar_wait(&sd[j], g & 1u);     // every phase is waited for (a parity wait is only valid one phase deep)
             if (!ring_out) continue;
@@ -555,12 +817,13 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
   } else if (warp == 2 + CH_EPI_WARPS) {
     // ================================ store warp ==================================
     if (elect_one()) {
-      uint32_t g = 0, stage_cnt = 0;
-      for (int item = (int)cid; item < n_items; item += (int)ncl) {
+      uint32_t g = 0, stage_cnt = 0, pw_rows = 0, items = 0;
+      for (int item = (int)cid; item < n_items; ++items, item = next_item(items)) {
         const int img = item / nbands, band = item - img * nbands, y0 = band * R;
         for (int l = 0; l < nL; ++l, ++g) {
           const ChLayer& Lr = p.L[l];
-          const bool ring_out = Lr.ring_out != 0, g0_staged = !ring_out && Lr.mode0 == 0, g1_staged = Lr.n1 > 0;
+          const bool to_pw = has_pw && l == nL - 1 && p.pw.from_smem != 0;
+          const bool ring_out = Lr.ring_out != 0, g0_staged = !ring_out && Lr.mode0 == 0 && !to_pw, g1_staged = Lr.n1 > 0;
           const bool staged = g1_staged || g0_staged;
           const CUtensorMap* const map_out = &maps.m[Lr.map_out];
           const CUtensorMap* const map_g1 = &maps.m[Lr.map_g1];
@@ -582,6 +845,13 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
               mbar_arrive(&sfree[buf]);
               ++stage_cnt;
             }
+            if (has_pw && l == nL - 1 && !to_pw) {
+              // the pointwise stage reads rows back from global memory: everything this CTA has stored for output row j
+              // and before (all layers) must have landed
+              tma_store_wait_all<0>();
+              fence_proxy_async_all();
+              mbar_arrive(&pw_drow[j]);
+            }
             if (ring_out && j == R - 2) {
               // rows R-1 and R-2 (the halo of the band below) are on their way: publish them
               tma_store_wait_all<0>();
@@ -595,6 +865,40 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
             tma_store_wait_read<0>();
             mbar_arrive(&ring_read);
           }
+          if (has_pw && p.pw.from_smem && l == nL - 2) {
+            // the pointwise stage reads these layers' staged outputs back from global memory
+            tma_store_wait_all<0>();
+            fence_proxy_async_all();
+            mbar_arrive(&pw_dpre);
+          }
+        }
+        if (has_pw) {
+          const ChPw& P = p.pw;
+          const int ngr = P.ngroups, ring_off = p.ring_off, stage_off = p.stage_off, stage_bytes = p.stage_bytes;
+          bool has16 = false;
+          for (int k = 0; k < ngr; ++k) has16 = has16 || P.g_stage[k] == 2;
+          const bool dbl = P.nbuf == 2, one64 = P.n64 <= 1;
+          for (int j = R - 1; j >= 0; --j) {
+            const int y = y0 - (nL - 1) + j;
+            mbar_wait(&wrote[j], g & 1u);
+            const uint32_t buf = stage_cnt & 1u;
+            const uint32_t pb = dbl ? (pw_rows & 1u) : 0u;
+            if (y >= 0 && y < H && !(p.dbg_flags & 4))
+              for (int k = 0; k < ngr; ++k) {
+                const int q = P.g_stage[k];
+                const uint8_t* src = q == 2 ? smem + stage_off + buf * stage_bytes
+                                   : one64 ? smem + ring_off + (int)(1u - pb) * CH_SLOT_BYTES + CH_PX0 * 128
+                                   : (pb == 0 ? smem + ring_off + (1 - q) * CH_SLOT_BYTES + CH_PX0 * 128 : smem + p.w_off + q * 16384);
+                tma_store_4d(&maps.m[P.g_map[k]], src, 0, x0, y, img);
+              }
+            tma_store_commit();
+            tma_store_wait_read<0>();
+            mbar_arrive(&pw_sfree[pb]);
+            if (has16) { mbar_arrive(&sfree[buf]); ++stage_cnt; }
+            ++pw_rows;
+          }
+          mbar_arrive(&pw_done);
+          ++g;
         }
       }
       tma_store_wait_all<0>();

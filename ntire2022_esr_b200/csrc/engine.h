@@ -85,7 +85,10 @@ struct ChainLayerDecl {
   size_t w_goff = 0;            // offset of the layer inside the chain blob
 };
 struct ChainDecl {
-  int first_op = 0, n_ops = 0;
+  int first_op = 0, n_ops = 0;  // n_ops = number of 3x3 layers
+  int pw_tc = -1;               // >= 0: the op after them is a pointwise layer executed as the chain's last stage (Graph::tc index)
+  size_t pw_bias_goff = 0;      // 160 bias floats (per accumulator column) inside the blob
+  int n_ops_total() const { return n_ops + (pw_tc >= 0 ? 1 : 0); }
   std::vector<ChainLayerDecl> layers;
   std::vector<uint8_t> blob;    // per layer: 3 dy parts (atoms interleaved over dx), centre block, 128 bias floats
   size_t off_blob = 0;

@@ -65,7 +65,11 @@ struct Engine {
   // options
   int opt_tc = 1, opt_shift_mode = 0, opt_use_graph = 1, opt_rows_per_item = 0, opt_timeline = 0, opt_dbg_flags = 0, opt_acc_slots = 4, opt_pdl = 0;
   int opt_chain = 1, opt_chain_store_all = 0, opt_chain_mask = -1;   // mask: bit k enables the k-th chain of the graph (debug)
+  int opt_chain_pw = 0;   // 1: the pointwise layer behind a chain (RFDB c5, IMDB conv1x1) runs as the chain's last stage.  Off by
+                          // default: measured 385.6 vs 375.2 us per RFDN forward at batch 1 - the 144-column epilogue of c5 is
+                          // issue bound either way and inside the chain it queues behind the last 3x3 layer's epilogues
   bool attr_tc = false, attr_chain = false, attr_esa = false;   // per-handle (= per-device) function attribute opt-ins
+  int chain_capacity[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};          // co-resident clusters of the fused chain kernel by cluster size (0 = not queried)
   long long* d_timeline = nullptr;  // 128 stamps per tcgen05 launch (debug option tc_timeline)
   std::list<Plan> plans;
   // host-buffer path: kHostSlots requests in flight.  Every slot owns its device buffers, its workspace and its
@@ -185,9 +189,9 @@ struct WsLayout {
   size_t flags_off = 0, flags_bytes = 0;   // halo flags of the fused chains (conv_chain.cuh), zeroed at the start of a forward
   size_t total = 0;
 };
-static size_t chain_flag_ints(int B, int H, int W, int n_layers) {
+static size_t chain_flag_ints(int B, int H, int W, int n_layers) {   // halo flags + the band counter
   const int nbands = (H + n_layers - 1 + CH_R - 1) / CH_R, strips = (W + TC_TILE_PX - 1) / TC_TILE_PX;
-  return (size_t)B * nbands * strips * n_layers;
+  return (size_t)B * nbands * strips * n_layers + 1;
 }
 static WsLayout ws_layout(const Graph& g, int B, int H, int W, int dtype) {
   WsLayout L;
@@ -402,9 +406,48 @@ static int plan_tc(Engine* e, const DevGraph& dg, const TcConv& c, const std::st
 
 
 // Is the chain starting at op `oi` executed as one fused launch for this call?
-static const ChainDecl* chain_at(const Engine* e, const Graph& g, int oi, int W) {
+// The fused kernel is the small-image (latency) path: it is used when the bands of ONE image fit the device with one
+// cluster each (a property of H and W only, so that image i of a batch is bit-identical to its single-image run whatever
+// the batch size).  Larger images go through the per-layer kernel, which amortises a layer's weights over many tiles;
+// the fused kernel re-streams them for every 4-row band.  Option chain_enable = 2 lifts the limit (tests).
+static const size_t kChainSmemMax = 232448 - 8192;   // dynamic shared memory the chain kernel may ask for (static part: barriers, biases)
+// How many clusters of `strips` chain CTAs the device holds at once (host-only handles: SM count / cluster size).
+static int chain_clusters(Engine* e, int strips) {
+  if (strips < 1 || strips > 8) return 0;
+  if (!e->has_gpu) return e->num_sms / strips;
+  if (e->chain_capacity[strips] == 0) {
+    if (!e->attr_chain) {
+      if (cudaFuncSetAttribute(conv_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemMax) != cudaSuccess ||
+          cudaFuncSetAttribute(conv_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemMax) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+      }
+      e->attr_chain = true;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(strips * (e->num_sms / strips))); cfg.blockDim = dim3(CH_THREADS); cfg.dynamicSmemBytes = kChainSmemMax;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)strips; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, conv_chain_kernel<true>, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = -1; }
+    e->chain_capacity[strips] = n;
+  }
+  return std::max(e->chain_capacity[strips], 0);
+}
+static const ChainDecl* chain_at(Engine* e, const Graph& g, int oi, int B, int H, int W) {
   if (!e->opt_chain) return nullptr;
-  if ((W + TC_TILE_PX - 1) / TC_TILE_PX > 8) return nullptr;   // one cluster (<= 8 CTAs) spans the strips of a band
+  const int strips = (W + TC_TILE_PX - 1) / TC_TILE_PX;
+  if (strips > 8) return nullptr;   // one cluster (<= 8 CTAs) spans the strips of a band
+  if (e->opt_chain != 2) {
+    int max_layers = 2;
+    for (auto& ch : g.chains) max_layers = std::max(max_layers, ch.n_ops);
+    const long long bands = (H + max_layers - 1 + CH_R - 1) / CH_R;   // per image: the choice must not depend on the batch
+    if (bands > chain_clusters(e, strips)) return nullptr;              // size (image i of a batch == its single-image run)
+    (void)B;
+  }
   for (size_t k = 0; k < g.chains.size(); ++k)
     if (g.chains[k].first_op == oi) return ((e->opt_chain_mask >> (k < 31 ? k : 31)) & 1) ? &g.chains[k] : nullptr;
   return nullptr;
@@ -431,6 +474,7 @@ static int plan_chain(Engine* e, const DevGraph& dg, const ChainDecl& ch, const 
   p.ps_fp32 = 0;
   p.ps_out = pl.out;
   p.flags = reinterpret_cast<int32_t*>(ws + flags_off);
+  p.item_counter = p.flags + chain_flag_ints(B, H, W, nL) - 1;
   p.wblob = dg.d_blobs + ch.off_blob;
   p.dbg = nullptr;
   if (e->opt_timeline) {
@@ -529,6 +573,71 @@ static int plan_chain(Engine* e, const DevGraph& dg, const ChainDecl& ch, const 
       Lr.acc_col = pick;
     }
   }
+  if (ch.pw_tc >= 0 && e->opt_chain_pw) {
+    const TcConv& c = g.tc[ch.pw_tc];
+    ChPw& P = p.pw;
+    const ChLayer& last = p.L[nL - 1];
+    P.enabled = 1;
+    P.nchunks = c.nchunks;
+    P.ksteps = 1;
+    for (auto& en : c.entries) P.ksteps = std::max(P.ksteps, en.nsteps);
+    P.n = (c.acc_cols + 15) / 16 * 16;
+    P.w_bytes = c.nchunks * P.n * 128;
+    P.w = dg.d_blobs + c.off_blob;
+    P.bias_goff = (int)ch.pw_bias_goff;
+    // weights: behind the last 3x3 layer's parts if they fit (then they can arrive one layer ahead)
+    if (3 * last.part_bytes + P.w_bytes <= CH_W_BYTES) { P.w_soff = 3 * last.part_bytes; P.w_early = 1; }
+    else { P.w_soff = 0; P.w_early = 0; }
+    // accumulators: two row slots, disjoint from the last 3x3 layer's columns
+    P.acc_col = -1;
+    for (int cand : {0, 256}) {
+      if (cand + 2 * P.n > 512) continue;
+      if (cand < last.acc_col + CH_R * last.np && last.acc_col < cand + 2 * P.n) continue;
+      P.acc_col = cand;
+      break;
+    }
+    if (P.acc_col < 0) return fail(e, ESR_E_INVALID, "chain: no TMEM region for the pointwise stage");
+    {
+      const int Cs = g.bufs[c.in].C;
+      P.map_in = add_map(ws + L.off[c.in], Cs, Cs, 64, TC_TILE_PX, 1);
+      for (int k = 0; k < c.nchunks; ++k) P.chunk_c0[k] = c.chunk_c0[k];
+    }
+    P.ngroups = (int)c.groups.size();
+    int n64 = 0;
+    for (int k = 0; k < P.ngroups; ++k) {
+      const TcGroupDecl& gd = c.groups[k];
+      P.g_col0[k] = gd.col0; P.g_ncols[k] = gd.ncols;
+      P.g_slope[k] = gd.act == ACT_RELU ? 0.f : (gd.act == ACT_LRELU ? gd.slope : 1.f);
+      P.g_stage[k] = gd.ncols == 64 ? n64++ : 2;
+      const int Cs = g.bufs[gd.out].C;
+      __half* base = reinterpret_cast<__half*>(ws + L.off[gd.out]) + gd.out_coff;
+      P.g_map[k] = add_map(base, Cs, gd.ncols, gd.ncols, TC_TILE_PX, gd.ncols == 64 ? 1 : 3);
+      if (gd.ncols == 16) stage_cols = std::max(stage_cols, 16);
+      if (P.g_map[k] < 0) return fail(e, ESR_E_INVALID, "chain: too many tensor maps");
+    }
+    P.n64 = n64;
+    P.nbuf = (n64 <= 1 || P.w_soff >= 32768) ? 2 : 1;
+    const TcGroupDecl& g0 = c.groups[0];
+    if (g0.res != BUF_NONE) {
+      P.res = reinterpret_cast<const __half*>(ws + L.off[g0.res]);
+      P.res_stride = g.bufs[g0.res].C;
+      P.res_coff = g0.res_coff;
+      P.res_after = g0.res_after;
+    }
+    if (P.map_in < 0) return fail(e, ESR_E_INVALID, "chain: too many tensor maps");
+    {   // the last 3x3 layer's output is a channel range of this stage's input (r4 inside [d1|d2|d3|r4]): hand it over in
+        // shared memory instead of through a store + load
+      const TcGroupDecl& lg = g.tc[ch.layers[nL - 1].tc].groups[0];
+      const int rel = lg.out_coff - c.chunk_c0[0];
+      if (lg.out == c.in && lg.mode == 0 && lg.res == BUF_NONE && rel >= 0 && rel / 64 < c.nchunks && rel % 16 == 0 &&
+          rel % 64 + last.n0 <= 64 && last.n0 % 16 == 0 && last.n1 == 0) {
+        P.from_smem = 1;
+        P.fs_chunk = rel / 64;
+        P.fs_lane0 = rel % 64;
+      }
+    }
+    name += " | " + g.ops[ch.first_op + nL].name;
+  }
   for (int i = nmaps; i < CH_MAX_MAPS; ++i) pk->maps.m[i] = pk->maps.m[0];   // every slot is prefetched: keep them valid
   // shared memory carve-up
   p.ring_off = 0;
@@ -539,27 +648,11 @@ static int plan_chain(Engine* e, const DevGraph& dg, const ChainDecl& ch, const 
   p.ident = dg.d_ident;
   p.stage_bytes = (TC_TILE_PX * std::max(stage_cols, 16) * 2 + 1023) / 1024 * 1024;
   const size_t smem = (size_t)p.stage_off + 2 * (size_t)p.stage_bytes + 1024;
-  if (smem > kMaxSmem) return fail(e, ESR_E_INVALID, "chain: shared memory budget exceeded");
+  if (smem > kChainSmemMax) return fail(e, ESR_E_INVALID, "chain: shared memory budget exceeded");
   p.tmem_cols = 512;
-  if (!e->attr_chain) {
-    CUDA_TRY(e, cudaFuncSetAttribute(conv_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-    e->attr_chain = true;
-  }
   // persistent grid: as many clusters (one per band in flight) as fit the device
   const int strips = p.strips;
-  int max_clusters = e->num_sms / strips;
-  {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((unsigned)(strips * max_clusters)); cfg.blockDim = dim3(CH_THREADS); cfg.dynamicSmemBytes = smem;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = (unsigned)strips; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, conv_chain_kernel, &cfg) == cudaSuccess && n > 0) max_clusters = std::min(max_clusters, n);
-    else cudaGetLastError();
-  }
+  const int max_clusters = std::max(1, chain_clusters(e, strips));
   const int nclusters = std::max(1, std::min(p.n_items, max_clusters));
   const int grid = nclusters * strips;
   pl.launches.push_back(Launch{"conv_chain:" + name, [pk, grid, strips, smem](cudaStream_t s) {
@@ -573,7 +666,8 @@ static int plan_chain(Engine* e, const DevGraph& dg, const ChainDecl& ch, const 
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = g_pdl ? 2 : 1;
-    return cudaLaunchKernelEx(&cfg, conv_chain_kernel, pk->maps, pk->p);
+    return pk->p.pw.enabled ? cudaLaunchKernelEx(&cfg, conv_chain_kernel<true>, pk->maps, pk->p)
+                            : cudaLaunchKernelEx(&cfg, conv_chain_kernel<false>, pk->maps, pk->p);
   }});
   if (name_out) *name_out = name;
   return ESR_OK;
@@ -622,7 +716,7 @@ static int build_plan(Engine* e, Plan& pl) {
   for (size_t oi = 0; oi < g.ops.size(); ++oi) {
     const OpDecl& op = g.ops[oi];
     if (f16 && op.kind == OP_CONV_TC) {
-      if (const ChainDecl* ch = chain_at(e, g, (int)oi, W)) {
+      if (const ChainDecl* ch = chain_at(e, g, (int)oi, B, H, W)) {
         if (!flags_cleared) {   // one memset for the halo flags of every chain of the forward
           void* fp = ws + L.flags_off;
           const size_t fb = L.flags_bytes;
@@ -633,9 +727,10 @@ static int build_plan(Engine* e, Plan& pl) {
         if (rc) return rc;
         flags_off += (chain_flag_ints(B, H, W, ch->n_ops) * sizeof(int) + 1023) / 1024 * 1024;
         double fl = 0;
-        for (int k = 0; k < ch->n_ops; ++k) fl += op_flops(g.ops[oi + k], B, H, W);
+        const int nops = ch->n_ops + ((e->opt_chain_pw && ch->pw_tc >= 0) ? 1 : 0);
+        for (int k = 0; k < nops; ++k) fl += op_flops(g.ops[oi + k], B, H, W);
         pl.launches.back().flops = fl;
-        oi += ch->n_ops - 1;
+        oi += nops - 1;
         continue;
       }
     }
@@ -1223,16 +1318,17 @@ static Plan* dry_plan(esr_handle* h, int B, int H, int W, int dtype, Plan& tmp) 
   for (size_t oi = 0; oi < dgr.ops.size(); ++oi) {
     const OpDecl& op = dgr.ops[oi];
     if (dtype == ESR_DTYPE_F16 && op.kind == OP_CONV_TC) {
-      if (const ChainDecl* ch = chain_at(h, dgr, (int)oi, W)) {
+      if (const ChainDecl* ch = chain_at(h, dgr, (int)oi, B, H, W)) {
         std::string name;
         double fl = 0;
-        for (int k = 0; k < ch->n_ops; ++k) {
+        const int nops = ch->n_ops + ((h->opt_chain_pw && ch->pw_tc >= 0) ? 1 : 0);
+        for (int k = 0; k < nops; ++k) {
           name += (k ? " | " : "") + dgr.ops[oi + k].name;
           fl += op_flops(dgr.ops[oi + k], B, H, W);
         }
         tmp.launches.push_back(Launch{"conv_chain:" + name, nullptr, fl});
         any_chain = true;
-        oi += ch->n_ops - 1;
+        oi += nops - 1;
         continue;
       }
     }
@@ -1337,9 +1433,10 @@ int esr_set_option(esr_handle* h, const char* key, int value) {
   else if (k == "tc_dbg_flags") h->opt_dbg_flags = value;
   else if (k == "tc_acc_slots") h->opt_acc_slots = value == 4 ? 4 : 2;
   else if (k == "use_pdl") h->opt_pdl = value ? 1 : 0;
-  else if (k == "chain_enable") h->opt_chain = value ? 1 : 0;
+  else if (k == "chain_enable") h->opt_chain = value == 2 ? 2 : (value ? 1 : 0);
   else if (k == "chain_store_all") h->opt_chain_store_all = value ? 1 : 0;
   else if (k == "chain_mask") h->opt_chain_mask = value;
+  else if (k == "chain_pw") h->opt_chain_pw = value ? 1 : 0;
   else return fail(h, ESR_E_INVALID, "unknown option: " + k);
   drop_plans(h);
   return ESR_OK;

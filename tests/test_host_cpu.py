@@ -43,8 +43,14 @@ def test_strict_state_dict_and_plan_names(mid, arch):
     e.load_state_dict(w)
     n32 = e.launch_names(1, 64, 64, _cabi.DTYPE_F32)
     n16 = e.launch_names(1, 64, 64, _cabi.DTYPE_F16)
-    assert n32 and n16 and not any(n.startswith("conv_tc") for n in n32)
-    assert any(n.startswith("conv_tc") for n in n16)
+    tc = ("conv_tc", "conv_chain")      # the two tcgen05 kernels: per-layer and fused chain
+    assert n32 and n16 and not any(n.startswith(tc) for n in n32)
+    assert any(n.startswith(tc) for n in n16)
+    if arch != "bsrn":   # the stacked 3x3 layers of a block run as one fused launch (BSRN's border-class bias keeps it per-layer)
+        assert any(n.startswith("conv_chain") for n in n16)
+    e.set_option("chain_enable", 0)
+    assert not any(n.startswith("conv_chain") for n in e.launch_names(1, 64, 64, _cabi.DTYPE_F16))
+    e.set_option("chain_enable", 1)
     assert e.workspace_bytes(2, 64, 48, _cabi.DTYPE_F16) > 0
     with pytest.raises(EsrError) as ei:  # no GPU bound -> loud failure, never a CPU fallback
         e.forward_host(np.zeros((1, 3, 32, 32), np.float32))
@@ -153,6 +159,15 @@ def test_next_row_models_load_strictly_and_plan(mid):
     assert set(m.state_dict()) == set(w)
     e = Engine(reg["arch"], device=-1, nf=reg["kwargs"]["nf"], nblocks=reg["kwargs"]["nblocks"])
     e.load_state_dict(w)
+    n16 = e.launch_names(1, 64, 64, _cabi.DTYPE_F16)
+    # fused: one chain per RFDB (c1_r+d .. c4) and one for LR_conv + upsampler; c5 (+ ESA entry) and `c` stay plain launches
+    assert sum(n.startswith("conv_chain") for n in n16) == 5 and sum(n.startswith("conv_tc") for n in n16) == 5
+    assert len(n16) == 1 + 1 + 4 * 5 + 1 + 1            # flag memset, head, 4 x (chain + c5 + 3 ESA launches), c, tail chain
+    e.set_option("chain_pw", 1)                          # option: c5 as the chain's last (pointwise) stage
+    n16 = e.launch_names(1, 64, 64, _cabi.DTYPE_F16)
+    assert sum(n.startswith("conv_chain") for n in n16) == 5 and sum(n.startswith("conv_tc") for n in n16) == 1
+    e.set_option("chain_pw", 0)
+    e.set_option("chain_enable", 0)
     n16 = e.launch_names(1, 64, 64, _cabi.DTYPE_F16)
     assert sum(n.startswith("conv_tc") for n in n16) == 23 and len(n16) == 36
     with pytest.raises(Exception, match="size mismatch|missing key|unexpected key"):

@@ -102,7 +102,7 @@ def test_fp16_tcgen05_path_vs_oracle(mid, arch):
         p = _psnr(y, ref, dr)
         assert p >= FP16_PSNR_BAR_BY_ID.get(mid, FP16_PSNR_BAR), (arch, shape, p)
     names = _model(mid).engine(torch.device("cuda:0")).launch_names(1, 64, 64, 1)
-    assert any(n.startswith("conv_tc") for n in names)
+    assert any(n.startswith(("conv_tc", "conv_chain")) for n in names)
 
 
 @pytest.mark.parametrize("mid,arch", [(0, "rfdn"), (4, "rlfn"), (-1, "imdn"), (18, "bsrn")])
@@ -152,7 +152,7 @@ def test_fp16_cuda_core_path_close_to_tcgen05_path(mid, arch):
     xt = torch.from_numpy(x).cuda()
     a = m2(xt).float().cpu().numpy()
     b = _run(mid, x)
-    assert not any(n.startswith("conv_tc") for n in m2.engine(torch.device("cuda:0")).launch_names(1, 48, 80, 1))
+    assert not any(n.startswith(("conv_tc", "conv_chain")) for n in m2.engine(torch.device("cuda:0")).launch_names(1, 48, 80, 1))
     assert _psnr(a, b, dr) >= FP16_PSNR_BAR
     # the border ring on its own (2 LR pixels = 8 SR pixels wide): zero padding of every intermediate layer, and for
     # BSRN the border-class bias of the dense form of BSConvU, only show there

@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--mask", type=int, default=-1)
     ap.add_argument("--timeline", type=int, default=0)
     ap.add_argument("--dbg", type=int, default=0)
+    ap.add_argument("--force", type=int, default=0, help="1: chain_enable = 2 (fused kernel also when a cluster gets several bands)")
     ap.add_argument("--shapes", type=int, nargs="*", default=None)
     a = ap.parse_args()
     import torch
@@ -47,7 +48,7 @@ def main():
             xt = torch.from_numpy(x).cuda()
             ys = {}
             for chain in (0, 1):
-                eng.set_option("chain_enable", chain)
+                eng.set_option("chain_enable", (2 if a.force else 1) if chain else 0)
                 eng.set_option("chain_store_all", a.store_all)
                 eng.set_option("chain_mask", a.mask)
                 for graph in ((0, 1) if chain else (0,)):
@@ -79,7 +80,7 @@ def main():
             worst = max(worst, d)
             if a.time and (b, h, wd) in ((1, 256, 256), (5, 256, 256)):
                 for chain in (0, 1):
-                    eng.set_option("chain_enable", chain)
+                    eng.set_option("chain_enable", (2 if a.force else 1) if chain else 0)
                     eng.set_option("use_graph", 1)
                     yt = eng.forward(xt)
                     for _ in range(20):
@@ -122,13 +123,17 @@ def main():
                 t = tl[(224 + 2 * ci) * 128:(226 + 2 * ci) * 128]
                 t0 = t[0]
                 print(f"TLC chain {ci}: kernel start 0 end {int(t[1] - t0)} cycles")
-                for g in range(6):
+                for g in range(8):
                     mm = t[64 + g * 6: 64 + g * 6 + 6]
                     ep = t[128 + g * 4: 128 + g * 4 + 4]
                     if mm.max() == 0:
                         continue
                     print(f"   layer {g}: mma step commit (i=5..0): " + " ".join(f"{int(v - t0):7d}" for v in mm[::-1]) +
                           "   epilogue done (j=3..0): " + " ".join(f"{int(v - t0):7d}" for v in ep[::-1]), flush=True)
+                for j in (3, 2, 1, 0):
+                    e5 = t[8 + j * 8: 8 + j * 8 + 5]
+                    if e5.max() > 0:
+                        print(f"      pw epi row {j}: begin {int(e5[0] - t0)} +sd wait {int(e5[1] - e5[0])} +bar waits {int(e5[2] - e5[1])} +units {int(e5[3] - e5[2])} +fence/arrive {int(e5[4] - e5[3])}")
                 for g in range(4):
                     w = t[192 + g * 12: 192 + g * 12 + 12]
                     if w.max() == 0:
