@@ -738,7 +738,12 @@ static int build_plan(Engine* e, Plan& pl) {
       case OP_HEAD:
       case OP_BSRN_HEAD: {
         const long long npix = (long long)B * H * W;
-        const dim3 grid(op.kind == OP_HEAD ? (unsigned)((long long)B * H * ((W + 255) / 256)) : (unsigned)((npix + 127) / 128));
+        // head: 256-pixel row segments per block, or 128-pixel ones when those would not give every SM two blocks
+        // (measured at 256x256, batch 1: 19.3 us with 128-pixel blocks against 14.3 us with 256-pixel ones: the 4-pixel
+        // register tile is what keeps the kernel off the shared-memory limit; kept as a template parameter, not used)
+        const bool head_small = false;
+        const dim3 grid(op.kind == OP_HEAD ? (unsigned)((long long)B * H * (head_small ? (W + 127) / 128 : (W + 255) / 256))
+                                           : (unsigned)((npix + 127) / 128));
         const void* in = pl.in;
         void* out = ptr(op.out);
         const int stride = g.bufs[op.out].C;
@@ -748,13 +753,17 @@ static int build_plan(Engine* e, Plan& pl) {
         const float in_div = (float)(255.0 / (double)pl.data_range);   // uint2tensor4: .div(255. / data_range)
         if (op.kind == OP_HEAD) {
           pl.launches.push_back(Launch{"head:" + op.name, [=](cudaStream_t s) {
+            if (u8 && f16 && head_small)
+              return launch_k(k_head_conv<uint8_t, __half, float, 2>, grid, dim3(256), 0, s, (const uint8_t*)in, (__half*)out, w, b, B, H, W, stride, 64, in_div);
             if (u8 && f16)
-              return launch_k(k_head_conv<uint8_t, __half, float>, grid, dim3(256), 0, s, (const uint8_t*)in, (__half*)out, w, b, B, H, W, stride, 64, in_div);
+              return launch_k(k_head_conv<uint8_t, __half, float, 4>, grid, dim3(256), 0, s, (const uint8_t*)in, (__half*)out, w, b, B, H, W, stride, 64, in_div);
             if (u8)
-              return launch_k(k_head_conv<uint8_t, float, double>, grid, dim3(256), 0, s, (const uint8_t*)in, (float*)out, w, b, B, H, W, stride, 64, in_div);
+              return launch_k(k_head_conv<uint8_t, float, double, 4>, grid, dim3(256), 0, s, (const uint8_t*)in, (float*)out, w, b, B, H, W, stride, 64, in_div);
+            if (f16 && head_small)
+              return launch_k(k_head_conv<__half, __half, float, 2>, grid, dim3(256), 0, s, (const __half*)in, (__half*)out, w, b, B, H, W, stride, 64, 1.f);
             if (f16)
-              return launch_k(k_head_conv<__half, __half, float>, grid, dim3(256), 0, s, (const __half*)in, (__half*)out, w, b, B, H, W, stride, 64, 1.f);
-            return launch_k(k_head_conv<float, float, double>, grid, dim3(256), 0, s, (const float*)in, (float*)out, w, b, B, H, W, stride, 64, 1.f);
+              return launch_k(k_head_conv<__half, __half, float, 4>, grid, dim3(256), 0, s, (const __half*)in, (__half*)out, w, b, B, H, W, stride, 64, 1.f);
+            return launch_k(k_head_conv<float, float, double, 4>, grid, dim3(256), 0, s, (const float*)in, (float*)out, w, b, B, H, W, stride, 64, 1.f);
           }});
         } else {
           const float* wd = dg.d_params + dg.tables[op.tab2].off_w;

@@ -103,29 +103,32 @@ __device__ __forceinline__ float ldin(const uint8_t* in, int b, int ci, int y, i
 // (channels >= cout are written as zero so padded lanes stay finite).
 // w: [27][64] fp32, index (ky*3+kx)*3+ci; bias [64].
 // ---------------------------------------------------------------------------------------------
-template <typename TIn, typename TOut, typename TAcc>
+template <typename TIn, typename TOut, typename TAcc, int PX = 4>
 __global__ void __launch_bounds__(256) k_head_conv(const TIn* __restrict__ in, TOut* __restrict__ out,
                                                    const float* __restrict__ w, const float* __restrict__ bias,
                                                    int B, int H, int W, int out_stride, int cstore, float in_div) {
-  // block = up to 256 consecutive pixels of one image row; thread = 4 consecutive pixels x 16 output
-  // channels (64 accumulators): every weight fetched from shared memory (broadcast LDS.128) feeds 4 FMAs
-  // per lane, which is what keeps a CUDA-core convolution off the shared-memory bandwidth limit.
+  // block = up to 64 * PX consecutive pixels of one image row; thread = PX consecutive pixels x 16 output
+  // channels (16 * PX accumulators): every weight fetched from shared memory (broadcast LDS.128) feeds PX FMAs
+  // per lane, which is what keeps a CUDA-core convolution off the shared-memory bandwidth limit.  PX = 4 for large
+  // workloads; PX = 2 doubles the number of blocks when a batch-1 image would otherwise leave the GPU half empty
+  // (256 rows = 256 blocks of 8 warps on 148 SMs: two latency-bound waves).
+  constexpr int BPX = 64 * PX;
   __shared__ __align__(16) float ws[27 * 64];
   __shared__ __align__(16) float bs[64];
-  __shared__ float xs[3][3][260];
-  const int segs = (W + 255) / 256;
+  __shared__ float xs[3][3][BPX + 4];
+  const int segs = (W + BPX - 1) / BPX;
   const int seg = blockIdx.x % segs;
   const int y = (blockIdx.x / segs) % H;
   const int b = blockIdx.x / (segs * H);
-  const int x0 = seg * 256;
+  const int x0 = seg * BPX;
   {
     const float4* src = reinterpret_cast<const float4*>(w);
     float4* dst = reinterpret_cast<float4*>(ws);
     for (int i = threadIdx.x; i < 27 * 16; i += 256) dst[i] = __ldg(src + i);
     if (threadIdx.x < 64) bs[threadIdx.x] = __ldg(bias + threadIdx.x);
     pdl_wait();
-    for (int i = threadIdx.x; i < 3 * 3 * 258; i += 256) {
-      const int xx = i % 258, r = (i / 258) % 3, ci = i / 774;
+    for (int i = threadIdx.x; i < 3 * 3 * (BPX + 2); i += 256) {
+      const int xx = i % (BPX + 2), r = (i / (BPX + 2)) % 3, ci = i / (3 * (BPX + 2));
       const int gy = y + r - 1, gx = x0 + xx - 1;
       const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
       xs[ci][r][xx] = ok ? ldin<TOut>(in, b, ci, gy, gx, H, W, in_div) : 0.f;
@@ -133,21 +136,22 @@ __global__ void __launch_bounds__(256) k_head_conv(const TIn* __restrict__ in, T
   }
   __syncthreads();
   const int quad = threadIdx.x >> 2, g = threadIdx.x & 3;
-  const int xq = x0 + quad * 4;
+  const int xq = x0 + quad * PX;
   if (xq >= W || g * 16 >= cstore) return;
-  TAcc acc[4][16];
+  TAcc acc[PX][16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     const TAcc bv = (TAcc)bs[g * 16 + j];
-    acc[0][j] = bv; acc[1][j] = bv; acc[2][j] = bv; acc[3][j] = bv;
+#pragma unroll
+    for (int px = 0; px < PX; ++px) acc[px][j] = bv;
   }
 #pragma unroll
   for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
     for (int ci = 0; ci < 3; ++ci) {
-      float xv[6];
+      float xv[PX + 2];
 #pragma unroll
-      for (int j = 0; j < 6; ++j) xv[j] = xs[ci][ky][quad * 4 + j];
+      for (int j = 0; j < PX + 2; ++j) xv[j] = xs[ci][ky][quad * PX + j];
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
         const float4* w4 = reinterpret_cast<const float4*>(ws + ((ky * 3 + kx) * 3 + ci) * 64 + g * 16);
@@ -156,7 +160,7 @@ __global__ void __launch_bounds__(256) k_head_conv(const TIn* __restrict__ in, T
           const float4 ww = w4[q];
           const float wv[4] = {ww.x, ww.y, ww.z, ww.w};
 #pragma unroll
-          for (int px = 0; px < 4; ++px) {
+          for (int px = 0; px < PX; ++px) {
             const TAcc xa = (TAcc)xv[px + kx];
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[px][4 * q + j] = fma(xa, (TAcc)wv[j], acc[px][4 * q + j]);
@@ -165,7 +169,7 @@ __global__ void __launch_bounds__(256) k_head_conv(const TIn* __restrict__ in, T
       }
     }
 #pragma unroll
-  for (int px = 0; px < 4; ++px) {
+  for (int px = 0; px < PX; ++px) {
     if (xq + px >= W) break;
     const long long pix = ((long long)b * H + y) * W + xq + px;
     TOut* o = out + pix * out_stride + g * 16;

@@ -139,6 +139,9 @@ REGISTRY: Dict[int, dict] = {
     # RFDN40 (models/team22_rep_rfdn.py:134-165, test_demo.py:175-181): the RFDN graph at nf = 40, data range 1
     22: dict(arch="rfdn", kwargs=dict(nf=40, nblocks=4), file="team22_rep_rfdn.pth", wrap=None,
              name="RFDN40", data_range=1.0),
+    # IMDN with seven blocks (test_demo.py:203-209)
+    26: dict(arch="imdn", kwargs=dict(nf=64, nblocks=7), file="team26_imdn_nb7.pth", wrap=None,
+             name="IMDN", data_range=1.0),
     # pruned RFDN (models/team40_rfdn_pruned.py:186-213, test_demo.py:302-308): nf = 40, RFDBs without the inner
     # residual adds, ESA width 12
     40: dict(arch="rfdn_pruned", kwargs=dict(nf=40, nblocks=4), file="team40_rfdn_pruned.pth", wrap=None,

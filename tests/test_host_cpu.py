@@ -189,3 +189,73 @@ def test_uint8_entry_points_refuse_without_a_gpu():
     assert ei.value.code == _cabi.E_NOGPU
     with pytest.raises(EsrError):
         e.forward_host_uint8(np.zeros((1, 32, 32, 3), np.float32), 255.0)   # wrong dtype
+
+
+# utils/model_summary.py numbers of the UNMODIFIED reference for input (3, 256, 256), produced in the build container
+# with get_model_activation / get_model_flops on test_demo.select_model(id) (test_demo.py:522-533):
+# id -> (#activations, #Conv2d, FLOPs, #params)
+REFERENCE_SUMMARY = {
+    -1: (154140672, 43, 58531512320, 893936), 0: (112034240, 64, 27102622560, 433448), 4: (80045184, 39, 19695306752, 317218),
+    18: (65757744, 43, 2022422883, 156288), 22: (90500128, 64, 17613787280, 282688), 26: (136314880, 38, 51757711360, 790496),
+    40: (91718080, 64, 17700828000, 289888),
+}
+
+
+@pytest.mark.parametrize("mid", sorted(REFERENCE_SUMMARY))
+def test_model_summary_hooks_see_the_reference_layers(mid, monkeypatch):
+    """The harness prints #Activations / #Conv2d / FLOPs / #Params of the selected model through forward hooks on its
+    nn.Conv2d / nn.Linear / nn.ReLU / nn.LeakyReLU leaves (test_demo.py:522-533, utils/model_summary.py:230-245,390-400).
+    The drop-in keeps its weights in real leaves of the reference's types and serves the hooks with shape-only tensors
+    after the engine forward, so the same code reports the reference's numbers.  The hook arithmetic is restated here
+    (model_summary.py:283-318, 428-438); with /root/reference present the reference's own functions are used as well."""
+    import numpy as np
+    import torch.nn as nn
+
+    from ntire2022_esr_b200 import build_model
+
+    m = build_model(mid, state_dict=_weights(mid))
+
+    class _NoEngine:   # the CPU suite has no GPU: stand-in for the engine call (the hooks never look at values)
+        def forward(self, x):
+            return torch.zeros(x.shape[0], 3, 4 * x.shape[2], 4 * x.shape[3])
+
+    monkeypatch.setattr(m, "engine", lambda dev: _NoEngine())
+    counts = {"flops": 0, "act": 0, "nconv": 0}
+
+    def conv_hook(mod, inp, out):
+        counts["flops"] += int(np.prod(mod.kernel_size) * mod.in_channels * (mod.out_channels // mod.groups)) * int(out.shape[0] * np.prod(out.shape[2:]))
+        counts["act"] += out.numel()
+        counts["nconv"] += 1
+
+    def relu_hook(mod, inp, out):
+        counts["flops"] += out.numel()
+
+    def linear_hook(mod, inp, out):
+        counts["flops"] += int(inp[0].shape[0] * inp[0].shape[1] * out.shape[1])
+
+    handles = []
+    for mod in m.modules():
+        if isinstance(mod, nn.Conv2d):
+            handles.append(mod.register_forward_hook(conv_hook))
+        elif isinstance(mod, (nn.ReLU, nn.LeakyReLU)):
+            handles.append(mod.register_forward_hook(relu_hook))
+        elif isinstance(mod, nn.Linear):
+            handles.append(mod.register_forward_hook(linear_hook))
+    m(torch.zeros(1, 3, 256, 256))
+    for h in handles:
+        h.remove()
+    want = REFERENCE_SUMMARY[mid]
+    assert (counts["act"], counts["nconv"], counts["flops"], sum(p.numel() for p in m.parameters())) == want
+    if os.path.isdir("/root/reference/utils"):
+        import sys
+        import types
+
+        for name in ("matplotlib", "matplotlib.pyplot"):
+            sys.modules.setdefault(name, types.ModuleType(name))
+        sys.path.insert(0, "/root/reference")
+        try:
+            from utils.model_summary import get_model_activation, get_model_flops
+        finally:
+            sys.path.remove("/root/reference")
+        assert get_model_activation(m, (3, 256, 256)) == want[:2]
+        assert get_model_flops(m, (3, 256, 256), False) == want[2]

@@ -18,7 +18,7 @@ from oracle import esr_oracle as O  # noqa: E402
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ARCHS = [(-1, "imdn"), (0, "rfdn"), (4, "rlfn"), (18, "bsrn")]
-GOLDEN = ARCHS + [(22, "rfdn40"), (40, "rfdn_pruned")]   # (model id, golden file tag): SURVEY row N1 (RFDN at nf = 40, pruned RFDN)
+GOLDEN = ARCHS + [(22, "rfdn40"), (40, "rfdn_pruned"), (26, "imdn_nb7")]   # (model id, golden file tag): SURVEY row N1 (RFDN at nf = 40, pruned RFDN, IMDN nb = 7)
 FP32_BAR = 1e-5
 FP16_PSNR_BAR = 60.0
 # The pruned RFDN (id 40) has the widest dynamic range of the set (|out_lr| up to 3.9e3 on uniform noise at
@@ -105,40 +105,92 @@ def test_fp16_tcgen05_path_vs_oracle(mid, arch):
     assert any(n.startswith(("conv_tc", "conv_chain")) for n in names)
 
 
-@pytest.mark.parametrize("mid,arch", [(0, "rfdn"), (4, "rlfn"), (-1, "imdn"), (18, "bsrn")])
-def test_fp16_psnr_delta_on_pseudo_pairs(mid, arch):
-    """north_star fp16 bar (1e-3 dB PSNR).  Set: test.bmp (256x256, the configs[1] size) and its flips /
-    transpose as LR, pseudo-HR = 4x pixel replication (1024x1024 each, 12.6 M samples in total).
+def _dihedral(img):
+    """the eight flips / transposes of an HWC image"""
+    out = []
+    for t in (img, img.transpose(1, 0, 2)):
+        out += [t, t[::-1], t[:, ::-1], t[::-1, ::-1]]
+    return [np.ascontiguousarray(v) for v in out]
 
-    (a) float domain - PSNR(SR, HR) of the fp16 engine output vs the fp32 output, no quantiser in between:
-        |delta| <= 1e-3 dB per image for RFDN (the north-star network); 2e-3 for the others (RLFN measures
-        -1.3e-3: its fp16 error, 74.7 dB below the signal, is not independent of the SR error).
-    (b) uint8 domain, as the harness reports it (tensor2uint, border 4, test_demo.py:434-447), averaged over
-        the set like test_demo.py:468-471: <= 1e-3 dB for RFDN (the north-star network).  For the others the
-        bar is 3e-3: an fp16 output that is 74-75 dB close to the fp32 one still flips ~4 % of the uint8
-        pixels by one LSB, and every flip adds exactly +1 to the squared error whatever its sign
-        ((e +- 1)^2 = e^2 +- 2e + 1), i.e. a systematic -1e-3..-1.5e-3 dB at a 26 dB operating point that no
-        fp16 evaluation (PyTorch's own .half() included) can avoid."""
+
+@pytest.mark.parametrize("mid,arch", GOLDEN)
+def test_fp16_psnr_delta_on_pseudo_pairs(mid, arch, record_property):
+    """north_star fp16 bar: |PSNR(ours fp16, HR) - PSNR(reference fp32, HR)| <= 1e-3 dB, with the pseudo-pair protocol of
+    SURVEY 8(d): HR = the one natural image the reference ships (test.bmp, 256x256) in its eight flips / transposes, LR =
+    the uint8 MATLAB-bicubic x1/4 of HR (utils_image.imresize_np, :704-774 - how DIV2K's LR images are made), SR through
+    uint2tensor4 -> model -> tensor2uint, PSNR with border 4 (test_demo.py:423-447), and - like the harness
+    (test_demo.py:468-471) - the figure is the average over the set.  The bar is 1e-3 dB for every network, in the uint8
+    domain the harness reports and in the float domain (no quantiser); the reference side is the fp32 oracle (ATen CPU
+    kernels, pinned on the reference goldens).  Per-image deltas scatter by +-1.5e-3 on 196 k samples (one uint8 flip
+    moves an image's PSNR by 5e-6 dB); they are recorded, not asserted."""
+    from oracle import esr_oracle_torch as OT
+
     img = np.load(os.path.join(ROOT, "tests", "golden", "test_bmp.npz"))["img"]
     dr = O.MODELS[mid]["data_range"]
-    z = np.load(os.path.join(ROOT, "tests", "golden", f"ref_{arch}_256.npz"))
-    deltas = []
-    for i, lr in enumerate([img, img[:, ::-1], img[::-1], img.transpose(1, 0, 2)]):
-        lr = np.ascontiguousarray(lr)
-        hr = np.repeat(np.repeat(lr, 4, axis=0), 4, axis=1)
+    wt = OT.prepare(_weights(mid))
+    d_float, d_u8, p_ref = [], [], []
+    for hr in _dihedral(img):
+        lr = np.clip(np.round(O.imresize_np(hr.astype(np.float32) / 255.0, 1 / 4) * 255.0), 0, 255).astype(np.uint8)
         x = O.uint2tensor4(lr, dr)
-        ours16 = _run(mid, x.astype(np.float16))
-        ours32 = _run(mid, x)      # fp32 engine output == reference fp32 forward to 1e-5 (pinned below for i = 0)
-        if i == 0:
-            for (a, b), crop in zip(z["crops_yx"], z["crops"]):
-                assert np.abs(ours32[0, :, a:a + 32, b:b + 32] - crop).max() / dr <= FP32_BAR
+        ref = OT.forward(O.MODELS[mid]["arch"], wt, x).numpy()
+        ours = _run(mid, x.astype(np.float16))
         hr_f = hr.astype(np.float64).transpose(2, 0, 1)[None] * (dr / 255.0)
-        d_float = _psnr(ours16, hr_f, dr) - _psnr(ours32, hr_f, dr)
-        assert abs(d_float) <= (1e-3 if arch == "rfdn" else 2e-3), (i, d_float)
-        d = O.psnr(O.tensor2uint(ours16, dr), hr, border=4) - O.psnr(O.tensor2uint(ours32, dr), hr, border=4)
-        assert _psnr(ours16, ours32, dr) >= 70.0       # natural image: 73-78 dB measured
-        deltas.append(d)
-    assert abs(np.mean(deltas)) <= (1e-3 if arch == "rfdn" else 3e-3), deltas
+        d_float.append(_psnr(ours, hr_f, dr) - _psnr(ref, hr_f, dr))
+        d_u8.append(O.psnr(O.tensor2uint(ours, dr), hr, border=4) - O.psnr(O.tensor2uint(ref, dr), hr, border=4))
+        p_ref.append(_psnr(ours, ref, dr))
+    print(f"fp16 PSNR delta {arch}: uint8 mean {np.mean(d_u8):+.2e} dB, float mean {np.mean(d_float):+.2e} dB, "
+          f"per image uint8 {np.round(d_u8, 5).tolist()}, PSNR(ours, ref) {np.round(p_ref, 1).tolist()} dB")
+    record_property("psnr_delta_uint8_mean_db", float(np.mean(d_u8)))
+    record_property("psnr_delta_float_mean_db", float(np.mean(d_float)))
+    assert min(p_ref) >= 68.0                      # natural image: 70-76 dB measured
+    assert abs(np.mean(d_u8)) <= 1e-3, d_u8
+    assert abs(np.mean(d_float)) <= 1e-3, d_float
+
+
+@pytest.mark.parametrize("mid,arch,shape", [(0, "rfdn", (339, 510)), (18, "bsrn", (270, 480))])
+def test_baseline_config_shapes_vs_reference(mid, arch, shape):
+    """BASELINE.json configs[2] (RFDN, DIV2K-shaped 339x510 LR) and configs[4] (BSRN, 270x480): the fp32 engine against
+    crops / a strided subsample / channel sums of the UNMODIFIED reference's output (tests/golden/ref_<arch>_<H>x<W>.npz,
+    bar 1e-5 of range), and the fp16 engine against the fp32 oracle on the whole image (PSNR >= 60 dB on uniform noise,
+    the worst case for fp16)."""
+    from oracle import esr_oracle_torch as OT
+
+    z = np.load(os.path.join(ROOT, "tests", "golden", f"ref_{arch}_{shape[0]}x{shape[1]}.npz"))
+    dr = float(z["data_range"])
+    x = O.shaped_input(int(z["seed"]), shape[0], shape[1], dr)
+    y32 = _run(mid, x)
+    assert y32.shape == (1, 3, 4 * shape[0], 4 * shape[1])
+    for (a, b), crop in zip(z["crops_yx"], z["crops"]):
+        assert np.abs(y32[0, :, a:a + 32, b:b + 32] - crop).max() / dr <= FP32_BAR
+    assert np.abs(y32[0, :, ::16, ::16] - z["sub16"]).max() / dr <= FP32_BAR
+    np.testing.assert_allclose(y32.astype(np.float64).sum(axis=(0, 2, 3)), z["sum_c"], rtol=2e-6)
+    ref = OT.forward(arch, OT.prepare(_weights(mid)), x).numpy()       # the reference graph on the ATen CPU kernels, whole image
+    assert np.abs(ref[0, :, ::16, ::16] - z["sub16"]).max() / dr <= FP32_BAR
+    y16 = _run(mid, x.astype(np.float16))
+    assert np.isfinite(y16).all()
+    assert _psnr(y16, ref, dr) >= FP16_PSNR_BAR
+    ring = np.ones(ref.shape[2:], bool)
+    ring[8:-8, 8:-8] = False                                              # the border ring on its own (zero padding of every layer)
+    assert _psnr(y16[..., ring], ref[..., ring], dr) >= FP16_PSNR_BAR - 2.0
+
+
+@pytest.mark.parametrize("mid,arch", GOLDEN)
+def test_fp16_full_256_output_vs_oracle(mid, arch):
+    """configs[1] size: the fp16 engine's WHOLE 1024x1024 output on test.bmp against the fp32 oracle (not against the
+    engine's own fp32 mode), plus the reference's committed crops as the pin of that oracle run."""
+    from oracle import esr_oracle_torch as OT
+
+    z = np.load(os.path.join(ROOT, "tests", "golden", f"ref_{arch}_256.npz"))
+    img = np.load(os.path.join(ROOT, "tests", "golden", "test_bmp.npz"))["img"]
+    dr = float(z["data_range"])
+    x = O.uint2tensor4(img, dr)
+    ref = OT.forward(O.MODELS[mid]["arch"], OT.prepare(_weights(mid)), x).numpy()
+    for (a, b), crop in zip(z["crops_yx"], z["crops"]):
+        assert np.abs(ref[0, :, a:a + 32, b:b + 32] - crop).max() / dr <= FP32_BAR
+    y16 = _run(mid, x.astype(np.float16))
+    assert y16.shape == ref.shape == (1, 3, 1024, 1024)
+    assert _psnr(y16, ref, dr) >= 70.0, arch            # measured 73-78 dB
+    assert np.abs(y16 - ref).max() / dr <= 2e-2
 
 
 @pytest.mark.parametrize("mid,arch", ARCHS)
