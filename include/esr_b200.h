@@ -54,7 +54,8 @@ int esr_load_weights(esr_handle* h, const char* name, const float* host_ptr, con
  * K-major blocks for the tcgen05 kernels) and uploads them. */
 int esr_finalize(esr_handle* h);
 
-/* Scratch bytes esr_forward needs for a (B,3,H,W) input of `dtype`; 0 on error. */
+/* Scratch bytes esr_forward needs for a (B,3,H,W) input of `dtype`; 0 on error.  The workspace holds state between
+ * calls (cleared pad lanes): the caller must not write to it; a call with another shape / dtype re-clears it. */
 size_t esr_workspace_bytes(esr_handle* h, int B, int H, int W, int dtype);
 
 /* Replaces `model(img_lq)` (test_demo.py:367, and :380 for each tile): in = (B,3,H,W) NCHW, values

@@ -43,6 +43,7 @@ struct Plan {
   std::vector<Launch> launches;
   cudaGraphExec_t gexec = nullptr;
   bool graph_failed = false;
+  int hits = 0;   // the CUDA graph is captured on the second use of a plan: a one-off shape never pays the ~1 ms of capture + instantiate
 };
 
 struct DevGraph {            // a Graph plus its device-side parameters
@@ -89,8 +90,24 @@ struct Engine {
   } hslot[kHostSlots];
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
   long long next_ticket = 0;
-  std::vector<std::pair<void*, size_t>> ws_zeroed;   // workspaces whose padded lanes have been cleared (pointer, bytes)
+  struct WsKey { void* p; size_t need; int B, H, W, dtype, gid; };
+  std::vector<WsKey> ws_zeroed;   // workspaces whose padded lanes have been cleared, keyed on the full buffer layout
   PFN_encodeTiled encode = nullptr;
+};
+
+// Every ABI entry point that touches the device runs on the handle's device and restores the caller's current device
+// afterwards (under PyTorch, torch.cuda.current_device() IS cudaGetDevice(): an engine bound to cuda:1 must not leave the
+// caller on cuda:1).
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (dev < 0) return;
+    if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) { ok = false; cudaGetLastError(); }
+    if (prev == dev) prev = -1;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
 static int fail(Engine* e, int code, const std::string& msg) {
@@ -1069,7 +1086,7 @@ int esr_create(esr_handle** out, int arch, int nf, int nblocks, int device) {
       return ESR_E_NOGPU;
     }
     e->has_gpu = true;
-    cudaSetDevice(device);
+    DeviceGuard guard(device);
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device);
     e->num_sms = prop.multiProcessorCount;
@@ -1104,7 +1121,7 @@ int esr_load_weights(esr_handle* h, const char* name, const float* host_ptr, con
 int esr_finalize(esr_handle* h) {
   if (!h) return ESR_E_INVALID;
   if (h->finalized) return fail(h, ESR_E_STATE, "esr_finalize called twice");
-  if (h->has_gpu) cudaSetDevice(h->device);
+  DeviceGuard guard(h->has_gpu ? h->device : -1);
   // both flavours are built now so that a bad state-dict is reported here, not at the first forward
   for (int gid = 0; gid < 2; ++gid) {
     int rc = ensure_graph(h, gid);
@@ -1155,22 +1172,26 @@ static int forward_impl(esr_handle* h, const void* in_nchw, void* out_nchw, int 
     out_nchw = reinterpret_cast<uint8_t*>(workspace) + (need - 1024);
   }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  CUDA_TRY(h, cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
+  if (!guard.ok) return fail(h, ESR_E_CUDA, "cudaSetDevice failed");
   bool zeroed = false;
-  for (auto& z : h->ws_zeroed) zeroed = zeroed || (z.first == workspace && z.second >= need);
+  const int zgid = graph_id(h, dtype);
+  for (auto& z : h->ws_zeroed)
+    zeroed = zeroed || (z.p == workspace && z.need == need && z.B == B && z.H == H && z.W == W && z.dtype == dtype && z.gid == zgid);
   if (!zeroed) {
-    // padded channel lanes are never written by some layers and are multiplied by zero weights later:
-    // they must hold finite values
+    // padded channel lanes are never written by some layers and are multiplied by zero weights later: they must hold
+    // finite values.  Another shape / dtype / graph lays the buffers out differently (stale fp32 bytes read as fp16
+    // can be Inf / NaN), so the cache is keyed on the whole layout; the workspace must not be modified between calls.
     CUDA_TRY(h, cudaMemsetAsync(workspace, 0, need - 1024, s));
     for (auto it = h->ws_zeroed.begin(); it != h->ws_zeroed.end();)
-      it = it->first == workspace ? h->ws_zeroed.erase(it) : it + 1;
+      it = it->p == workspace ? h->ws_zeroed.erase(it) : it + 1;
     if (h->ws_zeroed.size() >= 8) h->ws_zeroed.erase(h->ws_zeroed.begin());
-    h->ws_zeroed.emplace_back(workspace, need);
+    h->ws_zeroed.push_back(Engine::WsKey{workspace, need, B, H, W, dtype, zgid});
   }
   Plan* pl = get_plan(h, in_nchw, out_nchw, B, H, W, dtype, workspace, rc, io);
   if (!pl) return rc;
   struct PdlScope { PdlScope(bool on) { g_pdl = on; } ~PdlScope() { g_pdl = false; } } pdl_scope(h->opt_pdl != 0);
-  if (h->opt_use_graph && !pl->graph_failed) {
+  if (h->opt_use_graph && !pl->graph_failed && ++pl->hits >= 2) {
     if (!pl->gexec) {
       cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
       cudaStreamIsCapturing(s, &st);
@@ -1218,6 +1239,7 @@ int esr_forward_u8(esr_handle* h, const uint8_t* in_hwc, uint8_t* out_hwc, int B
 int esr_host_wait(esr_handle* h, long long ticket) {
   if (!h) return ESR_E_INVALID;
   if (!h->has_gpu) return fail(h, ESR_E_NOGPU, "no sm_100 device bound to this handle (the engine has no CPU fallback)");
+  DeviceGuard guard(h->device);
   for (auto& sl : h->hslot) {
     if (!sl.busy) continue;
     if (ticket >= 0 && sl.ticket > ticket) continue;   // requests complete in order: wait for everything up to `ticket`
@@ -1235,7 +1257,8 @@ static int forward_host_impl(esr_handle* h, const void* in_host, void* out_host,
   int rc = check_shape(h, B, H, W, dtype);
   if (rc) return rc;
   if (!in_host || !out_host) return fail(h, ESR_E_INVALID, "null host pointer");
-  CUDA_TRY(h, cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
+  if (!guard.ok) return fail(h, ESR_E_CUDA, "cudaSetDevice failed");
   const size_t elt = io.u8 ? 1 : (dtype == ESR_DTYPE_F16 ? 2 : 4);
   const size_t in_b = (size_t)B * 3 * H * W * elt, out_b = in_b * 16;
   const size_t ws_b = io.u8 ? esr_workspace_bytes_u8(h, B, H, W, dtype) : esr_workspace_bytes(h, B, H, W, dtype);
@@ -1269,7 +1292,7 @@ static int forward_host_impl(esr_handle* h, const void* in_host, void* out_host,
   CUDA_TRY(h, grow(sl.d_out, sl.out_sz, out_b));
   if (sl.ws_sz < ws_b) {   // a regrown workspace is a new allocation: forget what was cleared at the old address
     for (auto it = h->ws_zeroed.begin(); it != h->ws_zeroed.end();)
-      it = it->first == reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(sl.ws) + 1023) & ~uintptr_t(1023)) ? h->ws_zeroed.erase(it) : it + 1;
+      it = it->p == reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(sl.ws) + 1023) & ~uintptr_t(1023)) ? h->ws_zeroed.erase(it) : it + 1;
   }
   CUDA_TRY(h, grow(sl.ws, sl.ws_sz, ws_b));
   CUDA_TRY(h, cudaMemcpyAsync(sl.d_in, in_host, in_b, cudaMemcpyHostToDevice, h->s_h2d));
@@ -1516,7 +1539,7 @@ const char* esr_last_error(esr_handle* h) { return h ? h->err.c_str() : "null ha
 void esr_destroy(esr_handle* h) {
   if (!h) return;
   if (h->has_gpu) {
-    cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     drop_plans(h);
     for (auto& dg : h->graphs) {
       if (dg.d_params) cudaFree(dg.d_params);

@@ -110,6 +110,13 @@ class Engine:
         self._check(lib.esr_debug_timeline(self._h, buf, n_launches))
         return np.frombuffer(buf, dtype=np.int64).reshape(n_launches, 4, 32).copy()
 
+    @staticmethod
+    def _check_out(out, shape, dtype, device):
+        """A caller-supplied output goes to the engine as a raw pointer: refuse anything the kernels would overrun."""
+        if (not hasattr(out, "data_ptr") or tuple(out.shape) != tuple(shape) or out.dtype != dtype or out.device != device
+                or not out.is_contiguous() or out.data_ptr() % 16):
+            raise EsrError(_cabi.E_INVALID, f"`out` must be a contiguous, 16-byte aligned {dtype} tensor of shape {tuple(shape)} on {device}")
+
     # -- compute ----------------------------------------------------------------------------------
     def forward(self, x, out=None):
         """x: CUDA torch tensor (B,3,H,W) fp32 or fp16 on this engine's device -> (B,3,4H,4W)."""
@@ -137,6 +144,8 @@ class Engine:
             self._ws = torch.empty(need, dtype=torch.uint8, device=x.device)
         if out is None:
             out = torch.empty((B, 3, 4 * H, 4 * W), dtype=x.dtype, device=x.device)
+        else:
+            self._check_out(out, (B, 3, 4 * H, 4 * W), x.dtype, x.device)
         stream = torch.cuda.current_stream(x.device).cuda_stream
         self._check(lib.esr_forward(self._h, x.data_ptr(), out.data_ptr(), B, H, W, dt, self._ws.data_ptr(),
                                     self._ws.numel(), stream))
@@ -166,6 +175,8 @@ class Engine:
             self._ws = torch.empty(need, dtype=torch.uint8, device=img.device)
         if out is None:
             out = torch.empty((B, 4 * H, 4 * W, 3), dtype=torch.uint8, device=img.device)
+        else:
+            self._check_out(out, (B, 4 * H, 4 * W, 3), torch.uint8, img.device)
         stream = torch.cuda.current_stream(img.device).cuda_stream
         self._check(lib.esr_forward_u8(self._h, img.data_ptr(), out.data_ptr(), B, H, W, float(data_range), dt,
                                        self._ws.data_ptr(), self._ws.numel(), stream))
@@ -206,6 +217,9 @@ class Engine:
         B, _, H, W = x.shape
         if out is None:
             out = np.empty((B, 3, 4 * H, 4 * W), dtype=x.dtype)
+        elif (not isinstance(out, np.ndarray) or out.shape != (B, 3, 4 * H, 4 * W) or out.dtype != x.dtype
+              or not out.flags["C_CONTIGUOUS"] or not out.flags["WRITEABLE"]):
+            raise EsrError(_cabi.E_INVALID, f"`out` must be a writeable C-contiguous {x.dtype} array of shape {(B, 3, 4 * H, 4 * W)}")
         self._check(lib.esr_forward_host(self._h, x.ctypes.data_as(ctypes.c_void_p),
                                          out.ctypes.data_as(ctypes.c_void_p), B, H, W, dt))
         return out

@@ -356,3 +356,40 @@ def test_large_batch_odd_shape_stress(mid):
         assert torch.equal(y, y0)
     # image 5 of the batch equals its single-image run (batch invariance at this shape)
     assert torch.equal(m(x[5:6].contiguous())[0], y0[5])
+
+
+def test_caller_supplied_output_is_validated():
+    """A wrong-sized / wrong-dtype / non-contiguous `out` must raise instead of being handed to the kernels as a raw pointer."""
+    from ntire2022_esr_b200 import EsrError
+
+    eng = _model(0).engine(torch.device("cuda:0"))
+    x = torch.rand(1, 3, 32, 40, device="cuda").half() * 255
+    good = torch.empty(1, 3, 128, 160, dtype=torch.float16, device="cuda")
+    assert eng.forward(x, out=good) is good
+    for bad in (torch.empty(1, 3, 128, 159, dtype=torch.float16, device="cuda"),
+                torch.empty(1, 3, 128, 160, dtype=torch.float32, device="cuda"),
+                torch.empty(1, 3, 160, 128, dtype=torch.float16, device="cuda").transpose(2, 3),
+                torch.empty(1, 3, 128, 160, dtype=torch.float16)):
+        with pytest.raises(EsrError):
+            eng.forward(x, out=bad)
+
+
+@pytest.mark.parametrize("mid", [0, 18])
+def test_workspace_reuse_across_shapes_and_dtypes(mid):
+    """One engine workspace serves calls of different shape / dtype / graph: a large fp32 call followed by a small fp16
+    one lays the buffers out differently, and the pad lanes of the second layout must not see stale fp32 bytes (Inf /
+    NaN as fp16).  Result must equal a fresh engine's."""
+    from ntire2022_esr_b200 import build_model
+
+    dr = O.MODELS[mid]["data_range"]
+    g = torch.Generator().manual_seed(3)
+    big = (torch.rand(2, 3, 96, 80, generator=g) * dr).cuda()
+    small = (torch.rand(1, 3, 40, 56, generator=g) * dr).cuda().half()
+    fresh = build_model(mid, state_dict=_weights(mid)).eval().to("cuda:0")
+    want = fresh(small).clone()
+    m = build_model(mid, state_dict=_weights(mid)).eval().to("cuda:0")
+    m(big)
+    m.engine(torch.device("cuda:0"))._ws.fill_(0x7C)          # 0x7C7C = fp16 Inf: the worst bytes the big fp32 call could leave behind
+    got = m(small)
+    assert torch.isfinite(got).all() and torch.equal(got, want)
+    assert torch.equal(m(small), want)
