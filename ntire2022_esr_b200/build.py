@@ -31,7 +31,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + \
+    cmd = [nvcc] + NVCC_FLAGS + os.environ.get("ESR_NVCC_EXTRA", "").split() + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + \
           [os.path.join(CSRC, s) for s in SOURCES]
     subprocess.run(cmd, check=True)
     return OUT

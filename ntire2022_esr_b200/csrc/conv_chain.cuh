@@ -171,6 +171,34 @@ __device__ __forceinline__ void mbar_wait_cl(uint64_t* bar, uint32_t parity) {
     }
   }
 }
+// The same on a precomputed 32-bit shared address.  In a cluster launch every use of a __shared__ symbol's address
+// costs an S2R of the CTA's cluster rank plus address arithmetic; the single-thread roles keep ONE laundered base
+// address in a register and add compile-time offsets instead.
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t}\n"
+      : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __noinline__ void mbar_wait_slow_a(uint32_t addr, uint32_t parity) {
+  const long long t0 = clock64();
+  while (!mbar_try_wait_a(addr, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("esr chain: mbarrier timeout block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x, addr, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t addr, uint32_t parity) {
+  if (mbar_try_wait_a(addr, parity)) return;
+  mbar_wait_slow_a(addr, parity);
+}
+__device__ __forceinline__ void umma_commit_a(uint32_t addr) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(addr) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
   int v;
@@ -192,6 +220,32 @@ __device__ __forceinline__ void umma_f16_ss_hi(uint32_t tmem_d, uint32_t a_lo, u
       ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(a_hi), "r"(b_hi));
 }
 
+// n (0..4) consecutive K steps of one tap in ONE asm statement: the descriptors advance by 32 bytes (+2) per K step
+// inside the statement, so ptxas keeps them in uniform registers (UIADD3.64) instead of moving four operands from
+// vector registers (R2UR) and two constants (UMOV) for every MMA - ~4 instead of ~8 instructions per MMA for the
+// single issuing thread, whose instruction rate is what bounds a step.  The first MMA uses `acc0`, the others accumulate.
+__device__ __forceinline__ void umma_f16_ss_run(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                uint32_t idesc, uint32_t acc0, int n) {
+  asm volatile(
+      "{\n\t.reg .pred p, q0, q1, q2, q3;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.gt.s32 q0, %7, 0;\n\t"
+      "setp.gt.s32 q1, %7, 1;\n\t"
+      "setp.gt.s32 q2, %7, 2;\n\t"
+      "setp.gt.s32 q3, %7, 3;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %6};\n\t"
+      "@q0 tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
+      "add.s64 da, da, 2;\n\tadd.s64 db, db, 2;\n\t"
+      "@q1 tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, 1;\n\t"
+      "add.s64 da, da, 2;\n\tadd.s64 db, db, 2;\n\t"
+      "@q2 tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, 1;\n\t"
+      "add.s64 da, da, 2;\n\tadd.s64 db, db, 2;\n\t"
+      "@q3 tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, 1;\n\t"
+      "}\n"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(acc0), "r"(a_hi), "r"(b_hi), "r"(n));
+}
+
 __device__ __forceinline__ long long global_timer_ns() {
   long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -199,7 +253,7 @@ __device__ __forceinline__ long long global_timer_ns() {
 }
 #define CH_STAMP(role, idx)                                                                        \
   do {                                                                                             \
-    if (dbg != nullptr && blockIdx.x == 0 && (idx) < 64) dbg[(role) * 64 + (idx)] = clock64();      \
+    if (dbg != nullptr && (int)blockIdx.x == (p.dbg_flags >> 8) && (idx) < 64) dbg[(role) * 64 + (idx)] = clock64();  /* dbg_flags >> 8: the block whose roles are stamped */      \
   } while (0)
 
 // kPw: compiled with / without the optional pointwise last stage (its code costs the common instantiation registers)
@@ -207,8 +261,17 @@ template <bool kPw>
 __global__ void __launch_bounds__(CH_THREADS, 1)
 conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ ChainParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t tma_full[CH_SLOTS], sd[CH_SLOTS], ready[CH_R], wrote[CH_R], nfree[CH_R], wfull[4], sfree[2], ring_read, ident_bar,
-      pw_afull[2], pw_wfull, pw_drow[CH_R], pw_sfree[2], pw_done, pw_dpre;
+  // every mbarrier of the CTA in one array (the MMA issuer addresses them as base + compile-time offset)
+  enum { B_TMA_FULL = 0, B_SD = B_TMA_FULL + CH_SLOTS, B_READY = B_SD + CH_SLOTS, B_WROTE = B_READY + CH_R, B_NFREE = B_WROTE + CH_R,
+         B_WFULL = B_NFREE + CH_R, B_SFREE = B_WFULL + 4, B_RING_READ = B_SFREE + 2, B_IDENT = B_RING_READ + 1, B_PW_AFULL = B_IDENT + 1,
+         B_PW_WFULL = B_PW_AFULL + 2, B_PW_DROW = B_PW_WFULL + 1, B_PW_SFREE = B_PW_DROW + CH_R, B_PW_DONE = B_PW_SFREE + 2,
+         B_PW_DPRE = B_PW_DONE + 1, B_COUNT = B_PW_DPRE + 1 };
+  __shared__ uint64_t bars[B_COUNT];
+  uint64_t* const tma_full = bars + B_TMA_FULL; uint64_t* const sd = bars + B_SD; uint64_t* const ready = bars + B_READY;
+  uint64_t* const wrote = bars + B_WROTE; uint64_t* const nfree = bars + B_NFREE; uint64_t* const wfull = bars + B_WFULL;
+  uint64_t* const sfree = bars + B_SFREE; uint64_t& ring_read = bars[B_RING_READ]; uint64_t& ident_bar = bars[B_IDENT];
+  uint64_t* const pw_afull = bars + B_PW_AFULL; uint64_t& pw_wfull = bars[B_PW_WFULL]; uint64_t* const pw_drow = bars + B_PW_DROW;
+  uint64_t* const pw_sfree = bars + B_PW_SFREE; uint64_t& pw_done = bars[B_PW_DONE]; uint64_t& pw_dpre = bars[B_PW_DPRE];
   __shared__ uint64_t sched_bar[2];
   __shared__ int sched_item[2];
   __shared__ uint32_t tmem_base_s;
@@ -426,43 +489,51 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
     if (elect_one()) {
       const bool no_mma = (p.dbg_flags & 1) != 0;
       const uint32_t w_base = smem_base + p.w_off, ctr_base = smem_base + p.ctr_off, ident_base = smem_base + p.ident_off;
-      const int ctr_acc_col = p.ctr_acc_col;
       mbar_wait(&ident_bar, 0);
+      uint32_t bars_a;                                           // laundered: must not be rematerialised from the symbol
+      asm volatile("mov.u32 %0, %1;" : "=r"(bars_a) : "r"(smem_u32(bars)));
+      auto BA = [&](int idx) -> uint32_t { return bars_a + 8u * (uint32_t)idx; };
       const uint32_t HI_A = 0x40004040u, HI_B3 = 0x400040C0u;   // SBO 1024 / 3072 bytes, version 1, SWIZZLE_128B
       // position in the (band, layer, step) sequence
       int it_item = (int)cid, it_l = 0, it_i = R + 1;
       uint32_t it_g = 0, it_items = 0, it_ctr = 0;
       bool it_valid = it_item < n_items;
+      uint32_t ctr_mask = 0;
+      for (int l = 0; l < nL; ++l) if (p.L[l].ctr_n > 0) ctr_mask |= 1u << l;
       auto wait_step = [&](int l, int i, uint32_t g, uint32_t items, uint32_t ctrc) {
-        if (l == nL) {   // pointwise stage: steps R+1, R are empty; step j < R = output row j
+        if (kPw && l == nL) {   // pointwise stage: steps R+1, R are empty; step j < R = output row j
           if (i >= R) return;
           const int pr = (R - 1 - i) & 1;
-          if (i == R - 1) mbar_wait(&pw_wfull, items & 1u);
-          mbar_wait(&pw_afull[pr], i < R - 2 ? 1u : 0u);     // each slot pair is filled twice per band
-          if (p.pw.from_smem) mbar_wait(&ready[i], (g - 1) & 1u);   // ... and the last 3x3 layer's epilogue has added its channels
-          if (i < R - 2) mbar_wait(&ready[i + 2], g & 1u);    // row i+2 used the same accumulator: drained
+          if (i == R - 1) mbar_wait_a(BA(B_PW_WFULL), items & 1u);
+          mbar_wait_a(BA(B_PW_AFULL + pr), i < R - 2 ? 1u : 0u);     // each slot pair is filled twice per band
+          if (p.pw.from_smem) mbar_wait_a(BA(B_READY + i), (g - 1) & 1u);   // ... and the last 3x3 layer's epilogue has added its channels
+          if (i < R - 2) mbar_wait_a(BA(B_READY + i + 2), g & 1u);    // row i+2 used the same accumulator: drained
           return;
         }
         if (l == 0 && g > 0 && has_pw && i == R + 1)          // the pointwise accumulators overlap every row's columns
-          for (int j = 0; j < R; ++j) mbar_wait(&ready[j], (g - 1) & 1u);
+          for (int j = 0; j < R; ++j) mbar_wait_a(BA(B_READY + j), (g - 1) & 1u);
         const uint32_t g3 = g - items * (uint32_t)(nG - nL);   // 3x3 layers so far (the weight / halo-row barriers skip the pointwise stage)
-        if (l == 0 || i < 2) mbar_wait(&tma_full[i], (i < 2 ? g3 : items) & 1u);
+        if (l == 0 || i < 2) mbar_wait_a(BA(B_TMA_FULL + i), (i < 2 ? g3 : items) & 1u);
         // input row written (own + side pixels), accumulator drained.  The side pixels arrive as st.async transactions
         // on this barrier (async proxy, like a multicast TMA load): a plain CTA-scope wait orders them
-        if (g > 0 && i >= 2) mbar_wait(&ready[i - 2], (g - 1) & 1u);
-        if (i == R + 1) mbar_wait(&wfull[0], g3 & 1u);
-        if (i == R) { mbar_wait(&wfull[1], g3 & 1u); if (p.L[l].ctr_n > 0) mbar_wait(&wfull[3], ctrc & 1u); }
-        if (i == R - 1) mbar_wait(&wfull[2], g3 & 1u);
+        if (g > 0 && i >= 2) mbar_wait_a(BA(B_READY + i - 2), (g - 1) & 1u);
+        // weight part q is first needed by step R+1-q; the centre block by step R
+        if (i >= R - 1) mbar_wait_a(BA(B_WFULL + R + 1 - i), g3 & 1u);
+        if (i == R && ((ctr_mask >> l) & 1u)) mbar_wait_a(BA(B_WFULL + 3), ctrc & 1u);
       };
       if (it_valid) wait_step(0, R + 1, 0, 0, 0);
       // the current layer's constants live in registers and change only at a layer boundary (an indexed read of the
       // parameter bank per step costs the single issuing thread tens of cycles each)
       int np = 0, ks = 0, ctr_n = 0, acc_col = 0, part_bytes = 0, cur_l = -1;
       bool res_ident = false;
+      const uint32_t d_ctr = tmem_base + (uint32_t)p.ctr_acc_col;
+      const uint32_t A_RING = 0x10000u | (((ring_base + (CH_PX0 - 1) * 128) & 0x3FFFFu) >> 4);   // + SLOT >> 4 per row
+      const uint32_t B_W = 0x10000u | ((w_base & 0x3FFFFu) >> 4);
+      const uint32_t B_CTR = 0x10000u | ((ctr_base & 0x3FFFFu) >> 4), B_ID = 0x10000u | ((ident_base & 0x3FFFFu) >> 4);
       while (it_valid) {
         const int l = it_l, i = it_i;
         const uint32_t g = it_g;
-        if (l == nL) {
+        if (kPw && l == nL) {
           // ---- pointwise stage
           tc_fence_after_sync();
           if (i < R && !no_mma) {
@@ -476,7 +547,7 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
               for (int k = 0; k < P.ksteps; ++k) umma_f16_ss_hi(d, Ap + 2u * k, HI_A, Bp + 2u * k, HI_A, idp, (c | k) ? 1u : 0u);
             }
           }
-          umma_commit(&sd[i]);
+          umma_commit_a(BA(B_SD + i));
           if (g < 8) CH_STAMP(1, g * 6 + i);
           if (--it_i < 0) {
             it_i = R + 1;
@@ -491,7 +562,7 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
         }
         if (l != cur_l) {
           const ChLayer& Lr = p.L[l];
-          np = Lr.np; ks = Lr.ksteps; ctr_n = Lr.ctr_n; acc_col = Lr.acc_col; part_bytes = Lr.part_bytes;
+          np = Lr.np; ks = no_mma ? 0 : Lr.ksteps; ctr_n = Lr.ctr_n; acc_col = Lr.acc_col; part_bytes = Lr.part_bytes;
           res_ident = Lr.res_smem != 0;
           cur_l = l;
         }
@@ -500,31 +571,32 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
         if (g < 5) CH_STAMP(3, g * 12 + i * 2);
         const int jlo = max(i - 2, 0), jhi = min(i, R - 1), nj = jhi - jlo + 1;
         const int part0 = i >= 2 ? 0 : (i == 1 ? 1 : 2);
-        const uint32_t a_base = ring_base + (uint32_t)i * CH_SLOT_BYTES + (CH_PX0 - 1) * 128;
-        const uint32_t A0 = 0x10000u | ((a_base & 0x3FFFFu) >> 4);                               // + 8 per dx, + 2 per K step
-        const uint32_t B0 = 0x10000u | (((w_base + (uint32_t)(part0 * part_bytes)) & 0x3FFFFu) >> 4);   // + 64 per dx, + 2 per K step
+        const uint32_t A0 = A_RING + (uint32_t)i * (CH_SLOT_BYTES >> 4);                     // + 8 per dx, + 2 per K step
+        const uint32_t B0 = B_W + (uint32_t)part0 * pb16;                                    // + 64 per dx, + 2 per K step
         const uint32_t d0 = tmem_base + (uint32_t)(acc_col + jlo * np);
         const uint32_t id_all = umma_idesc_f16((uint32_t)(np * nj)), id_one = umma_idesc_f16((uint32_t)np);
-        const uint32_t id_rest = umma_idesc_f16((uint32_t)(np * (nj > 1 ? nj - 1 : 1)));
-        if (!no_mma) {
-          // dx = -1 and dx = 0 taps; the very first MMA of a step with i >= 2 initialises output row i-2
+        // the very first MMA of a step with i >= 2 initialises output row i-2 (and accumulates onto the others)
+        if (ks > 0) {
           if (i >= 2) {
             umma_f16_ss_hi(d0, A0, HI_A, B0, HI_B3, id_one, 0u);
-            if (nj > 1) umma_f16_ss_hi(d0 + (uint32_t)np, A0, HI_A, B0 + pb16, HI_B3, id_rest, 1u);
+            if (nj > 1) umma_f16_ss_hi(d0 + (uint32_t)np, A0, HI_A, B0 + pb16, HI_B3, umma_idesc_f16((uint32_t)(np * (nj - 1))), 1u);
           } else {
             umma_f16_ss_hi(d0, A0, HI_A, B0, HI_B3, id_all, 1u);
           }
-          if (ks > 1) umma_f16_ss_hi(d0, A0 + 2, HI_A, B0 + 2, HI_B3, id_all, 1u);
-          if (ks > 2) umma_f16_ss_hi(d0, A0 + 4, HI_A, B0 + 4, HI_B3, id_all, 1u);
-          if (ks > 3) umma_f16_ss_hi(d0, A0 + 6, HI_A, B0 + 6, HI_B3, id_all, 1u);
-          umma_f16_ss_hi(d0, A0 + 8, HI_A, B0 + 64, HI_B3, id_all, 1u);
-          if (ks > 1) umma_f16_ss_hi(d0, A0 + 10, HI_A, B0 + 66, HI_B3, id_all, 1u);
-          if (ks > 2) umma_f16_ss_hi(d0, A0 + 12, HI_A, B0 + 68, HI_B3, id_all, 1u);
-          if (ks > 3) umma_f16_ss_hi(d0, A0 + 14, HI_A, B0 + 70, HI_B3, id_all, 1u);
         }
+        // The short MMAs (the centre block of the distillation 1x1, N <= 32, on output row i-1, and the identity tap of
+        // the block residual) go right behind the first tap: the step ends with full-width MMAs, which is what the
+        // tensor pipe works on while this thread commits and sets up the next step
+        if (i >= 1 && i <= R) {
+          if (ctr_n > 0) umma_f16_ss_run(d_ctr + (uint32_t)((i - 1) * 32), A0 + 8, HI_A, B_CTR, HI_A, umma_idesc_f16((uint32_t)ctr_n), 0u, ks);
+          if (res_ident) umma_f16_ss_run(tmem_base + (uint32_t)(acc_col + (i - 1) * np), A0 + 8, HI_A, B_ID, HI_A, id_one, 1u, ks);
+        }
+        // dx = -1 (remaining K steps) and dx = 0 taps
+        umma_f16_ss_run(d0, A0 + 2, HI_A, B0 + 2, HI_B3, id_all, 1u, ks - 1);
+        umma_f16_ss_run(d0, A0 + 8, HI_A, B0 + 64, HI_B3, id_all, 1u, ks);
         // advance, and take the next step's waits while the MMAs above execute - unless the next step opens a new
-        // stage: its weights may only be requested once THIS step has been committed (a wider layer after a narrower
-        // one waits for sd[0]), so waiting for them here would be a cycle
+        // stage whose weights may only be requested once THIS step has been committed (a wider layer after a narrower
+        // one waits for sd[0]; the pointwise stage): waiting for them here would be a cycle
         bool deferred_wait = false;
         {
           if (--it_i < 0) {
@@ -540,38 +612,14 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
           }
           if (it_valid) {
             // (equal widths: the next stage's first weight part was requested after step 2 - safe to wait for here)
-            if (it_i == R + 1 && (it_l == nL || (p.L[it_l].part_bytes - 1) / part_bytes >= 2)) deferred_wait = true;
+            if (it_i == R + 1 && (it_l == nL || p.L[it_l].part_bytes > 2 * part_bytes)) deferred_wait = true;
             else wait_step(it_l, it_i, it_g, it_items, it_ctr);
           }
         }
-        if (!no_mma) {
-          umma_f16_ss_hi(d0, A0 + 16, HI_A, B0 + 128, HI_B3, id_all, 1u);
-          if (ks > 1) umma_f16_ss_hi(d0, A0 + 18, HI_A, B0 + 130, HI_B3, id_all, 1u);
-          if (ks > 2) umma_f16_ss_hi(d0, A0 + 20, HI_A, B0 + 132, HI_B3, id_all, 1u);
-          if (ks > 3) umma_f16_ss_hi(d0, A0 + 22, HI_A, B0 + 134, HI_B3, id_all, 1u);
-          if (i >= 1 && i <= R) {
-            const uint32_t Ac = A0 + 8;   // centre tap
-            if (ctr_n > 0) {              // centre-tap-only block (distillation 1x1) of output row i-1
-              const uint32_t dc = tmem_base + (uint32_t)(ctr_acc_col + (i - 1) * 32);
-              const uint32_t Bc = 0x10000u | ((ctr_base & 0x3FFFFu) >> 4);
-              const uint32_t idc = umma_idesc_f16((uint32_t)ctr_n);
-              umma_f16_ss_hi(dc, Ac, HI_A, Bc, HI_A, idc, 0u);
-              if (ks > 1) umma_f16_ss_hi(dc, Ac + 2, HI_A, Bc + 2, HI_A, idc, 1u);
-              if (ks > 2) umma_f16_ss_hi(dc, Ac + 4, HI_A, Bc + 4, HI_A, idc, 1u);
-              if (ks > 3) umma_f16_ss_hi(dc, Ac + 6, HI_A, Bc + 6, HI_A, idc, 1u);
-            }
-            if (res_ident) {              // block residual `+ input`: exact identity tap onto output row i-1
-              const uint32_t dr = tmem_base + (uint32_t)(acc_col + (i - 1) * np);
-              const uint32_t Bi = 0x10000u | ((ident_base & 0x3FFFFu) >> 4);
-              umma_f16_ss_hi(dr, Ac, HI_A, Bi, HI_A, id_one, 1u);
-              if (ks > 1) umma_f16_ss_hi(dr, Ac + 2, HI_A, Bi + 2, HI_A, id_one, 1u);
-              if (ks > 2) umma_f16_ss_hi(dr, Ac + 4, HI_A, Bi + 4, HI_A, id_one, 1u);
-              if (ks > 3) umma_f16_ss_hi(dr, Ac + 6, HI_A, Bi + 6, HI_A, id_one, 1u);
-            }
-          }
-        }
+        // dx = +1 taps
+        umma_f16_ss_run(d0, A0 + 16, HI_A, B0 + 128, HI_B3, id_all, 1u, ks);
         if (g < 5) CH_STAMP(3, g * 12 + i * 2 + 1);
-        umma_commit(&sd[i]);
+        umma_commit_a(BA(B_SD + i));
         if (g < 8) CH_STAMP(1, g * 6 + i);
         if (deferred_wait) wait_step(it_l, it_i, it_g, it_items, it_ctr);
       }

@@ -55,6 +55,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) {
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
+#ifdef ESR_WAIT_NANOSLEEP
+    __nanosleep(ESR_WAIT_NANOSLEEP);
+#endif
     if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
       printf("esr: mbarrier timeout block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x,
              smem_u32(bar), parity);

@@ -393,3 +393,41 @@ def test_workspace_reuse_across_shapes_and_dtypes(mid):
     got = m(small)
     assert torch.isfinite(got).all() and torch.equal(got, want)
     assert torch.equal(m(small), want)
+
+
+@pytest.mark.parametrize("mid,arch", GOLDEN)
+def test_tcgen05_kernels_width_and_variant_sweep_vs_oracle(mid, arch):
+    """The shape family of the tcgen05 kernels, network by network (the channel counts of the seven graphs cover
+    Cin / Cout in {3, 12, 16, 24, 25, 40, 46..50, 64, 100, 200, 320}): widths around the 128-pixel strip boundaries
+    (one partial strip, exact strips, one pixel more, four strips), heights that are 3, 0, 1 and 2 rows past a multiple of
+    the fused chain kernel's 4-row band, batch 2, and every kernel variant that can serve them - fused chain kernel,
+    per-layer kernel with 3 and 4
+    accumulator slots, forced multi-band chains.  Every variant must agree with the numpy oracle to the fp16 bar and
+    the variants must agree with each other to the same bar."""
+    dr = O.MODELS[mid]["data_range"]
+    w = _weights(mid)
+    eng = _model(mid).engine(torch.device("cuda:0"))
+    rng = np.random.default_rng(77)
+    variants = [{"chain_enable": 1, "tc_acc_slots": 4}, {"chain_enable": 0, "tc_acc_slots": 4},
+                {"chain_enable": 0, "tc_acc_slots": 3}, {"chain_enable": 2, "tc_acc_slots": 4}]
+    try:
+        for (b, h, wd) in [(2, 15, 15), (1, 16, 127), (2, 17, 128), (1, 19, 129), (1, 15, 257), (1, 18, 510)]:   # 15 = ESA's minimum extent
+            x = (rng.random((b, 3, h, wd), dtype=np.float32) * dr).astype(np.float16)
+            ref = O.forward(O.MODELS[mid]["arch"], w, x.astype(np.float32), dtype=np.float32)
+            xt = torch.from_numpy(x).cuda()
+            outs = []
+            for v in variants:
+                for k, val in v.items():
+                    eng.set_option(k, val)
+                y = eng.forward(xt).float().cpu().numpy()
+                assert np.isfinite(y).all(), (arch, (b, h, wd), v)
+                p = _psnr(y, ref, dr)
+                assert p >= FP16_PSNR_BAR_BY_ID.get(mid, FP16_PSNR_BAR) - 1.0, (arch, (b, h, wd), v, p)
+                outs.append(y)
+            for y in outs[1:]:
+                # the variants round differently (fp16 storage between layers; an outlier activation on uniform noise costs
+                # every fp16 path, the CUDA-core one included, several units locally): they agree to the same PSNR bar
+                assert _psnr(y, outs[0], dr) >= FP16_PSNR_BAR_BY_ID.get(mid, FP16_PSNR_BAR) - 1.0, (arch, (b, h, wd))
+    finally:
+        eng.set_option("chain_enable", 1)
+        eng.set_option("tc_acc_slots", 4)

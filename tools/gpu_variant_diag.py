@@ -1,0 +1,58 @@
+"""Developer probe (GPU box): every tcgen05 kernel variant against the numpy oracle at one shape, with the location of the worst pixel.
+
+    python tools/gpu_variant_diag.py rlfn 1 19 129
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import esr_oracle as O  # noqa: E402
+
+IDS = {"imdn": -1, "rfdn": 0, "rlfn": 4, "bsrn": 18, "rfdn40": 22, "rfdn_pruned": 40, "imdn_nb7": 26}
+
+
+def main():
+    import torch
+    from ntire2022_esr_b200 import build_model
+    tag, b, h, wd = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
+    seed = int(sys.argv[5]) if len(sys.argv) > 5 else 77
+    mid = IDS[tag]
+    w = O.load_weights(os.path.join(ROOT, "tests", "golden", "weights", O.MODELS[mid]["weights"] + ".npz"))
+    dr = O.MODELS[mid]["data_range"]
+    m = build_model(mid, state_dict=w).eval().to("cuda:0")
+    eng = m.engine(torch.device("cuda:0"))
+    rng = np.random.default_rng(seed)
+    if len(sys.argv) > 6:      # replay the sweep test's draw sequence up to this shape
+        for (b0, h0, w0) in [(2, 15, 15), (1, 16, 127), (2, 17, 128), (1, 19, 129), (1, 15, 257), (1, 18, 510)]:
+            if (b0, h0, w0) == (b, h, wd):
+                break
+            rng.random((b0, 3, h0, w0), dtype=np.float32)
+    x = (rng.random((b, 3, h, wd), dtype=np.float32) * dr).astype(np.float16)
+    ref = O.forward(O.MODELS[mid]["arch"], w, x.astype(np.float32), dtype=np.float32)
+    xt = torch.from_numpy(x).cuda()
+    for v in ({"chain_enable": 1, "tc_acc_slots": 4}, {"chain_enable": 0, "tc_acc_slots": 4}, {"chain_enable": 0, "tc_acc_slots": 3},
+              {"chain_enable": 2, "tc_acc_slots": 4}, {"tc_enable": 0}):
+        eng.set_option("tc_enable", 1)
+        for k, val in v.items():
+            eng.set_option(k, val)
+        y = eng.forward(xt).float().cpu().numpy()
+        e = np.abs(y - ref)
+        idx = np.unravel_index(np.argmax(e), e.shape)
+        mse = np.mean((y.astype(np.float64) - ref) ** 2)
+        if "y0" not in dir():
+            y0 = y
+        dv = np.abs(y - y0)
+        iv = np.unravel_index(np.argmax(dv), dv.shape)
+        print(f"   vs variant 0: max {dv.max():.3f} at {tuple(int(t) for t in iv)} (y {y[iv]:.2f}, y0 {y0[iv]:.2f}, ref {ref[iv]:.2f})")
+        print(f"{v}: max|err| {e.max():.3f} at (b,c,Y,X)={idx} -> LR ({idx[2] // 4},{idx[3] // 4}); >1.0: {(e > 1.0).sum()}  psnr {10 * np.log10(dr * dr / mse):.2f} dB; "
+              f"ref there {ref[idx]:.2f}", flush=True)
+        rows = np.unique(np.nonzero(e.max(axis=(0, 1, 3)) > 1.0)[0] // 4)
+        cols = np.unique(np.nonzero(e.max(axis=(0, 1, 2)) > 1.0)[0] // 4)
+        print("   LR rows with err > 1:", rows[:30], " cols:", cols[:30])
+
+
+if __name__ == "__main__":
+    main()
