@@ -500,7 +500,9 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
       bool it_valid = it_item < n_items;
       uint32_t ctr_mask = 0;
       for (int l = 0; l < nL; ++l) if (p.L[l].ctr_n > 0) ctr_mask |= 1u << l;
+      const bool no_wait = (p.dbg_flags & 16) != 0, no_short = (p.dbg_flags & 32) != 0;   // timing experiments (results are wrong)
       auto wait_step = [&](int l, int i, uint32_t g, uint32_t items, uint32_t ctrc) {
+        if (no_wait) return;
         if (kPw && l == nL) {   // pointwise stage: steps R+1, R are empty; step j < R = output row j
           if (i >= R) return;
           const int pr = (R - 1 - i) & 1;
@@ -587,7 +589,7 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
         // The short MMAs (the centre block of the distillation 1x1, N <= 32, on output row i-1, and the identity tap of
         // the block residual) go right behind the first tap: the step ends with full-width MMAs, which is what the
         // tensor pipe works on while this thread commits and sets up the next step
-        if (i >= 1 && i <= R) {
+        if (i >= 1 && i <= R && !no_short) {
           if (ctr_n > 0) umma_f16_ss_run(d_ctr + (uint32_t)((i - 1) * 32), A0 + 8, HI_A, B_CTR, HI_A, umma_idesc_f16((uint32_t)ctr_n), 0u, ks);
           if (res_ident) umma_f16_ss_run(tmem_base + (uint32_t)(acc_col + (i - 1) * np), A0 + 8, HI_A, B_ID, HI_A, id_one, 1u, ks);
         }
@@ -613,7 +615,11 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
           if (it_valid) {
             // (equal widths: the next stage's first weight part was requested after step 2 - safe to wait for here)
             if (it_i == R + 1 && (it_l == nL || p.L[it_l].part_bytes > 2 * part_bytes)) deferred_wait = true;
-            else wait_step(it_l, it_i, it_g, it_items, it_ctr);
+            else {
+              if (g == 2) CH_STAMP(3, 48 + i * 2);        // (timeline: how long the mid-step wait of layer 2 blocks)
+              wait_step(it_l, it_i, it_g, it_items, it_ctr);
+              if (g == 2) CH_STAMP(3, 49 + i * 2);
+            }
           }
         }
         // dx = +1 taps

@@ -25,13 +25,21 @@ def shard_bounds(n_images: int, world: int) -> List[Tuple[int, int]]:
     return out
 
 
+def _p2p(ops) -> None:
+    """All point-to-point transfers of one phase as ONE grouped operation (NCCL: ncclGroupStart/End, the transfers
+    run concurrently over NVLink instead of one after the other)."""
+    if ops:
+        for q in dist.batch_isend_irecv(ops):
+            q.wait()
+
+
 def forward_sharded(model: Callable[[torch.Tensor], torch.Tensor], images: Optional[torch.Tensor], n_images: int,
                     shape_chw: Sequence[int], dtype: torch.dtype, device: torch.device, root: int = 0,
-                    gather: bool = True, group=None) -> Optional[torch.Tensor]:
+                    gather: bool = True, group=None, out: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
     """Rank `root` holds `images` (n_images, 3, H, W); every rank runs `model` on its shard.
 
-    Returns the (n_images, 3, 4H, 4W) result on `root` when gather=True (None elsewhere); with
-    gather=False every rank returns its own shard (true data-parallel serving: outputs stay sharded).
+    Returns the (n_images, 3, 4H, 4W) result on `root` when gather=True (None elsewhere; `out`, if given on the root,
+    receives it); with gather=False every rank returns its own shard (true data-parallel serving: outputs stay sharded).
     """
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -41,30 +49,27 @@ def forward_sharded(model: Callable[[torch.Tensor], torch.Tensor], images: Optio
     if world == 1:
         x = images.to(device)
     else:
-        x = torch.empty((e - s, c, h, w), dtype=dtype, device=device)
         if rank == root:
-            reqs = []
-            for r, (rs, re_) in enumerate(bounds):
-                if r == root:
-                    x.copy_(images[rs:re_])
-                elif re_ > rs:
-                    reqs.append(dist.isend(images[rs:re_].contiguous().to(device), dst=r, group=group))
-            for q in reqs:
-                q.wait()
-        elif e > s:
-            dist.recv(x, src=root, group=group)
-    y = model(x) if e > s else torch.empty((0, c, 4 * h, 4 * w), dtype=dtype, device=device)
+            src = images.to(device)
+            x = src[s:e]
+            _p2p([dist.P2POp(dist.isend, src[rs:re_], r, group) for r, (rs, re_) in enumerate(bounds) if r != root and re_ > rs])
+        else:
+            x = torch.empty((e - s, c, h, w), dtype=dtype, device=device)
+            if e > s:
+                _p2p([dist.P2POp(dist.irecv, x, root, group)])
+    y = model(x.contiguous()) if e > s else torch.empty((0, c, 4 * h, 4 * w), dtype=dtype, device=device)
     if not gather or world == 1:
         return y
     if rank == root:
-        out = torch.empty((n_images, c, 4 * h, 4 * w), dtype=dtype, device=device)
+        if out is None:
+            out = torch.empty((n_images, c, 4 * h, 4 * w), dtype=dtype, device=device)
+        elif tuple(out.shape) != (n_images, c, 4 * h, 4 * w) or out.dtype != dtype or not out.is_contiguous():
+            raise ValueError("forward_sharded: `out` must be a contiguous (n_images, C, 4H, 4W) tensor of the model dtype")
         out[s:e].copy_(y)
-        for r, (rs, re_) in enumerate(bounds):
-            if r != root and re_ > rs:
-                dist.recv(out[rs:re_], src=r, group=group)
+        _p2p([dist.P2POp(dist.irecv, out[rs:re_], r, group) for r, (rs, re_) in enumerate(bounds) if r != root and re_ > rs])
         return out
     if e > s:
-        dist.send(y.contiguous(), dst=root, group=group)
+        _p2p([dist.P2POp(dist.isend, y.contiguous(), root, group)])
     return None
 
 

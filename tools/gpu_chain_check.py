@@ -134,6 +134,9 @@ def main():
                     e5 = t[8 + j * 8: 8 + j * 8 + 5]
                     if e5.max() > 0:
                         print(f"      pw epi row {j}: begin {int(e5[0] - t0)} +sd wait {int(e5[1] - e5[0])} +bar waits {int(e5[2] - e5[1])} +units {int(e5[3] - e5[2])} +fence/arrive {int(e5[4] - e5[3])}")
+                w4 = t[192 + 48: 192 + 60]
+                if w4.max() > 0:
+                    print("      layer 2 mid-step wait for the next step (i=5..0) begin/+blocked: " + "  ".join(f"{int(w4[2 * i] - t0)}/+{int(w4[2 * i + 1] - w4[2 * i])}" for i in range(5, -1, -1) if w4[2 * i] > 0))
                 for g in range(4):
                     w = t[192 + g * 12: 192 + g * 12 + 12]
                     if w.max() == 0:
