@@ -132,6 +132,15 @@ int esr_debug_timeline(esr_handle* h, long long* out, int n_launches);
 int esr_debug_tc_layer(esr_handle* h, int index, char* name, int name_cap, int32_t* meta, int32_t* entries, int32_t* groups,
                        float* bias, float* bias9, uint8_t* blob, size_t blob_cap);
 
+/* Test aid (host only): the packed form of the index-th fused chain of the fp16 plan - what conv_chain_kernel is
+ * handed (tests/test_chain_packing_cpu.py replays it in the kernel's row-stationary order).  index < 0 returns the
+ * number of chains.  meta[4] = {n_layers, blob_bytes, first tcgen05 layer (esr_debug_tc_layer index), has pointwise stage};
+ * layers[l][12] = {tcgen05 layer index, np, k16_steps, centre_cols, part_bytes, blob_offset, identity_tap, n0, n1,
+ * group1_is_centre_block, group1_first_column, 0}.  Blob layout per layer: three dy parts (dy = +1, 0, -1), each
+ * [np/8 atoms][3 dx][8 rows x 128 B, SWIZZLE_128B]; the centre block [centre_cols x 64] K-major SWIZZLE_128B (4 KB);
+ * 128 bias floats (group 0 at [0, 64), group 1 at [64, 128)). */
+int esr_debug_chain(esr_handle* h, int index, int32_t* meta, int32_t* layers, uint8_t* blob, size_t blob_cap);
+
 const char* esr_last_error(esr_handle* h);
 void esr_destroy(esr_handle* h);
 

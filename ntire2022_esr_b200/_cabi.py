@@ -45,6 +45,7 @@ SYMBOLS = [
     ("esr_debug_tc_layer", _c.c_int, [_c.c_void_p, _c.c_int, _c.c_char_p, _c.c_int, _c.POINTER(_c.c_int32),
                                       _c.POINTER(_c.c_int32), _c.POINTER(_c.c_int32), _c.POINTER(_c.c_float),
                                       _c.POINTER(_c.c_float), _c.c_void_p, _c.c_size_t]),
+    ("esr_debug_chain", _c.c_int, [_c.c_void_p, _c.c_int, _c.POINTER(_c.c_int32), _c.POINTER(_c.c_int32), _c.c_void_p, _c.c_size_t]),
     ("esr_last_error", _c.c_char_p, [_c.c_void_p]),
     ("esr_destroy", None, [_c.c_void_p]),
     ("esr_version", _c.c_char_p, []),

@@ -1534,6 +1534,29 @@ int esr_debug_tc_layer(esr_handle* h, int index, char* name, int name_cap, int32
   return ESR_OK;
 }
 
+int esr_debug_chain(esr_handle* h, int index, int32_t* meta, int32_t* layers, uint8_t* blob, size_t blob_cap) {
+  if (!h) return ESR_E_INVALID;
+  if (!h->finalized) return fail(h, ESR_E_STATE, "esr_debug_chain before esr_finalize");
+  const DevGraph& dg = h->graphs[1];
+  const int n = (int)dg.g.chains.size();
+  if (index < 0) return n;                     // query: number of fused chains of the fp16 graph
+  if (index >= n || !meta || !layers) return fail(h, ESR_E_INVALID, "bad argument");
+  const ChainDecl& ch = dg.g.chains[index];
+  meta[0] = (int)ch.layers.size(); meta[1] = (int)ch.blob.size(); meta[2] = ch.layers.empty() ? -1 : ch.layers[0].tc;
+  meta[3] = ch.pw_tc >= 0 ? 1 : 0;
+  for (size_t l = 0; l < ch.layers.size(); ++l) {
+    const ChainLayerDecl& d = ch.layers[l];
+    int32_t* o = layers + 12 * l;
+    o[0] = d.tc; o[1] = d.np; o[2] = d.ksteps; o[3] = d.ctr_n; o[4] = d.part_bytes; o[5] = (int32_t)d.w_goff; o[6] = d.res_smem;
+    o[7] = d.n0; o[8] = d.n1; o[9] = d.g1_ctr; o[10] = d.col1; o[11] = 0;
+  }
+  if (blob) {
+    if (blob_cap < ch.blob.size()) return fail(h, ESR_E_INVALID, "blob buffer too small");
+    memcpy(blob, ch.blob.data(), ch.blob.size());
+  }
+  return ESR_OK;
+}
+
 const char* esr_last_error(esr_handle* h) { return h ? h->err.c_str() : "null handle"; }
 
 void esr_destroy(esr_handle* h) {
