@@ -1190,7 +1190,11 @@ static int forward_impl(esr_handle* h, const void* in_nchw, void* out_nchw, int 
   }
   Plan* pl = get_plan(h, in_nchw, out_nchw, B, H, W, dtype, workspace, rc, io);
   if (!pl) return rc;
-  struct PdlScope { PdlScope(bool on) { g_pdl = on; } ~PdlScope() { g_pdl = false; } } pdl_scope(h->opt_pdl != 0);
+  // use_pdl: 1 = every launch, 2 = only the small ESA kernels (their weight prologue and launch latency overlap the
+  // predecessor's tail; the 200 KB tcgen05 CTAs cannot co-reside with their predecessor, so they gain nothing)
+  struct PdlScope { ~PdlScope() { g_pdl = false; } } pdl_scope;
+  const int pdl_mode = h->opt_pdl;
+  auto set_pdl = [pdl_mode](const Launch& l) { g_pdl = pdl_mode == 1 || (pdl_mode == 2 && l.name.compare(0, 4, "esa_") == 0); };
   if (h->opt_use_graph && !pl->graph_failed && ++pl->hits >= 2) {
     if (!pl->gexec) {
       cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
@@ -1201,8 +1205,10 @@ static int forward_impl(esr_handle* h, const void* in_nchw, void* out_nchw, int 
         cudaGraph_t graph = nullptr;
         bool ok = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
         if (ok) {
-          for (auto& l : pl->launches)
+          for (auto& l : pl->launches) {
+            set_pdl(l);
             if (l.fn(cs) != cudaSuccess) { ok = false; break; }
+          }
           if (cudaStreamEndCapture(cs, &graph) != cudaSuccess) ok = false;
         }
         if (ok && cudaGraphInstantiate(&pl->gexec, graph, 0) != cudaSuccess) { ok = false; pl->gexec = nullptr; }
@@ -1217,6 +1223,7 @@ static int forward_impl(esr_handle* h, const void* in_nchw, void* out_nchw, int 
     }
   }
   for (auto& l : pl->launches) {
+    set_pdl(l);
     cudaError_t err = l.fn(s);
     if (err != cudaSuccess) return fail(h, ESR_E_CUDA, l.name + ": " + cudaGetErrorString(err));
   }
@@ -1464,7 +1471,7 @@ int esr_set_option(esr_handle* h, const char* key, int value) {
   else if (k == "tc_timeline") h->opt_timeline = value ? 1 : 0;
   else if (k == "tc_dbg_flags") h->opt_dbg_flags = value;
   else if (k == "tc_acc_slots") h->opt_acc_slots = value == 4 ? 4 : 2;
-  else if (k == "use_pdl") h->opt_pdl = value ? 1 : 0;
+  else if (k == "use_pdl") h->opt_pdl = value < 0 || value > 2 ? 0 : value;
   else if (k == "chain_enable") h->opt_chain = value == 2 ? 2 : (value ? 1 : 0);
   else if (k == "chain_store_all") h->opt_chain_store_all = value ? 1 : 0;
   else if (k == "chain_mask") h->opt_chain_mask = value;

@@ -7,6 +7,7 @@ matplotlib, force map_location, chdir to the reference root) and writes, next to
 
   weights/<name>.npz      state-dicts of the four in-scope checkpoints as fp32 numpy arrays
   test_bmp.npz            utils/test.bmp as uint8 HWC RGB (via the reference's imread_uint)
+  metrics_golden.npz      the reference's calculate_psnr / calculate_ssim / modcrop on a deterministic image pair (-101)
   test_bmp_lr.npz         the reference's imresize_np (MATLAB bicubic) of test.bmp: x1/4 (64x64), an odd crop, x2
   ref_<arch>_small.npz    seeded small inputs + FULL reference outputs (several odd sizes)
   ref_<arch>_256.npz      reference output on test.bmp (256x256): crops, strided subsample, stats
@@ -69,6 +70,17 @@ def main():
         hr = img.astype(np.float32) / 255.
         np.savez_compressed(os.path.join(HERE, "test_bmp_lr.npz"), lr64=util.imresize_np(hr.copy(), 1 / 4),
                             lr_odd=util.imresize_np(hr[:130, :77].copy(), 1 / 4), up2=util.imresize_np(hr[:40, :36].copy(), 2))
+    if not only or -101 in only:
+        # the harness metrics (row N3): the reference's calculate_psnr / calculate_ssim / modcrop on a deterministic pair
+        # (test.bmp and a perturbed copy), borders 0 and 4, RGB and grey  -> metrics_golden.npz
+        rng = np.random.default_rng(5)
+        a = img[:203, :187].copy()
+        b = np.clip(a.astype(np.int32) + rng.integers(-9, 10, a.shape), 0, 255).astype(np.uint8)
+        np.savez_compressed(os.path.join(HERE, "metrics_golden.npz"), a=a, b=b,
+                            psnr=np.array([util.calculate_psnr(a, b, border=k) for k in (0, 4)]),
+                            ssim=np.array([util.calculate_ssim(a, b, border=k) for k in (0, 4)]),
+                            ssim_grey=np.float64(util.calculate_ssim(a[..., 0], b[..., 0], border=4)),
+                            modcrop_shape=np.array(util.modcrop(a, 4).shape))
     for mid, (arch, fname) in MODELS.items():
         if only and mid not in only:
             continue
