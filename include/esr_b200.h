@@ -27,7 +27,7 @@ typedef struct esr_engine esr_handle;
 
 /* architectures: the four networks SURVEY.md section 8(a) puts on the hot path, plus the pruned RFDN of row N1
  * (models/team40_rfdn_pruned.py: RFDBs without the inner residual adds, ESA width 12) */
-enum { ESR_ARCH_IMDN = 0, ESR_ARCH_RFDN = 1, ESR_ARCH_RLFN = 2, ESR_ARCH_BSRN = 3, ESR_ARCH_RFDN_PRUNED = 4 };
+enum { ESR_ARCH_IMDN = 0, ESR_ARCH_RFDN = 1, ESR_ARCH_RLFN = 2, ESR_ARCH_BSRN = 3, ESR_ARCH_RFDN_PRUNED = 4, ESR_ARCH_FMEN = 5 };
 /* I/O + storage dtype of a forward call (math is fp32-accumulate in both) */
 enum { ESR_DTYPE_F32 = 0, ESR_DTYPE_F16 = 1 };
 enum {

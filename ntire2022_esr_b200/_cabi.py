@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libesr_b200.so")
 
-ARCH_IMDN, ARCH_RFDN, ARCH_RLFN, ARCH_BSRN, ARCH_RFDN_PRUNED = 0, 1, 2, 3, 4
+ARCH_IMDN, ARCH_RFDN, ARCH_RLFN, ARCH_BSRN, ARCH_RFDN_PRUNED, ARCH_FMEN = 0, 1, 2, 3, 4, 5
 DTYPE_F32, DTYPE_F16 = 0, 1
 OK, E_INVALID, E_STATE, E_WEIGHTS, E_CUDA, E_NOGPU = 0, -1, -2, -3, -4, -5
 

@@ -129,6 +129,32 @@ inline bool chain_pw_ok(const TcConv& c) {
   return n64 <= 2 && n16 <= 1 && col <= n;
 }
 
+// Is buffer `buf` (as written by op `writer`) read by any op after op index `from` before it is written again?
+// (Inputs, residual / gate operands of tensor-core groups and of the CUDA-core ops, the ESA operands.)
+inline bool chain_buffer_read_later(const Graph& g, size_t from, int buf) {
+  for (size_t k = from; k < g.ops.size(); ++k) {
+    const OpDecl& op = g.ops[k];
+    bool writes = false;
+    if (op.kind == OP_CONV_TC) {
+      const TcConv& c = g.tc[op.tc];
+      if (c.in == buf) return true;
+      for (auto& gd : c.groups) {
+        if (gd.res == buf) return true;
+        writes = writes || gd.out == buf;
+      }
+    } else {
+      if (op.in == buf || op.res == buf || op.c1 == buf || op.c3 == buf) return true;
+      writes = op.out == buf;
+    }
+    if (writes) return false;
+  }
+  return false;
+}
+
+// Longest chain the planner forms: validated on hardware up to this depth (three global row buffers for the halo
+// exchange, 16 of the 20 tensor maps); CH_MAX_LAYERS is the kernel's table size.
+constexpr int CH_CHAIN_CAP = 4;
+
 // Scans the op list for maximal runs of chainable layers where each layer feeds the next one.
 inline void find_chains(Graph& g) {
   g.chains.clear();
@@ -138,7 +164,7 @@ inline void find_chains(Graph& g) {
     ChainDecl ch;
     ch.first_op = (int)i;
     size_t j = i;
-    while (j < g.ops.size() && g.ops[j].kind == OP_CONV_TC && (int)ch.layers.size() < CH_MAX_LAYERS) {
+    while (j < g.ops.size() && g.ops[j].kind == OP_CONV_TC && (int)ch.layers.size() < CH_CHAIN_CAP) {
       const TcConv& c = g.tc[g.ops[j].tc];
       ChainLayerDecl d;
       d.tc = g.ops[j].tc;
@@ -149,12 +175,33 @@ inline void find_chains(Graph& g) {
         // the previous layer's group 0 must be exactly this layer's input, stored as plain NHWC, and its padded width
         // must cover this layer's K extent
         if (pg.mode != 0 || pg.out != c.in || pg.out_coff != c.chunk_c0[0] || d.ksteps * 16 > 64) break;
-        if (ch.layers.back().n1 > 0 && 0) break;
+        // a chain never writes a buffer one of its earlier layers reads as residual / gate operand, nor its own input
+        // (the bands of a chain run at different paces)
+        const TcGroupDecl& og = c.groups[0];
+        auto overlaps = [&](int buf, int c0, int n) { return buf == og.out && c0 < og.out_coff + og.ncols && og.out_coff < c0 + n; };
+        const TcConv& first = g.tc[ch.layers[0].tc];
+        bool clash = overlaps(first.in, first.chunk_c0[0], 64);
+        for (auto& dl : ch.layers)
+          for (auto& gd : g.tc[dl.tc].groups) clash = clash || (gd.res != BUF_NONE && overlaps(gd.res, gd.res_coff, gd.ncols));
+        if (clash) break;
       }
       ch.layers.push_back(d);
       ++j;
       // a layer whose group 0 is the pixel-shuffle store, or that has two stored groups at the end, closes the chain
       if (c.groups[0].mode != 0) break;
+      // ... and so does a layer whose output somebody other than the next layer reads later (FMEN: the input of a
+      // high-frequency attention block is also its gate): only the last layer of a chain stores every row
+      {
+        const int ob = c.groups[0].out;                                       // (j is already the next op)
+        bool other_reader = false, rewritten = false;
+        if (j < g.ops.size() && g.ops[j].kind == OP_CONV_TC) {                // the next layer may read it as its input only
+          for (auto& gd : g.tc[g.ops[j].tc].groups) {
+            other_reader = other_reader || gd.res == ob;
+            rewritten = rewritten || gd.out == ob;
+          }
+        }
+        if (other_reader || (!rewritten && chain_buffer_read_later(g, j + 1, ob))) break;
+      }
     }
     // the last layer of a chain stores group 0 itself: it must be its only group
     while (!ch.layers.empty() && g.tc[ch.layers.back().tc].groups.size() != 1) ch.layers.pop_back();

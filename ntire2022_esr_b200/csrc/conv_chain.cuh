@@ -110,7 +110,7 @@ struct ChPw {
 struct ChainParams {
   int32_t B, H, W, n_layers;
   int32_t strips, nbands, n_items;     // item = one band of one image (all strips = one cluster)
-  int32_t ring_off, w_off, ctr_off, ident_off, stage_off, stage_bytes;
+  int32_t ring_off, w_off, ctr_off, ident_off, stage_off, stage_bytes, ident_bytes;
   int32_t tmem_cols, ctr_acc_col;      // consecutive layers of different width use disjoint accumulator regions: the
                                        // per-row "accumulator drained" hand-over only holds between equal layouts
   int32_t store_all;                   // debug: every ring row also goes to global memory
@@ -353,8 +353,9 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (elect_one()) {
-      mbar_arrive_expect_tx(&ident_bar, (uint32_t)CH_IDENT_BYTES);     // constant: does not depend on the previous kernel
-      bulk_load_1d(smem + p.ident_off, p.ident, (uint32_t)CH_IDENT_BYTES, &ident_bar);
+      // the identity block (constant: does not depend on the previous kernel) - only chains with a block residual have it
+      mbar_arrive_expect_tx(&ident_bar, (uint32_t)p.ident_bytes);
+      if (p.ident_bytes > 0) bulk_load_1d(smem + p.ident_off, p.ident, (uint32_t)p.ident_bytes, &ident_bar);
       griddep_wait();
       uint32_t g = 0, ctr_cnt = 0, ring_cnt = 0, items = 0;
       for (int item = (int)cid; item < n_items; ++items, item = next_item(items)) {

@@ -197,7 +197,7 @@ __device__ __forceinline__ void tc_epi_math16(const uint32_t (&v)[16], const flo
       rv[2 * j] = a.x; rv[2 * j + 1] = a.y; rv[8 + 2 * j] = c.x; rv[8 + 2 * j + 1] = c.y;
     }
   }
-  if (!res_after) {
+  if (res_after == 0) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) f[j] += rv[j];
   }
@@ -207,7 +207,10 @@ __device__ __forceinline__ void tc_epi_math16(const uint32_t (&v)[16], const flo
 #pragma unroll
     for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], f[j] * slope);
   }
-  if (res_after) {
+  if (res_after == 2) {          // gate: sigmoid(v) * res (FMEN's high-frequency attention, team03_fmen.py:72-74)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] = rv[j] * __fdividef(1.f, 1.f + __expf(-f[j]));
+  } else if (res_after) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) f[j] += rv[j];
   }

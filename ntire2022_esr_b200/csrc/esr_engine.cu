@@ -19,7 +19,7 @@
 
 namespace esr {
 
-static const int kNumArch = 5;
+static const int kNumArch = 6;
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -138,6 +138,7 @@ static std::string build_dev_graph(Engine& e, int gid) {
     case ESR_ARCH_RLFN: gb.build_rlfn(e.nf, e.nblocks, tc); break;
     case ESR_ARCH_IMDN: gb.build_imdn(e.nf, e.nblocks, tc); break;
     case ESR_ARCH_BSRN: gb.build_bsrn(e.nf, e.nblocks, tc); break;
+    case ESR_ARCH_FMEN: gb.build_fmen(e.nf, e.nblocks, tc); break;
     default: return "unknown architecture";
   }
   if (!gb.wts.err.empty()) return gb.wts.err;
@@ -660,8 +661,13 @@ static int plan_chain(Engine* e, const DevGraph& dg, const ChainDecl& ch, const 
   p.ring_off = 0;
   p.w_off = CH_SLOTS * CH_SLOT_BYTES;
   p.ctr_off = p.w_off + CH_W_BYTES;
-  p.ident_off = p.ctr_off + CH_CTR_BYTES;
-  p.stage_off = p.ident_off + CH_IDENT_BYTES;
+  // the centre block and the identity block only exist in chains that use them (an IMDB / FMEN chain whose last layer
+  // stages 64 columns needs the room)
+  bool any_ctr_blk = false, any_ident = false;
+  for (int l = 0; l < nL; ++l) { any_ctr_blk = any_ctr_blk || ch.layers[l].ctr_n > 0; any_ident = any_ident || ch.layers[l].res_smem != 0; }
+  p.ident_off = p.ctr_off + (any_ctr_blk ? CH_CTR_BYTES : 0);
+  p.ident_bytes = any_ident ? CH_IDENT_BYTES : 0;
+  p.stage_off = p.ident_off + p.ident_bytes;
   p.ident = dg.d_ident;
   p.stage_bytes = (TC_TILE_PX * std::max(stage_cols, 16) * 2 + 1023) / 1024 * 1024;
   const size_t smem = (size_t)p.stage_off + 2 * (size_t)p.stage_bytes + 1024;
@@ -983,7 +989,7 @@ static int build_plan(Engine* e, Plan& pl) {
 static int check_shape(Engine* e, int B, int H, int W, int dtype) {
   if (B < 1 || H < 1 || W < 1) return fail(e, ESR_E_INVALID, "B, H, W must be positive");
   if (dtype != ESR_DTYPE_F32 && dtype != ESR_DTYPE_F16) return fail(e, ESR_E_INVALID, "unknown dtype");
-  if (e->arch != ESR_ARCH_IMDN) {   // every other network has an ESA branch
+  if (e->arch != ESR_ARCH_IMDN && e->arch != ESR_ARCH_FMEN) {   // every other network has an ESA branch
     int H2, W2, H3, W3;
     esa_dims(H, W, H2, W2, H3, W3);
     if (H2 < 7 || W2 < 7 || H < 3 || W < 3)
@@ -1067,14 +1073,15 @@ int esr_create(esr_handle** out, int arch, int nf, int nblocks, int device) {
   if (arch < 0 || arch >= kNumArch) return ESR_E_INVALID;
   esr_engine* e = new esr_engine();
   e->arch = arch;
-  static const int def_nf[kNumArch] = {64, 50, 46, 48, 40}, def_nb[kNumArch] = {8, 4, 4, 5, 4};
+  static const int def_nf[kNumArch] = {64, 50, 46, 48, 40, 50}, def_nb[kNumArch] = {8, 4, 4, 5, 4, 4};
   e->nf = nf > 0 ? nf : def_nf[arch];
   e->nblocks = nblocks > 0 ? nblocks : def_nb[arch];
   const bool ok_cfg = (arch == ESR_ARCH_IMDN && e->nf == 64 && e->nblocks <= 16) ||
                       ((arch == ESR_ARCH_RFDN || arch == ESR_ARCH_RFDN_PRUNED) && e->nf >= 16 && e->nf <= 64 && e->nf % 4 == 0 &&
                        e->nblocks <= 4) ||
                       (arch == ESR_ARCH_RLFN && e->nf >= 16 && e->nf <= 48 && e->nblocks <= 8) ||
-                      (arch == ESR_ARCH_BSRN && e->nf == 48 && e->nblocks <= 5);
+                      (arch == ESR_ARCH_BSRN && e->nf == 48 && e->nblocks <= 5) ||
+                      (arch == ESR_ARCH_FMEN && e->nf >= 16 && e->nf <= 64 && e->nblocks <= 8);
   if (!ok_cfg && !(arch == ESR_ARCH_RFDN && e->nf == 50)) {
     delete e;
     return ESR_E_INVALID;

@@ -752,6 +752,91 @@ struct GraphBuilder {
   }
 
   // =============================================================================================
+  // FMEN (models/team03_fmen.py:78-134; model id 3): 3x3 convolutions only.  head; warm-up conv + HFAB (two basic
+  // blocks, 12 channels); nblocks x [BasicBlock(nf), HFAB(one basic block, 16 channels)]; lr_conv + head; tail conv +
+  // PixelShuffle(4).  An HFAB gates its own input: out = sigmoid(excitate(...)) * x (res_after = 2 in the epilogues),
+  // so the buffer holding x (`gate`) must reach global memory in full - the chain planner ends a chain there.
+  // =============================================================================================
+  void build_fmen(int nf, int nblocks, bool tc) {
+    const float sl = 0.1f;
+    // Range management.  The reference runs FMEN in fp32 at data range 255; inside an HFAB the activations reach
+    // 2e5 (5e7 in the warm-up HFAB) - far beyond fp16.  Convolution + bias + LeakyReLU is positively homogeneous, so the
+    // trunk runs at scale S_T (biases scaled, the head's weights scaled once), the warm-up HFAB's inner path at an
+    // extra S_H0 (its squeeze weights scaled), and the two places that are NOT homogeneous undo the scale exactly
+    // where they need the true value: the excitate convolution in front of the sigmoid (weights / (S_T * S_H)) and
+    // the tail convolution (weights / S_T).  All scales are powers of two: in fp32 mode the result is unchanged.
+    const double S_T = 1.0 / 1024.0, S_H0 = 1.0 / 16.0;
+    // two gate buffers, alternating: a fused chain must never write the buffer one of its own layers still reads as
+    // its gate (the bands of a chain run at different paces)
+    const int fea = buf(BK_FULL, 64), gate_a = buf(BK_FULL, 64), gate_b = buf(BK_FULL, 64), ta = buf(BK_FULL, 64),
+              tb = buf(BK_FULL, 64), ha = buf(BK_FULL, 64), hb = buf(BK_FULL, 64);
+    auto scaled = [](Mat m, double ws, double bs) {
+      for (auto& v : m.w) v *= ws;
+      for (auto& v : m.b) v *= bs;
+      return m;
+    };
+    {
+      OpDecl op;
+      op.kind = OP_HEAD;
+      op.name = "head";
+      op.in = BUF_IN; op.out = fea;
+      const Mat m = scaled(conv_mat("head", nf, 3, 3), S_T, S_T);
+      const int ti = new_table(1, 32, 64);
+      for (int o = 0; o < nf; ++o) {
+        tables[ti].b[o] = (float)m.b[o];
+        for (int ci = 0; ci < 3; ++ci)
+          for (int tp = 0; tp < 9; ++tp) tables[ti].w[(size_t)(tp * 3 + ci) * 64 + o] = (float)m.at(o, ci, tp);
+      }
+      op.tab = ti;
+      op.macs_pp = 27.0 * nf;
+      g.ops.push_back(op);
+    }
+    // one 3x3 convolution: in -> out, weights * ws, bias * bs, optional LeakyReLU(0.1), optional operand (rmode 0: added
+    // before the activation, 2: multiplied with the sigmoid of the result), optional pixel-shuffle store
+    auto conv3 = [&](const std::string& name, int O, int I, int in, int out, bool lrelu, double ws, double bs,
+                     int res = BUF_NONE, int rmode = 0, bool ps = false) {
+      const Mat m = scaled(conv_mat(name, O, I, 3), ws, bs);
+      const int act = lrelu ? ACT_LRELU : ACT_NONE;
+      if (!tc) {
+        OpDecl& o = conv_op(name, dense_table(m, 64, ps ? 48 : 64, pos_id(), pos_id()), in, 0, ps ? BUF_OUT : out, 0, act, sl);
+        if (res != BUF_NONE) { o.res = res; o.res_coff = 0; o.res_after = rmode; }
+        o.ps = ps;
+      } else {
+        const int N = (O + 15) / 16 * 16;
+        TcBuild b = tc_begin(1, N, {{0, N}});
+        tc_add(b, m, pos_id(), pos_id());
+        tc_emit(name, b, in, 0, 1, {tc_group(0, N, act, sl, ps ? BUF_OUT : out, 0, res, 0, rmode, ps ? 1 : 0)});
+      }
+    };
+    // HFAB (team03_fmen.py:68-75): x lives in `gate` (trunk scale); inner path at S_T * sh; result into `dst` (trunk scale)
+    auto hfab = [&](const std::string& p, int up, int mid, int gate, int dst, double sh) {
+      conv3(p + "squeeze", mid, nf, gate, ta, true, sh, S_T * sh);
+      int cur = ta, oth = tb;
+      for (int k = 0; k < up; ++k) {
+        const std::string q = p + "convs." + std::to_string(k) + ".";
+        conv3(q + "conv1.rep_conv", mid, mid, cur, oth, true, 1.0, S_T * sh);
+        // the LeakyReLU behind `convs` applies to the last basic block's second convolution only
+        conv3(q + "conv2.rep_conv", mid, mid, oth, cur, k == up - 1, 1.0, S_T * sh);
+      }
+      conv3(p + "excitate", nf, mid, cur, dst, false, 1.0 / (S_T * sh), 1.0, gate, 2);
+    };
+    conv3("warmup.0", nf, nf, fea, gate_a, false, 1.0, S_T);
+    hfab("warmup.1.", 2, 12, gate_a, ha, S_H0);
+    int h = ha;
+    for (int i = 0; i < nblocks; ++i) {
+      const std::string p = "basic_blocks." + std::to_string(i) + ".";
+      const int gate = (i & 1) ? gate_a : gate_b;
+      conv3(p + "conv1.rep_conv", nf, nf, h, ta, true, 1.0, S_T);
+      conv3(p + "conv2.rep_conv", nf, nf, ta, gate, false, 1.0, S_T);
+      const int hn = h == ha ? hb : ha;
+      hfab("hfabs." + std::to_string(i) + ".", 1, 16, gate, hn, 1.0);
+      h = hn;
+    }
+    conv3("lr_conv", nf, nf, h, ta, false, 1.0, S_T, fea, 0);
+    conv3("tail.0", 48, nf, ta, BUF_OUT, false, 1.0 / S_T, 1.0, BUF_NONE, 0, true);
+  }
+
+  // =============================================================================================
   // IMDN (nc 64, d_nc 16, r_nc 48).  Output channels of conv1..3 are permuted to [r(48) | d(16)]
   // so the next conv reads a contiguous K = 48.
   // =============================================================================================

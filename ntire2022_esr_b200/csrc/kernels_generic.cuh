@@ -46,6 +46,8 @@ __device__ __forceinline__ double apply_act(double v, int act, float slope) {
   }
 }
 __device__ __forceinline__ float sigmoid_acc(float z) { return 1.f / (1.f + expf(-z)); }
+__device__ __forceinline__ float sigmoid_gate(float z) { return 1.f / (1.f + expf(-z)); }
+__device__ __forceinline__ double sigmoid_gate(double z) { return 1.0 / (1.0 + exp(-z)); }
 __device__ __forceinline__ double sigmoid_acc(double z) { return 1.0 / (1.0 + exp(-z)); }
 
 // ---- 8-channel vector load/store helpers ------------------------------------------------------
@@ -249,7 +251,7 @@ __global__ void __launch_bounds__(128) k_bsrn_head(const TIn* __restrict__ in, T
 //   w:    [taps][cin8][cout16] fp32 (cin8 = Cin rounded up to 8, cout16 = columns rounded to 16;
 //         rows/columns beyond the logical extent are zero)
 //   out:  NHWC (16 columns of the group are stored) or pixel-shuffle x4 NCHW
-// residual is added before (res_after=0) or after (res_after=1) the activation.
+// residual is added before (res_after=0) or after (res_after=1) the activation; res_after=2: out = sigmoid(act(v)) * res.
 // ---------------------------------------------------------------------------------------------
 struct ConvGenericParams {
   const void* in; int in_stride, in_coff, cin8;
@@ -332,7 +334,8 @@ __global__ void __launch_bounds__(128) k_conv_generic(const ConvGenericParams p)
     TAcc v = acc[j];
     if (!p.res_after) v += (TAcc)rv[j];
     v = apply_act(v, p.act, p.slope);
-    if (p.res_after) v += (TAcc)rv[j];
+    if (p.res_after == 2) v = (TAcc)rv[j] * sigmoid_gate(v);      // gate: sigmoid(v) * res
+    else if (p.res_after) v += (TAcc)rv[j];
     o16[j] = (float)v;
   }
   if (!p.ps_mode) {
@@ -449,7 +452,8 @@ __global__ void __launch_bounds__(128) k_conv16(const ConvGenericParams p) {
       TAcc v = acc[h][j];
       if (p.res != nullptr && !p.res_after) v += (TAcc)rv[j];
       v = apply_act(v, p.act, p.slope);
-      if (p.res != nullptr && p.res_after) v += (TAcc)rv[j];
+      if (p.res != nullptr && p.res_after == 2) v = (TAcc)rv[j] * sigmoid_gate(v);
+      else if (p.res != nullptr && p.res_after) v += (TAcc)rv[j];
       o8[j] = (float)v;
     }
     store8(reinterpret_cast<TOut*>(p.out) + pix * p.out_stride + p.out_coff + g8 * 8, o8);

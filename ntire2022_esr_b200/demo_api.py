@@ -24,7 +24,7 @@ MODEL_ZOO_ENV = "ESR_MODEL_ZOO"
 class B200SRModel(nn.Module):
     """nn.Module facade over an esr_b200 `Engine`.
 
-    arch in {'imdn','rfdn','rlfn','bsrn','rfdn_pruned'}; nf / nblocks follow the reference constructors
+    arch in {'imdn','rfdn','rlfn','bsrn','rfdn_pruned','fmen'}; nf / nblocks follow the reference constructors
     (IMDN(nc=64, nb=8), RFDN(nf=50, 4 blocks), RLFN_cut(46), BSRN(num_feat=48, num_block=5), pruned RFDN(nf=40)).
     """
 
@@ -33,7 +33,7 @@ class B200SRModel(nn.Module):
         if arch not in specs.SPECS:
             raise NotImplementedError(f"architecture {arch!r} is not implemented")
         self.arch = arch
-        defaults = {"imdn": (64, 8), "rfdn": (50, 4), "rlfn": (46, 4), "bsrn": (48, 5), "rfdn_pruned": (40, 4)}[arch]
+        defaults = {"imdn": (64, 8), "rfdn": (50, 4), "rlfn": (46, 4), "bsrn": (48, 5), "rfdn_pruned": (40, 4), "fmen": (50, 4)}[arch]
         self.nf = nf or defaults[0]
         self.nblocks = nblocks or defaults[1]
         self._spec = specs.SPECS[arch](self.nf, self.nblocks)
@@ -128,7 +128,7 @@ def build_model(model_id: int, state_dict=None) -> B200SRModel:
 
 
 def select_model(args, device):
-    """test_demo.select_model for the accelerated ids (-1 IMDN, 0 RFDN, 4 RLFN, 18 BSRN, 22 RFDN40, 26 IMDN nb=7,
+    """test_demo.select_model for the accelerated ids (-1 IMDN, 0 RFDN, 3 FMEN, 4 RLFN, 18 BSRN, 22 RFDN40, 26 IMDN nb=7,
     40 pruned RFDN)."""
     model_id = args.model_id
     if model_id in specs.REGISTRY:

@@ -15,7 +15,7 @@ from . import _cabi
 from ._cabi import EsrError, lib
 
 ARCHS = {"imdn": _cabi.ARCH_IMDN, "rfdn": _cabi.ARCH_RFDN, "rlfn": _cabi.ARCH_RLFN, "bsrn": _cabi.ARCH_BSRN,
-         "rfdn_pruned": _cabi.ARCH_RFDN_PRUNED}
+         "rfdn_pruned": _cabi.ARCH_RFDN_PRUNED, "fmen": _cabi.ARCH_FMEN}
 
 
 def _as_f32_numpy(v) -> np.ndarray:

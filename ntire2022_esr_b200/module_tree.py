@@ -12,7 +12,7 @@ numbers for the drop-in (tests/test_host_cpu.py pins them to values produced by 
 
 Reference graphs: models/rfdn_baseline/{RFDN.py:29-41, block.py:117-129,148-166}, models/imdn_baseline.py:46-65 +
 models/basicblock.py:259-265, models/team04_rlfn.py:76-152, models/team18_bsrn.py:82-236,
-models/team22_rep_rfdn.py:87-165, models/team40_rfdn_pruned.py:103-213.
+models/team22_rep_rfdn.py:87-165, models/team40_rfdn_pruned.py:103-213, models/team03_fmen.py:10-134.
 """
 from __future__ import annotations
 
@@ -50,6 +50,12 @@ def _act_modules(arch: str, nb: int) -> Dict[str, nn.Module]:
         for b in range(nb):
             for c in (1, 2, 3):
                 acts[f"model.1.sub.{b}.conv{c}.1"] = nn.LeakyReLU(0.05, inplace=True)
+    elif arch == "fmen":
+        # FMEN's LeakyReLU(0.1) is a module-level global, not a sub-module (team03_fmen.py:6-7): model_summary never sees
+        # it.  The HFABs own an nn.Sigmoid (team03_fmen.py:66), which carries no hooks either but is part of .modules()
+        acts["warmup.1.sigmoid"] = nn.Sigmoid()
+        for b in range(nb):
+            acts[f"hfabs.{b}.sigmoid"] = nn.Sigmoid()
     return acts
 
 
@@ -187,6 +193,27 @@ def _trace_bsrn(nf: int, nb: int, f: int, B: int, H: int, W: int) -> Iterator[Ca
     yield "upsampler.upsampleOneStep.0", nchw(nf), nchw(48)
 
 
+def _trace_fmen(nf: int, nb: int, B: int, H: int, W: int) -> Iterator[Call]:
+    full = lambda c: (B, c, H, W)
+
+    def hfab(p, up, mid):                                    # team03_fmen.py:68-75
+        yield p + "squeeze", full(nf), full(mid)
+        for k in range(up):
+            yield p + f"convs.{k}.conv1.rep_conv", full(mid), full(mid)
+            yield p + f"convs.{k}.conv2.rep_conv", full(mid), full(mid)
+        yield p + "excitate", full(mid), full(nf)
+
+    yield "head", full(3), full(nf)                          # team03_fmen.py:121-134
+    yield "warmup.0", full(nf), full(nf)
+    yield from hfab("warmup.1.", 2, 12)
+    for i in range(nb):
+        yield f"basic_blocks.{i}.conv1.rep_conv", full(nf), full(nf)
+        yield f"basic_blocks.{i}.conv2.rep_conv", full(nf), full(nf)
+        yield from hfab(f"hfabs.{i}.", 1, 16)
+    yield "lr_conv", full(nf), full(nf)
+    yield "tail.0", full(nf), full(48)
+
+
 def trace(arch: str, nf: int, nb: int, esa_f: int, B: int, H: int, W: int) -> List[Call]:
     if arch in ("rfdn", "rfdn_pruned"):
         return list(_trace_rfdn(nf, nb, esa_f, B, H, W))
@@ -196,6 +223,8 @@ def trace(arch: str, nf: int, nb: int, esa_f: int, B: int, H: int, W: int) -> Li
         return list(_trace_imdn(nf, nb, B, H, W))
     if arch == "bsrn":
         return list(_trace_bsrn(nf, nb, esa_f, B, H, W))
+    if arch == "fmen":
+        return list(_trace_fmen(nf, nb, B, H, W))
     raise NotImplementedError(arch)
 
 

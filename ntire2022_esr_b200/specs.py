@@ -123,13 +123,42 @@ def rfdn_pruned_spec(nf=40, nb=4):
     return rfdn_spec(nf, nb, f=12)
 
 
-SPECS = {"imdn": imdn_spec, "rfdn": rfdn_spec, "rlfn": rlfn_spec, "bsrn": bsrn_spec, "rfdn_pruned": rfdn_pruned_spec}
+def fmen_spec(nf=50, nb=4):
+    """models/team03_fmen.py:83-118: head, warm-up conv + HFAB(two basic blocks, 12 channels), nb x [BasicBlock(nf),
+    HFAB(one basic block, 16 channels)], lr_conv, tail conv in front of PixelShuffle(4).  Every convolution is 3x3."""
+    d = OrderedDict()
+
+    def hfab(p, up, mid):
+        _conv(d, p + "squeeze", mid, nf, 3)
+        for k in range(up):
+            _conv(d, p + f"convs.{k}.conv1.rep_conv", mid, mid, 3)
+            _conv(d, p + f"convs.{k}.conv2.rep_conv", mid, mid, 3)
+        _conv(d, p + "excitate", nf, mid, 3)
+
+    _conv(d, "head", nf, 3, 3)
+    _conv(d, "warmup.0", nf, nf, 3)
+    hfab("warmup.1.", 2, 12)
+    for i in range(nb):
+        _conv(d, f"basic_blocks.{i}.conv1.rep_conv", nf, nf, 3)
+        _conv(d, f"basic_blocks.{i}.conv2.rep_conv", nf, nf, 3)
+    for i in range(nb):
+        hfab(f"hfabs.{i}.", 1, 16)
+    _conv(d, "lr_conv", nf, nf, 3)
+    _conv(d, "tail.0", 48, nf, 3)
+    return d
+
+
+SPECS = {"imdn": imdn_spec, "rfdn": rfdn_spec, "rlfn": rlfn_spec, "bsrn": bsrn_spec, "rfdn_pruned": rfdn_pruned_spec,
+         "fmen": fmen_spec}
 
 # model registry: id -> (arch, ctor kwargs, checkpoint file, state-dict wrapper key, name, data_range)
-# (test_demo.py:17-23 IMDN, :24-30 RFDN, :52-58 RLFN, :150-157 BSRN, :175-181 RFDN40, :203-209 IMDN nb=7, :302-308 pruned RFDN)
+# (test_demo.py:17-23 IMDN, :24-30 RFDN, :45-51 FMEN, :52-58 RLFN, :150-157 BSRN, :175-181 RFDN40, :203-209 IMDN nb=7, :302-308 pruned RFDN)
 REGISTRY: Dict[int, dict] = {
     -1: dict(arch="imdn", kwargs=dict(nf=64, nblocks=8), file="imdn_baseline.pth", wrap=None,
              name="IMDN_baseline", data_range=1.0),
+    # FMEN (models/team03_fmen.py:78-134, test_demo.py:45-51)
+    3: dict(arch="fmen", kwargs=dict(nf=50, nblocks=4), file="team03_fmen.pth", wrap=None,
+            name="FMEN", data_range=255.0),
     0: dict(arch="rfdn", kwargs=dict(nf=50, nblocks=4), file="rfdn_baseline.pth", wrap=None,
             name="RFDN_baseline", data_range=255.0),
     4: dict(arch="rlfn", kwargs=dict(nf=46, nblocks=4), file="team04_rlfn.pth", wrap=None,

@@ -315,9 +315,44 @@ def bsrn_forward(weights, x, dtype=np.float32):
 
 
 # ------------------------------------------------------------------------------------------------
+# FMEN  (models/team03_fmen.py:10-134; model id 3, test_demo.py:45-51): 3x3 convolutions only, LeakyReLU(0.1),
+# high-frequency attention blocks that gate their input with a sigmoid
+# ------------------------------------------------------------------------------------------------
+def _fmen_basic(wt, p, x):
+    """BasicBlock.forward, team03_fmen.py:37-42: RepConv - LeakyReLU(0.1) - RepConv"""
+    return _conv(wt, p + "conv2.rep_conv", leaky_relu(_conv(wt, p + "conv1.rep_conv", x, padding=1), 0.1), padding=1)
+
+
+def _fmen_hfab(wt, p, x):
+    """HFAB.forward, team03_fmen.py:68-75"""
+    out = leaky_relu(_conv(wt, p + "squeeze", x, padding=1), 0.1)
+    k = 0
+    while p + f"convs.{k}.conv1.rep_conv.weight" in wt:
+        out = _fmen_basic(wt, p + f"convs.{k}.", out)
+        k += 1
+    out = leaky_relu(out, 0.1)
+    return sigmoid(_conv(wt, p + "excitate", out, padding=1)) * x
+
+
+def fmen_forward(weights, x, dtype=np.float32):
+    """FMEN.forward, team03_fmen.py:121-134 (n_feats 50, four down blocks, warm-up HFAB with two basic blocks)."""
+    wt = _cast(weights, dtype)
+    x = _conv(wt, "head", np.asarray(x, dtype=dtype), padding=1)
+    h = _fmen_hfab(wt, "warmup.1.", _conv(wt, "warmup.0", x, padding=1))
+    i = 0
+    while f"basic_blocks.{i}.conv1.rep_conv.weight" in wt:
+        h = _fmen_hfab(wt, f"hfabs.{i}.", _fmen_basic(wt, f"basic_blocks.{i}.", h))
+        i += 1
+    h = _conv(wt, "lr_conv", h, padding=1) + x
+    return pixel_shuffle(_conv(wt, "tail.0", h, padding=1), 4)
+
+
+# ------------------------------------------------------------------------------------------------
 # registry mirroring test_demo.select_model (test_demo.py:13-30,52-58,150-157)
 # ------------------------------------------------------------------------------------------------
 MODELS = {
+    # id 3: FMEN (test_demo.py:45-51)
+    3: dict(arch="fmen", name="03_FMEN", data_range=255.0, weights="team03_fmen", fn=fmen_forward),
     -1: dict(arch="imdn", name="-1_IMDN_baseline", data_range=1.0, weights="imdn_baseline", fn=imdn_forward),
     0: dict(arch="rfdn", name="00_RFDN_baseline", data_range=255.0, weights="rfdn_baseline", fn=rfdn_forward),
     4: dict(arch="rlfn", name="04_RLFN", data_range=255.0, weights="team04_rlfn", fn=rlfn_forward),
@@ -330,7 +365,7 @@ MODELS = {
     40: dict(arch="rfdn_pruned", name="40_RFDNPrune", data_range=255.0, weights="team40_rfdn_pruned", fn=rfdn_pruned_forward),
 }
 FORWARD = {"imdn": imdn_forward, "rfdn": rfdn_forward, "rlfn": rlfn_forward, "bsrn": bsrn_forward,
-           "rfdn_pruned": rfdn_pruned_forward}
+           "rfdn_pruned": rfdn_pruned_forward, "fmen": fmen_forward}
 
 
 def forward(arch, weights, x, dtype=np.float32):

@@ -125,8 +125,30 @@ def bsrn_forward(w, x):
     return F.pixel_shuffle(_conv(w, "upsampler.upsampleOneStep.0", out_lr, padding=1), 4)
 
 
+def fmen_forward(w, x):
+    """models/team03_fmen.py:37-42 (BasicBlock), :68-75 (HFAB), :121-134 (FMEN)"""
+    a = lambda t: F.leaky_relu(t, 0.1)
+    basic = lambda p, t: _conv(w, p + "conv2.rep_conv", a(_conv(w, p + "conv1.rep_conv", t, padding=1)), padding=1)
+
+    def hfab(p, t):
+        out = a(_conv(w, p + "squeeze", t, padding=1))
+        k = 0
+        while p + f"convs.{k}.conv1.rep_conv.weight" in w:
+            out = basic(p + f"convs.{k}.", out)
+            k += 1
+        return torch.sigmoid(_conv(w, p + "excitate", a(out), padding=1)) * t
+
+    x = _conv(w, "head", x, padding=1)
+    h = hfab("warmup.1.", _conv(w, "warmup.0", x, padding=1))
+    i = 0
+    while f"basic_blocks.{i}.conv1.rep_conv.weight" in w:
+        h = hfab(f"hfabs.{i}.", basic(f"basic_blocks.{i}.", h))
+        i += 1
+    return F.pixel_shuffle(_conv(w, "tail.0", _conv(w, "lr_conv", h, padding=1) + x, padding=1), 4)
+
+
 FORWARD = {"imdn": imdn_forward, "rfdn": rfdn_forward, "rlfn": rlfn_forward, "bsrn": bsrn_forward,
-           "rfdn_pruned": lambda w, x: rfdn_forward(w, x, residual=False)}
+           "rfdn_pruned": lambda w, x: rfdn_forward(w, x, residual=False), "fmen": fmen_forward}
 
 
 def forward(arch, weights, x, dtype=torch.float32):

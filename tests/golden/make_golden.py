@@ -46,7 +46,7 @@ torch.set_num_threads(os.cpu_count())
 MODELS = {-1: ("imdn", "imdn_baseline.pth"), 0: ("rfdn", "rfdn_baseline.pth"),
           4: ("rlfn", "team04_rlfn.pth"), 18: ("bsrn", "team18_bsrn.pth"),
           22: ("rfdn40", "team22_rep_rfdn.pth"), 40: ("rfdn_pruned", "team40_rfdn_pruned.pth"),
-          26: ("imdn_nb7", "team26_imdn_nb7.pth")}   # id 22 = RFDN at nf = 40 (test_demo.py:175-181): same graph, SURVEY row N1
+          26: ("imdn_nb7", "team26_imdn_nb7.pth"), 3: ("fmen", "team03_fmen.pth")}   # id 22 = RFDN at nf = 40 (test_demo.py:175-181): same graph, SURVEY row N1
 SMALL_SIZES = [(15, 15), (24, 20), (33, 47), (64, 64)]
 CROPS = [(0, 0), (0, 992), (992, 0), (992, 992), (500, 500), (0, 480), (700, 0), (301, 777)]
 SHAPED = {0: (339, 510), 18: (270, 480)}   # model id -> LR shape of its BASELINE.json config

@@ -197,7 +197,7 @@ def test_uint8_entry_points_refuse_without_a_gpu():
 REFERENCE_SUMMARY = {
     -1: (154140672, 43, 58531512320, 893936), 0: (112034240, 64, 27102622560, 433448), 4: (80045184, 39, 19695306752, 317218),
     18: (65757744, 43, 2022422883, 156288), 22: (90500128, 64, 17613787280, 282688), 26: (136314880, 38, 51757711360, 790496),
-    40: (91718080, 64, 17700828000, 289888),
+    40: (91718080, 64, 17700828000, 289888), 3: (72089600, 34, 22280011776, 341066),
 }
 
 
@@ -259,3 +259,31 @@ def test_model_summary_hooks_see_the_reference_layers(mid, monkeypatch):
             sys.path.remove("/root/reference")
         assert get_model_activation(m, (3, 256, 256)) == want[:2]
         assert get_model_flops(m, (3, 256, 256), False) == want[2]
+
+
+def test_fmen_loads_strictly_and_the_chain_planner_keeps_the_gate_operands_in_global_memory():
+    """SURVEY row N1, FMEN (id 3, models/team03_fmen.py:78-134): 34 3x3 convolutions.  An HFAB multiplies its own input
+    with the sigmoid of its last convolution, so the buffer holding that input must be complete in global memory when
+    the gate layer's epilogue reads it: the planner ends a fused chain at the layer that produces it, never lets a chain
+    write a buffer one of its own layers still reads, and plans at most four layers per launch."""
+    from ntire2022_esr_b200 import Engine, EsrError, _cabi, build_model
+
+    w = _weights(3)
+    m = build_model(3, state_dict=w)
+    assert set(m.state_dict()) == set(w) and sum(p.numel() for p in m.parameters()) == 341066
+    with pytest.raises(RuntimeError):
+        m.load_state_dict({k: v for k, v in m.state_dict().items() if k != "lr_conv.bias"}, strict=True)
+    e = Engine("fmen", device=-1)
+    e.load_state_dict(w)
+    n16 = e.launch_names(1, 64, 64, _cabi.DTYPE_F16)
+    chains = [n[len("conv_chain:"):].split(" | ") for n in n16 if n.startswith("conv_chain")]
+    assert n16[1] == "head:head" and n16[2] == "conv_tc:warmup.0"           # warm-up conv: its output is HFAB 0's gate
+    assert all(2 <= len(c) <= 4 for c in chains) and sum(len(c) for c in chains) + 1 == 33   # every conv but the head
+    assert chains[-1] == ["lr_conv", "tail.0"]
+    for c in chains:                                                      # a gate producer is always the last layer of its launch
+        for name in c[:-1]:
+            assert not (name.startswith("basic_blocks.") and name.endswith("conv2.rep_conv")), c
+    assert len(e.launch_names(1, 64, 64, _cabi.DTYPE_F32)) == 34
+    e.workspace_bytes(1, 5, 7, _cabi.DTYPE_F16)                          # no ESA: no 15-pixel minimum
+    with pytest.raises(EsrError):
+        Engine("fmen", device=-1).load_state_dict({k: v for k, v in w.items() if k != "head.weight"})

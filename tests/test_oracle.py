@@ -8,7 +8,7 @@ import pytest
 from oracle import esr_oracle as O
 
 ARCHS = [(-1, "imdn"), (0, "rfdn"), (4, "rlfn"), (18, "bsrn")]
-GOLDEN = ARCHS + [(22, "rfdn40"), (40, "rfdn_pruned"), (26, "imdn_nb7")]   # (model id, golden file tag): RFDN at nf = 40, pruned RFDN, IMDN nb = 7
+GOLDEN = ARCHS + [(22, "rfdn40"), (40, "rfdn_pruned"), (26, "imdn_nb7"), (3, "fmen")]   # (model id, golden file tag): RFDN at nf = 40, pruned RFDN, IMDN nb = 7, FMEN
 
 
 def _weights(golden_dir, mid):

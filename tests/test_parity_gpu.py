@@ -18,13 +18,24 @@ from oracle import esr_oracle as O  # noqa: E402
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ARCHS = [(-1, "imdn"), (0, "rfdn"), (4, "rlfn"), (18, "bsrn")]
-GOLDEN = ARCHS + [(22, "rfdn40"), (40, "rfdn_pruned"), (26, "imdn_nb7")]   # (model id, golden file tag): SURVEY row N1 (RFDN at nf = 40, pruned RFDN, IMDN nb = 7)
+GOLDEN = ARCHS + [(22, "rfdn40"), (40, "rfdn_pruned"), (26, "imdn_nb7"), (3, "fmen")]   # (model id, golden file tag): SURVEY row N1 (RFDN at nf = 40, pruned RFDN, IMDN nb = 7, FMEN)
 FP32_BAR = 1e-5
 FP16_PSNR_BAR = 60.0
 # The pruned RFDN (id 40) has the widest dynamic range of the set (|out_lr| up to 3.9e3 on uniform noise at
 # data range 255, no inner residuals): uniform noise measures 59.1-60.7 dB on the tcgen05 path (61-62 dB on the
 # CUDA-core fp16 path, i.e. fp16 storage itself is the floor) and 78.3 dB on test.bmp.
 FP16_PSNR_BAR_BY_ID = {40: 58.0}
+# FMEN (id 3) on uniform noise leaves its operating range: the reference's own fp32 output reaches +-43 000 at data range 255
+# (it grows block after block: 4.6e4 in the trunk, 3.4e6 inside the last HFAB, 6.8e7 inside the warm-up HFAB; the engine
+# runs them at a 2^-10 / 2^-14 scale to stay inside fp16).  A PSNR against the data range says nothing there - every fp16
+# path, the CUDA-core one included, measures 24-44 dB on such draws and 64.8 dB on tame ones - so on NOISE inputs FMEN's
+# PSNR is taken against the reference output's own peak.  On test.bmp and its DIV2K-protocol pseudo pairs FMEN is held to
+# the same bars as every other network (72 dB against the data range, PSNR delta +4.5e-4 dB).
+NOISE_PEAK_FROM_OUTPUT = {3}
+
+
+def _noise_peak(mid, ref, dr):
+    return max(dr, float(np.abs(ref).max())) if mid in NOISE_PEAK_FROM_OUTPUT else dr
 
 
 def _weights(mid):
@@ -99,7 +110,7 @@ def test_fp16_tcgen05_path_vs_oracle(mid, arch):
         y = _run(mid, x)
         ref = O.forward(O.MODELS[mid]["arch"], w, x.astype(np.float32), dtype=np.float32)
         assert np.isfinite(y).all()
-        p = _psnr(y, ref, dr)
+        p = _psnr(y, ref, _noise_peak(mid, ref, dr))
         assert p >= FP16_PSNR_BAR_BY_ID.get(mid, FP16_PSNR_BAR), (arch, shape, p)
     names = _model(mid).engine(torch.device("cuda:0")).launch_names(1, 64, 64, 1)
     assert any(n.startswith(("conv_tc", "conv_chain")) for n in names)
@@ -421,13 +432,13 @@ def test_tcgen05_kernels_width_and_variant_sweep_vs_oracle(mid, arch):
                     eng.set_option(k, val)
                 y = eng.forward(xt).float().cpu().numpy()
                 assert np.isfinite(y).all(), (arch, (b, h, wd), v)
-                p = _psnr(y, ref, dr)
+                p = _psnr(y, ref, _noise_peak(mid, ref, dr))
                 assert p >= FP16_PSNR_BAR_BY_ID.get(mid, FP16_PSNR_BAR) - 1.0, (arch, (b, h, wd), v, p)
                 outs.append(y)
             for y in outs[1:]:
                 # the variants round differently (fp16 storage between layers; an outlier activation on uniform noise costs
                 # every fp16 path, the CUDA-core one included, several units locally): they agree to the same PSNR bar
-                assert _psnr(y, outs[0], dr) >= FP16_PSNR_BAR_BY_ID.get(mid, FP16_PSNR_BAR) - 1.0, (arch, (b, h, wd))
+                assert _psnr(y, outs[0], _noise_peak(mid, ref, dr)) >= FP16_PSNR_BAR_BY_ID.get(mid, FP16_PSNR_BAR) - 1.0, (arch, (b, h, wd))
     finally:
         eng.set_option("chain_enable", 1)
         eng.set_option("tc_acc_slots", 4)

@@ -14,7 +14,7 @@ sys.path.insert(0, ROOT)
 
 from oracle import esr_oracle as O  # noqa: E402
 
-IDS = {"imdn": -1, "rfdn": 0, "rlfn": 4, "bsrn": 18}
+IDS = {"imdn": -1, "rfdn": 0, "rlfn": 4, "bsrn": 18, "fmen": 3}
 
 
 def main():

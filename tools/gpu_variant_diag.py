@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from oracle import esr_oracle as O  # noqa: E402
 
-IDS = {"imdn": -1, "rfdn": 0, "rlfn": 4, "bsrn": 18, "rfdn40": 22, "rfdn_pruned": 40, "imdn_nb7": 26}
+IDS = {"imdn": -1, "rfdn": 0, "rlfn": 4, "bsrn": 18, "rfdn40": 22, "rfdn_pruned": 40, "imdn_nb7": 26, "fmen": 3}
 
 
 def main():
