@@ -34,7 +34,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 IDS = {"imdn": -1, "rfdn": 0, "rlfn": 4, "bsrn": 18, "fmen": 3}
-WEIGHTS = {"imdn": "imdn_baseline", "rfdn": "rfdn_baseline", "rlfn": "team04_rlfn", "bsrn": "team18_bsrn"}
+WEIGHTS = {"imdn": "imdn_baseline", "rfdn": "rfdn_baseline", "rlfn": "team04_rlfn", "bsrn": "team18_bsrn", "fmen": "team03_fmen"}
 RANGE = {"imdn": 1.0, "rfdn": 255.0, "rlfn": 255.0, "bsrn": 1.0, "fmen": 255.0}
 L2_BYTES = 126 * 2 ** 20
 
