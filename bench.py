@@ -52,6 +52,8 @@ CONFIGS = {
 # dram__bytes_write.sum), keyed by (model, batch, H, W, dtype, kernel); anything else reports null.
 NCU_TRAFFIC = {
     ("rfdn", 1, 256, 256, "f16", "conv_tc"): (8.56e6, "profiles/r1_conv_tc_b1_ncu_summary.csv"),
+    # fused RFDB chain (four 3x3 layers): dram__bytes_read 17.245 MB + dram__bytes_write 0.242 MB per launch, cold cache
+    ("rfdn", 1, 256, 256, "f16", "conv_chain"): (17.49e6, "profiles/r2_conv_chain_b1_ncu_raw.csv"),
 }
 
 
