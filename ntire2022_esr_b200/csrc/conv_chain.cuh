@@ -116,6 +116,8 @@ struct ChainParams {
   int32_t store_all;                   // debug: every ring row also goes to global memory
   int32_t dbg_flags;                   // timing experiments (results are wrong): 1 no MMAs, 2 epilogue only synchronises, 4 no TMA stores
   int32_t ps_fp32;
+  int32_t ps_u8;                       // the pixel-shuffle layer writes uint8 HWC (tensor2uint of the reference, utils_image.py:204-208)
+  float ps_dr;                         // ... with this data range
   void* ps_out;
   int32_t* flags;                      // [n_items][strips][n_layers], zeroed before the launch
   int32_t* item_counter;               // bands beyond the first wave are handed out in order through this counter (zeroed with the flags)
@@ -644,7 +646,9 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
     const bool edgeL = hasL && m == 0, edgeR = hasR && m == TC_TILE_PX - 1, edge = edgeL || edgeR;
     const int x = x0 + m;
     void* const ps_out = p.ps_out;
-    const int ps_fp32 = p.ps_fp32;
+    const int ps_fp32 = p.ps_fp32, ps_u8 = p.ps_u8;
+    const float ps_dr = p.ps_dr;
+    uint32_t u8_cnt = 0;
     const int ring_off = p.ring_off, stage_off = p.stage_off, stage_bytes = p.stage_bytes, ctr_acc_col = p.ctr_acc_col;
     // byte offsets of this thread's two 16-byte pieces inside a ring slot, and of the neighbour's halo position
     const uint32_t roff0 = (uint32_t)(pos * 128 + (((2 * sub) ^ (pos & 7)) << 4)), roff1 = (uint32_t)(pos * 128 + (((2 * sub + 1) ^ (pos & 7)) << 4));
@@ -663,6 +667,9 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
         const bool ring_out = Lr.ring_out != 0;
         const bool to_pw = has_pw && l == nL - 1 && p.pw.from_smem != 0;   // group 0 goes straight into the pointwise stage's A slot
         const bool staged = (n1 > 0) || (!ring_out && Lr.mode0 == 0 && !to_pw);
+        // uint8 output: the pixel-shuffle layer converts in the epilogue (tensor2uint) and stages one LR row = 4 output rows
+        // x 128 x 4 pixels x 3 bytes in the (otherwise unused) staging buffers; the epilogue warps copy the tile out themselves
+        const bool u8_layer = ps_u8 != 0 && Lr.mode0 == 1 && !ring_out;
         const int pw_slot_c = p.pw.fs_chunk, pw_lane0 = p.pw.fs_lane0;
         const int c = sub * 16;
         // unit A = accumulator columns [c, c+16): kind 0 none, 1 group 0, 2 group 1 (IMDN: columns of the same conv)
@@ -743,6 +750,18 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
               const int ch = (pw_lane0 + c0A) >> 3;
               *reinterpret_cast<uint4*>(slot + pos * 128 + ((ch ^ (pos & 7)) << 4)) = o0;
               *reinterpret_cast<uint4*>(slot + pos * 128 + (((ch + 1) ^ (pos & 7)) << 4)) = o1;
+            } else if (kindA && !ringA && u8_layer) {
+              if (valid) {   // column 16*ch + 4*i + jj of pixel m -> byte (i, 4m + jj, ch) of the tile
+                uint8_t* const tile = smem + stage_off + (u8_cnt & 1u) * stage_bytes + (m * 4) * 3 + (c0A >> 4);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                  for (int jj = 0; jj < 4; ++jj) {
+                    const float hv = __half2float(__float2half_rn(f[4 * i + jj]));       // the fp16 engine's output value
+                    const float q = __fdiv_rn(__fmul_rn(fminf(fmaxf(hv, 0.f), ps_dr), 255.0f), ps_dr);
+                    tile[i * 1536 + jj * 3] = (uint8_t)rintf(q);                          // np.round: half to even
+                  }
+              }
             } else if (kindA && !ringA)
               tc_epi_store16(f, modeA, stage + strowA, c0A, swzA, valid, ps_out, ps_fp32, img, y, x, H, W);
           }
@@ -751,6 +770,23 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
             const uint4 z = make_uint4(0, 0, 0, 0);
             tc_epi_math16(vb, biasB, false, slopeB, false, z, z, 0, f);
             tc_epi_store16(f, 0, stage + strowB, c, swzB, valid, ps_out, ps_fp32, img, y, x, H, W);
+          }
+          if (u8_layer) {
+            // every epilogue warp has written its bytes: copy the tile out, 4 output rows x (3 * valid pixels) words.  Two
+            // tiles alternate, so the barrier of the next row also says that everybody is done reading this one.
+            named_bar_sync(1, 32 * CH_EPI_WARPS);
+            if (y >= 0 && y < H && !epi_skip) {
+              const uint32_t* const t32 = reinterpret_cast<const uint32_t*>(smem + stage_off + (u8_cnt & 1u) * stage_bytes);
+              const int nwords = 3 * min(TC_TILE_PX, W - x0);
+              uint8_t* const ob = reinterpret_cast<uint8_t*>(ps_out) + ((((long long)img * 4 * H + 4 * y) * (4 * W)) + 4 * x0) * 3;
+#pragma unroll
+              for (int t = 0; t < 3; ++t) {
+                const int k = (int)threadIdx.x - 64 + 32 * CH_EPI_WARPS * t;
+                const int i = k / 384, kk = k - 384 * i;
+                if (kk < nwords) reinterpret_cast<uint32_t*>(ob + (long long)i * (12 * W))[kk] = t32[k];
+              }
+            }
+            ++u8_cnt;
           }
           tc_fence_before_sync();
           fence_proxy_async_smem();

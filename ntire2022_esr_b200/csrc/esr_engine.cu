@@ -38,6 +38,7 @@ struct Plan {
   void* ws = nullptr;
   // uint8 I/O (esr_forward_u8): `in` is HWC uint8, `out` the engine's own NCHW buffer, `u8_out` the caller's HWC uint8
   bool u8 = false;
+  bool u8_folded = false;   // the pixel-shuffle layer wrote the uint8 image itself
   float data_range = 1.f;
   void* u8_out = nullptr;
   std::vector<Launch> launches;
@@ -491,6 +492,16 @@ static int plan_chain(Engine* e, const DevGraph& dg, const ChainDecl& ch, const 
   p.dbg_flags = e->opt_dbg_flags;
   p.ps_fp32 = 0;
   p.ps_out = pl.out;
+  p.ps_u8 = 0; p.ps_dr = 1.f;
+  // uint8 output (esr_forward_u8): when this chain ends in the pixel-shuffle layer, tensor2uint happens in its epilogue
+  // and the bytes go straight into the caller's HWC image - no NCHW intermediate, no conversion launch
+  if (pl.u8 && g.tc[ch.layers[nL - 1].tc].groups[0].mode == 1 && g.tc[ch.layers[nL - 1].tc].groups.size() == 1 &&
+      (reinterpret_cast<uintptr_t>(pl.u8_out) & 3) == 0) {
+    p.ps_u8 = 1;
+    p.ps_dr = pl.data_range;
+    p.ps_out = pl.u8_out;
+    pl.u8_folded = true;
+  }
   p.flags = reinterpret_cast<int32_t*>(ws + flags_off);
   p.item_counter = p.flags + chain_flag_ints(B, H, W, nL) - 1;
   p.wblob = dg.d_blobs + ch.off_blob;
@@ -669,6 +680,7 @@ static int plan_chain(Engine* e, const DevGraph& dg, const ChainDecl& ch, const 
   p.ident_bytes = any_ident ? CH_IDENT_BYTES : 0;
   p.stage_off = p.ident_off + p.ident_bytes;
   p.ident = dg.d_ident;
+  if (p.ps_u8) stage_cols = std::max(stage_cols, 24);   // one LR row of uint8 HWC output: 4 x 1536 bytes
   p.stage_bytes = (TC_TILE_PX * std::max(stage_cols, 16) * 2 + 1023) / 1024 * 1024;
   const size_t smem = (size_t)p.stage_off + 2 * (size_t)p.stage_bytes + 1024;
   if (smem > kChainSmemMax) return fail(e, ESR_E_INVALID, "chain: shared memory budget exceeded");
@@ -972,7 +984,7 @@ static int build_plan(Engine* e, Plan& pl) {
     }
     pl.launches.back().flops = op_flops(op, B, H, W);
   }
-  if (pl.u8) {   // tensor2uint of the reference, on the engine's NCHW output
+  if (pl.u8 && !pl.u8_folded) {   // tensor2uint of the reference, on the engine's NCHW output (folded into the tail chain's epilogue when there is one)
     const void* src = pl.out;
     uint8_t* dst = reinterpret_cast<uint8_t*>(pl.u8_out);
     const float dr = pl.data_range;
