@@ -259,7 +259,9 @@ __device__ __forceinline__ long long global_timer_ns() {
   } while (0)
 
 // kPw: compiled with / without the optional pointwise last stage (its code costs the common instantiation registers)
-template <bool kPw>
+// kU8: compiled with the uint8 pixel-shuffle epilogue (esr_forward_u8); measured: carrying that code in the common
+// instantiation costs every chain 5 % (37.2 vs 35.5 us per RFDB chain)
+template <bool kPw, bool kU8 = false>
 __global__ void __launch_bounds__(CH_THREADS, 1)
 conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ ChainParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -646,7 +648,7 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
     const bool edgeL = hasL && m == 0, edgeR = hasR && m == TC_TILE_PX - 1, edge = edgeL || edgeR;
     const int x = x0 + m;
     void* const ps_out = p.ps_out;
-    const int ps_fp32 = p.ps_fp32, ps_u8 = p.ps_u8;
+    const int ps_fp32 = p.ps_fp32, ps_u8 = kU8 ? p.ps_u8 : 0;
     const float ps_dr = p.ps_dr;
     uint32_t u8_cnt = 0;
     const int ring_off = p.ring_off, stage_off = p.stage_off, stage_bytes = p.stage_bytes, ctr_acc_col = p.ctr_acc_col;
@@ -669,7 +671,7 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
         const bool staged = (n1 > 0) || (!ring_out && Lr.mode0 == 0 && !to_pw);
         // uint8 output: the pixel-shuffle layer converts in the epilogue (tensor2uint) and stages one LR row = 4 output rows
         // x 128 x 4 pixels x 3 bytes in the (otherwise unused) staging buffers; the epilogue warps copy the tile out themselves
-        const bool u8_layer = ps_u8 != 0 && Lr.mode0 == 1 && !ring_out;
+        const bool u8_layer = kU8 && ps_u8 != 0 && Lr.mode0 == 1 && !ring_out;
         const int pw_slot_c = p.pw.fs_chunk, pw_lane0 = p.pw.fs_lane0;
         const int c = sub * 16;
         // unit A = accumulator columns [c, c+16): kind 0 none, 1 group 0, 2 group 1 (IMDN: columns of the same conv)

@@ -437,6 +437,7 @@ static int chain_clusters(Engine* e, int strips) {
   if (e->chain_capacity[strips] == 0) {
     if (!e->attr_chain) {
       if (cudaFuncSetAttribute(conv_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemMax) != cudaSuccess ||
+          cudaFuncSetAttribute(conv_chain_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemMax) != cudaSuccess ||
           cudaFuncSetAttribute(conv_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemMax) != cudaSuccess) {
         cudaGetLastError();
         return 0;
@@ -495,7 +496,8 @@ static int plan_chain(Engine* e, const DevGraph& dg, const ChainDecl& ch, const 
   p.ps_u8 = 0; p.ps_dr = 1.f;
   // uint8 output (esr_forward_u8): when this chain ends in the pixel-shuffle layer, tensor2uint happens in its epilogue
   // and the bytes go straight into the caller's HWC image - no NCHW intermediate, no conversion launch
-  if (pl.u8 && g.tc[ch.layers[nL - 1].tc].groups[0].mode == 1 && g.tc[ch.layers[nL - 1].tc].groups.size() == 1 &&
+  if (pl.u8 && !(ch.pw_tc >= 0 && e->opt_chain_pw) && g.tc[ch.layers[nL - 1].tc].groups[0].mode == 1 &&
+      g.tc[ch.layers[nL - 1].tc].groups.size() == 1 &&
       (reinterpret_cast<uintptr_t>(pl.u8_out) & 3) == 0) {
     p.ps_u8 = 1;
     p.ps_dr = pl.data_range;
@@ -701,6 +703,7 @@ static int plan_chain(Engine* e, const DevGraph& dg, const ChainDecl& ch, const 
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = g_pdl ? 2 : 1;
+    if (pk->p.ps_u8) return cudaLaunchKernelEx(&cfg, conv_chain_kernel<false, true>, pk->maps, pk->p);
     return pk->p.pw.enabled ? cudaLaunchKernelEx(&cfg, conv_chain_kernel<true>, pk->maps, pk->p)
                             : cudaLaunchKernelEx(&cfg, conv_chain_kernel<false>, pk->maps, pk->p);
   }});
