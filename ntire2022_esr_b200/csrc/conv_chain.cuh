@@ -255,13 +255,15 @@ __device__ __forceinline__ long long global_timer_ns() {
 }
 #define CH_STAMP(role, idx)                                                                        \
   do {                                                                                             \
-    if (dbg != nullptr && (int)blockIdx.x == (p.dbg_flags >> 8) && (idx) < 64) dbg[(role) * 64 + (idx)] = clock64();  /* dbg_flags >> 8: the block whose roles are stamped */      \
+    if (kDbg && dbg != nullptr && (int)blockIdx.x == (dbg_flags >> 8) && (idx) < 64) dbg[(role) * 64 + (idx)] = clock64();  /* dbg_flags >> 8: the block whose roles are stamped */      \
   } while (0)
 
 // kPw: compiled with / without the optional pointwise last stage (its code costs the common instantiation registers)
 // kU8: compiled with the uint8 pixel-shuffle epilogue (esr_forward_u8); measured: carrying that code in the common
 // instantiation costs every chain 5 % (37.2 vs 35.5 us per RFDB chain)
-template <bool kPw, bool kU8 = false>
+// kDbg: compiled with the clock64 / globaltimer stamps and the timing-experiment switches (dbg_flags); the production
+// instantiations carry none of that code
+template <bool kPw, bool kU8 = false, bool kDbg = false>
 __global__ void __launch_bounds__(CH_THREADS, 1)
 conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ ChainParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -283,8 +285,10 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
   __shared__ __align__(16) float pw_bias_s[160];               // pointwise stage: per accumulator column
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  long long* const dbg = p.dbg;
-  if (p.dbg_blocks != nullptr && threadIdx.x == 0) p.dbg_blocks[blockIdx.x * 4 + 0] = global_timer_ns();
+  long long* const dbg = kDbg ? p.dbg : nullptr;
+  long long* const dbg_blocks = kDbg ? p.dbg_blocks : nullptr;
+  const int dbg_flags = kDbg ? p.dbg_flags : 0;
+  if (kDbg && dbg_blocks != nullptr && threadIdx.x == 0) dbg_blocks[blockIdx.x * 4 + 0] = global_timer_ns();
   const uint32_t raw_u32 = smem_u32(smem_raw);
   const uint32_t pad = (1024u - (raw_u32 & 1023u)) & 1023u;
   uint8_t* const smem = smem_raw + pad;
@@ -352,7 +356,7 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
   tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_s;
   if (threadIdx.x == 0) CH_STAMP(0, 0);
-  if (p.dbg_blocks != nullptr && threadIdx.x == 0) p.dbg_blocks[blockIdx.x * 4 + 1] = global_timer_ns();
+  if (kDbg && dbg_blocks != nullptr && threadIdx.x == 0) dbg_blocks[blockIdx.x * 4 + 1] = global_timer_ns();
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -492,7 +496,7 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
     // pipe's queue is short, so (a) the MMAs of a step are issued from straight-line code and (b) the barrier waits of
     // the NEXT step are taken in the middle of the current step's MMAs: the pipe never drains while this thread polls.
     if (elect_one()) {
-      const bool no_mma = (p.dbg_flags & 1) != 0;
+      const bool no_mma = (dbg_flags & 1) != 0;
       const uint32_t w_base = smem_base + p.w_off, ctr_base = smem_base + p.ctr_off, ident_base = smem_base + p.ident_off;
       mbar_wait(&ident_bar, 0);
       uint32_t bars_a;                                           // laundered: must not be rematerialised from the symbol
@@ -505,7 +509,7 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
       bool it_valid = it_item < n_items;
       uint32_t ctr_mask = 0;
       for (int l = 0; l < nL; ++l) if (p.L[l].ctr_n > 0) ctr_mask |= 1u << l;
-      const bool no_wait = (p.dbg_flags & 16) != 0, no_short = (p.dbg_flags & 32) != 0;   // timing experiments (results are wrong)
+      const bool no_wait = (dbg_flags & 16) != 0, no_short = (dbg_flags & 32) != 0;   // timing experiments (results are wrong)
       auto wait_step = [&](int l, int i, uint32_t g, uint32_t items, uint32_t ctrc) {
         if (no_wait) return;
         if (kPw && l == nL) {   // pointwise stage: steps R+1, R are empty; step j < R = output row j
@@ -658,7 +662,7 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
     const uint32_t xoff0 = (uint32_t)(rpos * 128 + (((2 * sub) ^ (rpos & 7)) << 4)), xoff1 = (uint32_t)(rpos * 128 + (((2 * sub + 1) ^ (rpos & 7)) << 4));
     const uint32_t nb_rank = edgeL ? rank - 1 : rank + 1;
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    const bool epi_skip = (p.dbg_flags & 2) != 0;
+    const bool epi_skip = (dbg_flags & 2) != 0;
     griddep_wait();
     uint32_t g = 0, stage_cnt = 0, ring_cnt = 0, pw_rows = 0, items = 0;
     for (int item = (int)cid; item < n_items; ++items, item = next_item(items)) {
@@ -926,7 +930,7 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
             const bool row_valid = y >= 0 && y < H;
             mbar_wait(&wrote[j], g & 1u);
             const uint32_t buf = stage_cnt & 1u;
-            if (row_valid && !(p.dbg_flags & 4)) {
+            if (row_valid && !(dbg_flags & 4)) {
               if (ring_out && (store_all || j >= R - 2))
                 tma_store_4d(map_out, smem + ring_off + (j + 2) * CH_SLOT_BYTES + CH_PX0 * 128, 0, x0, y, img);
               if (g0_staged) tma_store_4d(map_out, smem + stage_off + buf * stage_bytes, 0, x0, y, img);
@@ -976,7 +980,7 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
             mbar_wait(&wrote[j], g & 1u);
             const uint32_t buf = stage_cnt & 1u;
             const uint32_t pb = dbl ? (pw_rows & 1u) : 0u;
-            if (y >= 0 && y < H && !(p.dbg_flags & 4))
+            if (y >= 0 && y < H && !(dbg_flags & 4))
               for (int k = 0; k < ngr; ++k) {
                 const int q = P.g_stage[k];
                 const uint8_t* src = q == 2 ? smem + stage_off + buf * stage_bytes
@@ -1000,14 +1004,14 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (p.dbg_blocks != nullptr && threadIdx.x == 0) p.dbg_blocks[blockIdx.x * 4 + 2] = global_timer_ns();
+  if (kDbg && dbg_blocks != nullptr && threadIdx.x == 0) dbg_blocks[blockIdx.x * 4 + 2] = global_timer_ns();
   // Every remote access to this CTA's shared memory has been consumed by now (the side pixels through ready[], the
   // "slot read" arrivals through nfree[]); the cluster barrier is only insurance and carries no data, so the relaxed
   // form is enough.  (The release / acquire form measured 4-8 us here: it drains the CTA's outstanding global writes.)
-  if (!(p.dbg_flags & 8)) asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+  if (!(dbg_flags & 8)) asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   if (threadIdx.x == 0) CH_STAMP(0, 1);
-  if (p.dbg_blocks != nullptr && threadIdx.x == 0) p.dbg_blocks[blockIdx.x * 4 + 3] = global_timer_ns();
+  if (kDbg && dbg_blocks != nullptr && threadIdx.x == 0) dbg_blocks[blockIdx.x * 4 + 3] = global_timer_ns();
 }
 
 }  // namespace esr

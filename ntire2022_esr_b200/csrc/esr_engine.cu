@@ -438,6 +438,8 @@ static int chain_clusters(Engine* e, int strips) {
     if (!e->attr_chain) {
       if (cudaFuncSetAttribute(conv_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemMax) != cudaSuccess ||
           cudaFuncSetAttribute(conv_chain_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemMax) != cudaSuccess ||
+          cudaFuncSetAttribute(conv_chain_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemMax) != cudaSuccess ||
+          cudaFuncSetAttribute(conv_chain_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemMax) != cudaSuccess ||
           cudaFuncSetAttribute(conv_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemMax) != cudaSuccess) {
         cudaGetLastError();
         return 0;
@@ -704,6 +706,9 @@ static int plan_chain(Engine* e, const DevGraph& dg, const ChainDecl& ch, const 
     cfg.attrs = at;
     cfg.numAttrs = g_pdl ? 2 : 1;
     if (pk->p.ps_u8) return cudaLaunchKernelEx(&cfg, conv_chain_kernel<false, true>, pk->maps, pk->p);
+    if (pk->p.dbg != nullptr || pk->p.dbg_flags != 0)     // timeline stamps / timing experiments: the instrumented instantiations
+      return pk->p.pw.enabled ? cudaLaunchKernelEx(&cfg, conv_chain_kernel<true, false, true>, pk->maps, pk->p)
+                              : cudaLaunchKernelEx(&cfg, conv_chain_kernel<false, false, true>, pk->maps, pk->p);
     return pk->p.pw.enabled ? cudaLaunchKernelEx(&cfg, conv_chain_kernel<true>, pk->maps, pk->p)
                             : cudaLaunchKernelEx(&cfg, conv_chain_kernel<false>, pk->maps, pk->p);
   }});
