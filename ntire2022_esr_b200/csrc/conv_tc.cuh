@@ -323,6 +323,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int last = min(j, nrows - 1), first = max(0, j - 2 * halo);
         need_a_s[pr_slot] = pr_tile_base + last;
         need_b_s[pr_slot] = (last - 1 >= first) ? pr_tile_base + last - 1 : -1;
+        // A strip with ONE reader tile (every strip of a 1x1 layer): the reader is one issuing thread, and the other issuing thread only watches its barrier to
+        // stay in phase (see the MMA issuers).  Nothing kept the producer from recycling the slot twice before that
+        // thread had looked at it - under multi-stream load (four requests in flight) it was lapped about once per
+        // 10^5 forwards and then waited for a phase that had already gone by (mbarrier time-out).  The slot is therefore
+        // only reused once the NEXT tile (the watcher's own, which it starts after having seen this strip) is done.
+        // (The same holds for the first and the last strip of an item in the 3x3 layers: one reader tile.)
+        if (need_b_s[pr_slot] < 0 && (last + 1 < nrows || pr_item + (int)gridDim.x < n_items)) need_b_s[pr_slot] = pr_tile_base + last + 1;
       }
       mbar_arrive_expect_tx(&full_bar[pr_slot], strip_tx);
       uint8_t* dst = smem + ring_off + pr_slot * strip_bytes;

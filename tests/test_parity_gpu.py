@@ -442,3 +442,35 @@ def test_tcgen05_kernels_width_and_variant_sweep_vs_oracle(mid, arch):
     finally:
         eng.set_option("chain_enable", 1)
         eng.set_option("tc_acc_slots", 4)
+
+
+def test_pipelined_host_path_survives_sustained_multi_stream_load():
+    """30 000 requests through esr_forward_host_async with four in flight (each on its own stream and workspace, so the
+    kernels of different requests share the SMs).  Before the slot-recycling rule of conv_tc's producer was tightened
+    (a strip with a single reader tile is only recycled once the OTHER issuing thread's next tile is done) the watching
+    issuer of a 1x1 layer was lapped about once per 10^5 forwards under exactly this load and the CTA died in an
+    mbarrier time-out ("unspecified launch failure"); the run failed within 30 000 requests four times out of four."""
+    from ntire2022_esr_b200 import Engine, _cabi
+
+    eng = Engine("rfdn", 0)
+    eng.load_state_dict(_weights(0))
+    h = wd = 256
+    nbuf = 6
+    g = torch.Generator().manual_seed(1)
+    xs = [(torch.rand(1, 3, h, wd, generator=g) * 255).half().pin_memory() for _ in range(nbuf)]
+    ys = [torch.empty(1, 3, 4 * h, 4 * wd, dtype=torch.float16).pin_memory() for _ in range(nbuf)]
+    submit = lambda k: eng.forward_host_async_ptr(xs[k].data_ptr(), ys[k].data_ptr(), 1, h, wd, _cabi.DTYPE_F16)
+    for k in range(nbuf):
+        submit(k)
+    eng.host_wait(-1)
+    want = [y.clone() for y in ys]
+    tickets = []
+    for i in range(30000):
+        k = i % nbuf
+        if i >= nbuf:
+            eng.host_wait(tickets[i - nbuf])
+            if i % 499 == 0:
+                assert torch.equal(ys[k], want[k]), i
+        tickets.append(submit(k))
+    eng.host_wait(-1)
+    assert all(torch.equal(ys[k], want[k]) for k in range(nbuf))
