@@ -263,7 +263,10 @@ __device__ __forceinline__ long long global_timer_ns() {
 // instantiation costs every chain 5 % (37.2 vs 35.5 us per RFDB chain)
 // kDbg: compiled with the clock64 / globaltimer stamps and the timing-experiment switches (dbg_flags); the production
 // instantiations carry none of that code
-template <bool kPw, bool kU8 = false, bool kDbg = false>
+// kTail: compiled with the global residual / gate operand and the pixel-shuffle store (the tail chain and FMEN's chains);
+// the block chains (RFDB, IMDB, RLFB) use the instantiation without them
+// kCtr: compiled with the centre block (the distillation 1x1 of an RFDB stage: its weights, MMAs, accumulator, epilogue unit)
+template <bool kPw, bool kU8 = false, bool kDbg = false, bool kTail = true, bool kCtr = true>
 __global__ void __launch_bounds__(CH_THREADS, 1)
 conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ ChainParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -429,7 +432,7 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
               mbar_arrive_expect_tx(&wfull[part], (uint32_t)Lr.part_bytes);
               bulk_load_1d(smem + p.w_off + part * Lr.part_bytes, wsrc + part * Lr.part_bytes, (uint32_t)Lr.part_bytes, &wfull[part]);
             }
-            if (i == (g > 0 ? 1 : R) && Lr.ctr_n > 0) {   // the centre block's last reader is step 1
+            if (kCtr && i == (g > 0 ? 1 : R) && Lr.ctr_n > 0) {   // the centre block's last reader is step 1
               mbar_arrive_expect_tx(&wfull[3], (uint32_t)(Lr.ctr_n * 128));
               bulk_load_1d(smem + p.ctr_off, wsrc + 3 * Lr.part_bytes, (uint32_t)(Lr.ctr_n * 128), &wfull[3]);
               ++ctr_cnt;
@@ -508,7 +511,7 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
       uint32_t it_g = 0, it_items = 0, it_ctr = 0;
       bool it_valid = it_item < n_items;
       uint32_t ctr_mask = 0;
-      for (int l = 0; l < nL; ++l) if (p.L[l].ctr_n > 0) ctr_mask |= 1u << l;
+      for (int l = 0; l < nL; ++l) if (kCtr && p.L[l].ctr_n > 0) ctr_mask |= 1u << l;
       const bool no_wait = (dbg_flags & 16) != 0, no_short = (dbg_flags & 32) != 0;   // timing experiments (results are wrong)
       auto wait_step = [&](int l, int i, uint32_t g, uint32_t items, uint32_t ctrc) {
         if (no_wait) return;
@@ -573,7 +576,7 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
         }
         if (l != cur_l) {
           const ChLayer& Lr = p.L[l];
-          np = Lr.np; ks = no_mma ? 0 : Lr.ksteps; ctr_n = Lr.ctr_n; acc_col = Lr.acc_col; part_bytes = Lr.part_bytes;
+          np = Lr.np; ks = no_mma ? 0 : Lr.ksteps; ctr_n = kCtr ? Lr.ctr_n : 0; acc_col = Lr.acc_col; part_bytes = Lr.part_bytes;
           res_ident = Lr.res_smem != 0;
           cur_l = l;
         }
@@ -599,7 +602,7 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
         // the block residual) go right behind the first tap: the step ends with full-width MMAs, which is what the
         // tensor pipe works on while this thread commits and sets up the next step
         if (i >= 1 && i <= R && !no_short) {
-          if (ctr_n > 0) umma_f16_ss_run(d_ctr + (uint32_t)((i - 1) * 32), A0 + 8, HI_A, B_CTR, HI_A, umma_idesc_f16((uint32_t)ctr_n), 0u, ks);
+          if (kCtr && ctr_n > 0) umma_f16_ss_run(d_ctr + (uint32_t)((i - 1) * 32), A0 + 8, HI_A, B_CTR, HI_A, umma_idesc_f16((uint32_t)ctr_n), 0u, ks);
           if (res_ident) umma_f16_ss_run(tmem_base + (uint32_t)(acc_col + (i - 1) * np), A0 + 8, HI_A, B_ID, HI_A, id_one, 1u, ks);
         }
         // dx = -1 (remaining K steps) and dx = 0 taps
@@ -684,12 +687,12 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
         else if (!Lr.g1_ctr && n1 > 0 && c >= Lr.col1 && c < Lr.col1 + n1) { kindA = 2; c0A = c - Lr.col1; }
         const bool zfillA = ring_out && kindA != 1;            // ring lanes this layer does not produce are written as zeros
         const bool ringA = ring_out && kindA == 1;
-        const bool kindB = Lr.g1_ctr && c < n1;                // unit B = the centre block's columns [c, c+16): always group 1
+        const bool kindB = kCtr && Lr.g1_ctr && c < n1;        // unit B = the centre block's columns [c, c+16): always group 1
         const uint32_t tcolA = (uint32_t)(Lr.acc_col + c), tcolB = (uint32_t)(ctr_acc_col + c);
         const float* const biasA = &bias_s[l][(kindA == 2 ? 64 : 0) + c0A];
         const float* const biasB = &bias_s[l][64 + c];
         const float slopeA = kindA == 2 ? Lr.slope1 : Lr.slope0, slopeB = Lr.slope1;
-        const int resA = (kindA == 1 && Lr.res != nullptr) ? 2 : 0;   // (the block residual arrives through the accumulator)
+        const int resA = (kTail && kindA == 1 && Lr.res != nullptr) ? 2 : 0;   // (the block residual arrives through the accumulator)
         const int res_after = Lr.res_after;
         const __half* const gres = Lr.res;
         const int gres_stride = Lr.res_stride, gres_coff = Lr.res_coff + c0A;
@@ -769,7 +772,7 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
                   }
               }
             } else if (kindA && !ringA)
-              tc_epi_store16(f, modeA, stage + strowA, c0A, swzA, valid, ps_out, ps_fp32, img, y, x, H, W);
+              tc_epi_store16(f, kTail ? modeA : 0, stage + strowA, c0A, swzA, valid, ps_out, ps_fp32, img, y, x, H, W);
           }
           if (kindB && !epi_skip) {
             float f[16];

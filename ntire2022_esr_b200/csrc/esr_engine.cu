@@ -439,6 +439,9 @@ static int chain_clusters(Engine* e, int strips) {
       if (cudaFuncSetAttribute(conv_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemMax) != cudaSuccess ||
           cudaFuncSetAttribute(conv_chain_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemMax) != cudaSuccess ||
           cudaFuncSetAttribute(conv_chain_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemMax) != cudaSuccess ||
+          cudaFuncSetAttribute(conv_chain_kernel<false, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemMax) != cudaSuccess ||
+          cudaFuncSetAttribute(conv_chain_kernel<false, false, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemMax) != cudaSuccess ||
+          cudaFuncSetAttribute(conv_chain_kernel<false, false, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemMax) != cudaSuccess ||
           cudaFuncSetAttribute(conv_chain_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemMax) != cudaSuccess ||
           cudaFuncSetAttribute(conv_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemMax) != cudaSuccess) {
         cudaGetLastError();
@@ -709,8 +712,19 @@ static int plan_chain(Engine* e, const DevGraph& dg, const ChainDecl& ch, const 
     if (pk->p.dbg != nullptr || pk->p.dbg_flags != 0)     // timeline stamps / timing experiments: the instrumented instantiations
       return pk->p.pw.enabled ? cudaLaunchKernelEx(&cfg, conv_chain_kernel<true, false, true>, pk->maps, pk->p)
                               : cudaLaunchKernelEx(&cfg, conv_chain_kernel<false, false, true>, pk->maps, pk->p);
-    return pk->p.pw.enabled ? cudaLaunchKernelEx(&cfg, conv_chain_kernel<true>, pk->maps, pk->p)
-                            : cudaLaunchKernelEx(&cfg, conv_chain_kernel<false>, pk->maps, pk->p);
+    if (pk->p.pw.enabled) return cudaLaunchKernelEx(&cfg, conv_chain_kernel<true>, pk->maps, pk->p);
+    // the block chains get the instantiation without the code they do not need (measured: 33.2 vs 34.7 us per RFDB chain
+    // without the tail features): `tail` = any layer with a global residual / gate operand or the pixel-shuffle store,
+    // `ctr` = any layer with a centre block
+    bool tail = false, ctr = false;
+    for (int l = 0; l < pk->p.n_layers; ++l) {
+      tail = tail || pk->p.L[l].res != nullptr || pk->p.L[l].mode0 != 0;
+      ctr = ctr || pk->p.L[l].ctr_n > 0;
+    }
+    if (tail && ctr) return cudaLaunchKernelEx(&cfg, conv_chain_kernel<false>, pk->maps, pk->p);
+    if (tail) return cudaLaunchKernelEx(&cfg, conv_chain_kernel<false, false, false, true, false>, pk->maps, pk->p);
+    if (ctr) return cudaLaunchKernelEx(&cfg, conv_chain_kernel<false, false, false, false>, pk->maps, pk->p);
+    return cudaLaunchKernelEx(&cfg, conv_chain_kernel<false, false, false, false, false>, pk->maps, pk->p);
   }});
   if (name_out) *name_out = name;
   return ESR_OK;
