@@ -106,7 +106,7 @@ struct TcParams {
 
 #define TC_STAMP(role, idx)                                                                        \
   do {                                                                                             \
-    if (dbg != nullptr && blockIdx.x == 0 && (idx) < 32) dbg[(role) * 32 + (idx)] = clock64();      \
+    if (kDbg && dbg != nullptr && blockIdx.x == 0 && (idx) < 32) dbg[(role) * 32 + (idx)] = clock64();      \
   } while (0)
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
@@ -254,6 +254,10 @@ __device__ __forceinline__ void tc_epi_store16(const float (&f)[16], int mode, u
 // One kernel for every network.  (A second instantiation without the GELU / border-class-bias code measured 1-2 %
 // faster on RFDN; it also made a latent barrier bug - see the strip waits of the MMA issuers below - fail often
 // enough to be found.  The split itself was not worth keeping.)
+// kDbg: compiled with the timeline stamps and the timing-experiment switches; kBsrn: with the GELU and the border-class
+// bias table (BSRN).  The production instantiations carry only what their network needs (the single-thread roles pay for
+// every instruction-cache line; the same measure gave the fused chain kernel 3-6 %).
+template <bool kDbg, bool kBsrn>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmO0,
                const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ CUtensorMap tmO2,
@@ -268,7 +272,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __shared__ TcOutGroup grp_s[TC_MAX_GROUPS];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  long long* const dbg = p.dbg;
+  long long* const dbg = kDbg ? p.dbg : nullptr;
   if (threadIdx.x == 0) TC_STAMP(0, 0);
   // 1024-byte aligned view of dynamic shared memory (SWIZZLE_128B atoms)
   const uint32_t raw_u32 = smem_u32(smem_raw);
@@ -281,7 +285,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int S = p.nslots, halo = p.halo, nchunks = p.nchunks, strip_bytes = p.strip_bytes, chunk_bytes = p.chunk_bytes;
   const int n_items = p.n_items, strips_x = p.strips_x, segs_y = p.segs_y, rows_per_item = p.rows_per_item;
   const int H = p.H, W = p.W, ring_off = p.ring_off, acc_cols = p.acc_cols, n_entries = p.n_entries, ngroups = p.ngroups;
-  const int dbg_flags = p.dbg_flags;
+  const int dbg_flags = kDbg ? p.dbg_flags : 0;
   const uint32_t NS = (uint32_t)p.acc_slots, ns_shift = NS == 4 ? 2u : 1u;
 
   auto decode = [&](int item, int& b, int& y0, int& y1, int& x0) {
@@ -385,7 +389,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int g = i >> 6, c = i & 63;
       bias_s[g][c] = (g < ngroups && c < p.g[g].ncols) ? p.g[g].bias[c] : 0.f;
     }
-    if (p.g[0].bias9 != nullptr)
+    if (kBsrn && p.g[0].bias9 != nullptr)
       for (int i = tid; i < 9 * 64; i += 32 * TC_EPI_WARPS) bias9_s[i >> 6][i & 63] = p.g[0].bias9[i];
     if (tid < TC_MAX_ENTRIES) ent_s[tid] = p.e[tid];
     if (tid >= 32 && tid < 32 + TC_MAX_GROUPS) grp_s[tid - 32] = p.g[tid - 32];
@@ -506,9 +510,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const TcOutGroup& g = grp_s[gi < ngroups ? gi : 0];
       gcol0[gi] = g.col0; gncols[gi] = gi < ngroups ? g.ncols : 0; gmode[gi] = g.mode; gswz[gi] = g.swizzle;
       gstage[gi] = g.stage_off; gstage_bytes[gi] = g.stage_bytes;
-      ggelu[gi] = g.act == ACT_GELU; gslope[gi] = g.slope;
+      ggelu[gi] = kBsrn && g.act == ACT_GELU; gslope[gi] = g.slope;
     }
-    const bool g0_bias9 = grp_s[0].bias9 != nullptr;
+    const bool g0_bias9 = kBsrn && grp_s[0].bias9 != nullptr;
     const bool g0_has_res = ng > 0 && grp_s[0].res != nullptr;
     const __half* const g0_res = g0_has_res ? grp_s[0].res + grp_s[0].res_coff : nullptr;
     const int g0_res_stride = grp_s[0].res_stride;

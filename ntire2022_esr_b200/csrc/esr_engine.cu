@@ -413,11 +413,18 @@ static int plan_tc(Engine* e, const DevGraph& dg, const TcConv& c, const std::st
   }
   const int grid = std::min(p.n_items, e->num_sms);
   if (!e->attr_tc) {   // function attributes are per device: tracked per handle (a handle is bound to one device)
-    CUDA_TRY(e, cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+    CUDA_TRY(e, cudaFuncSetAttribute(conv_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+    CUDA_TRY(e, cudaFuncSetAttribute(conv_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+    CUDA_TRY(e, cudaFuncSetAttribute(conv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
     e->attr_tc = true;
   }
-  pl.launches.push_back(Launch{"conv_tc:" + name, [pk, grid, smem](cudaStream_t s) {
-                                 return launch_k(conv_tc_kernel, dim3(grid), dim3(TC_THREADS), smem, s, pk->tmA, pk->tmO[0], pk->tmO[1],
+  // instantiation: instrumented (timeline / timing experiments), BSRN (GELU, border-class bias), or plain
+  bool bsrn = false;
+  for (auto& gd : c.groups) bsrn = bsrn || gd.act == ACT_GELU || gd.off_bias9 >= 0;
+  const int variant = (p.dbg != nullptr || p.dbg_flags != 0) ? 2 : (bsrn ? 1 : 0);
+  pl.launches.push_back(Launch{"conv_tc:" + name, [pk, grid, smem, variant](cudaStream_t s) {
+                                 auto kern = variant == 2 ? conv_tc_kernel<true, true> : (variant == 1 ? conv_tc_kernel<false, true> : conv_tc_kernel<false, false>);
+                                 return launch_k(kern, dim3(grid), dim3(TC_THREADS), smem, s, pk->tmA, pk->tmO[0], pk->tmO[1],
                                                  pk->tmO[2], pk->p);
                                }});
   return ESR_OK;
@@ -438,6 +445,7 @@ static int chain_clusters(Engine* e, int strips) {
     if (!e->attr_chain) {
       if (cudaFuncSetAttribute(conv_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemMax) != cudaSuccess ||
           cudaFuncSetAttribute(conv_chain_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemMax) != cudaSuccess ||
+          cudaFuncSetAttribute(conv_chain_kernel<false, true, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemMax) != cudaSuccess ||
           cudaFuncSetAttribute(conv_chain_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemMax) != cudaSuccess ||
           cudaFuncSetAttribute(conv_chain_kernel<false, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemMax) != cudaSuccess ||
           cudaFuncSetAttribute(conv_chain_kernel<false, false, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemMax) != cudaSuccess ||
@@ -708,7 +716,12 @@ static int plan_chain(Engine* e, const DevGraph& dg, const ChainDecl& ch, const 
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = g_pdl ? 2 : 1;
-    if (pk->p.ps_u8) return cudaLaunchKernelEx(&cfg, conv_chain_kernel<false, true>, pk->maps, pk->p);
+    if (pk->p.ps_u8) {
+      bool c = false;
+      for (int l = 0; l < pk->p.n_layers; ++l) c = c || pk->p.L[l].ctr_n > 0;
+      return c ? cudaLaunchKernelEx(&cfg, conv_chain_kernel<false, true>, pk->maps, pk->p)
+               : cudaLaunchKernelEx(&cfg, conv_chain_kernel<false, true, false, true, false>, pk->maps, pk->p);
+    }
     if (pk->p.dbg != nullptr || pk->p.dbg_flags != 0)     // timeline stamps / timing experiments: the instrumented instantiations
       return pk->p.pw.enabled ? cudaLaunchKernelEx(&cfg, conv_chain_kernel<true, false, true>, pk->maps, pk->p)
                               : cudaLaunchKernelEx(&cfg, conv_chain_kernel<false, false, true>, pk->maps, pk->p);
