@@ -257,7 +257,8 @@ __device__ __forceinline__ void tc_epi_store16(const float (&f)[16], int mode, u
 // kDbg: compiled with the timeline stamps and the timing-experiment switches; kBsrn: with the GELU and the border-class
 // bias table (BSRN).  The production instantiations carry only what their network needs (the single-thread roles pay for
 // every instruction-cache line; the same measure gave the fused chain kernel 3-6 %).
-template <bool kDbg, bool kBsrn>
+// kTail: with the residual / gate operand of group 0 and the pixel-shuffle store (LR_conv, upsampler, FMEN's gates).
+template <bool kDbg, bool kBsrn, bool kTail>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmO0,
                const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ CUtensorMap tmO2,
@@ -513,7 +514,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       ggelu[gi] = kBsrn && g.act == ACT_GELU; gslope[gi] = g.slope;
     }
     const bool g0_bias9 = kBsrn && grp_s[0].bias9 != nullptr;
-    const bool g0_has_res = ng > 0 && grp_s[0].res != nullptr;
+    const bool g0_has_res = kTail && ng > 0 && grp_s[0].res != nullptr;
     const __half* const g0_res = g0_has_res ? grp_s[0].res + grp_s[0].res_coff : nullptr;
     const int g0_res_stride = grp_s[0].res_stride;
     uint32_t t = 0;
@@ -569,7 +570,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (gi == 0 && g0_bias9)   // border class of this thread's pixel
             bias_row = &bias9_s[3 * (y == 0 ? 0 : (y == H - 1 ? 2 : 1)) + (x == 0 ? 0 : (x == W - 1 ? 2 : 1))][c0];
           tc_epi_math16(v, bias_row, ggelu[gi], gslope[gi], has_res, rpre[s & 1][0], rpre[s & 1][1], g.res_after, f);
-          tc_epi_store16(f, gmode[gi], stage_row, c0, swz, valid, ps_out, ps_fp32, b, y, x, H, W);
+          tc_epi_store16(f, kTail ? gmode[gi] : 0, stage_row, c0, swz, valid, ps_out, ps_fp32, b, y, x, H, W);
         };
         // With both MMA warps keeping the tensor pipe busy a tcgen05.ld takes ~0.7k cycles to come back, so
         // the loads of three slots are issued back to back and waited for once (two rounds cover all six)

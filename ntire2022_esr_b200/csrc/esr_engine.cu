@@ -413,17 +413,26 @@ static int plan_tc(Engine* e, const DevGraph& dg, const TcConv& c, const std::st
   }
   const int grid = std::min(p.n_items, e->num_sms);
   if (!e->attr_tc) {   // function attributes are per device: tracked per handle (a handle is bound to one device)
-    CUDA_TRY(e, cudaFuncSetAttribute(conv_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-    CUDA_TRY(e, cudaFuncSetAttribute(conv_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-    CUDA_TRY(e, cudaFuncSetAttribute(conv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+    CUDA_TRY(e, cudaFuncSetAttribute(conv_tc_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+    CUDA_TRY(e, cudaFuncSetAttribute(conv_tc_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+    CUDA_TRY(e, cudaFuncSetAttribute(conv_tc_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+    CUDA_TRY(e, cudaFuncSetAttribute(conv_tc_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+    CUDA_TRY(e, cudaFuncSetAttribute(conv_tc_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
     e->attr_tc = true;
   }
-  // instantiation: instrumented (timeline / timing experiments), BSRN (GELU, border-class bias), or plain
-  bool bsrn = false;
-  for (auto& gd : c.groups) bsrn = bsrn || gd.act == ACT_GELU || gd.off_bias9 >= 0;
-  const int variant = (p.dbg != nullptr || p.dbg_flags != 0) ? 2 : (bsrn ? 1 : 0);
+  // instantiation by feature set: instrumented (timeline / timing experiments), BSRN (GELU, border-class bias), tail
+  // (residual / gate operand, pixel-shuffle store), or plain
+  bool bsrn = false, tail = false;
+  for (auto& gd : c.groups) {
+    bsrn = bsrn || gd.act == ACT_GELU || gd.off_bias9 >= 0;
+    tail = tail || gd.res != BUF_NONE || gd.mode != 0;
+  }
+  const int variant = (p.dbg != nullptr || p.dbg_flags != 0) ? 4 : ((bsrn ? 2 : 0) + (tail ? 1 : 0));
   pl.launches.push_back(Launch{"conv_tc:" + name, [pk, grid, smem, variant](cudaStream_t s) {
-                                 auto kern = variant == 2 ? conv_tc_kernel<true, true> : (variant == 1 ? conv_tc_kernel<false, true> : conv_tc_kernel<false, false>);
+                                 auto kern = variant == 4 ? conv_tc_kernel<true, true, true>
+                                           : variant == 3 ? conv_tc_kernel<false, true, true>
+                                           : variant == 2 ? conv_tc_kernel<false, true, false>
+                                           : variant == 1 ? conv_tc_kernel<false, false, true> : conv_tc_kernel<false, false, false>;
                                  return launch_k(kern, dim3(grid), dim3(TC_THREADS), smem, s, pk->tmA, pk->tmO[0], pk->tmO[1],
                                                  pk->tmO[2], pk->p);
                                }});
