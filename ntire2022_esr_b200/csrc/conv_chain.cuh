@@ -266,7 +266,9 @@ __device__ __forceinline__ long long global_timer_ns() {
 // kTail: compiled with the global residual / gate operand and the pixel-shuffle store (the tail chain and FMEN's chains);
 // the block chains (RFDB, IMDB, RLFB) use the instantiation without them
 // kCtr: compiled with the centre block (the distillation 1x1 of an RFDB stage: its weights, MMAs, accumulator, epilogue unit)
-template <bool kPw, bool kU8 = false, bool kDbg = false, bool kTail = true, bool kCtr = true>
+// kDyn: compiled with the dynamic band scheduling (more bands than clusters in flight); the single-pass instantiations
+// (every cluster processes exactly one band: batch 1 at 256 x 256) drop the scheduling code from all five roles
+template <bool kPw, bool kU8 = false, bool kDbg = false, bool kTail = true, bool kCtr = true, bool kDyn = true>
 __global__ void __launch_bounds__(CH_THREADS, 1)
 conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ ChainParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -311,7 +313,7 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
   // the k-th is loading and posts it into every CTA of the cluster).  A band only depends on lower-numbered bands, and
   // a lower-numbered band is always held by a running (or finished) cluster, so the kernel makes progress with any
   // number of co-resident clusters - also next to kernels of other streams.
-  const bool dyn_sched = n_items > (int)ncl;
+  const bool dyn_sched = kDyn && n_items > (int)ncl;
   auto next_item = [&](uint32_t k) -> int {   // k-th band of this cluster, k >= 1
     if (!dyn_sched) return n_items;
     mbar_wait_cl(&sched_bar[k & 1u], ((k - 1) >> 1) & 1u);

@@ -452,14 +452,16 @@ static int chain_clusters(Engine* e, int strips) {
   if (!e->has_gpu) return e->num_sms / strips;
   if (e->chain_capacity[strips] == 0) {
     if (!e->attr_chain) {
-      if (cudaFuncSetAttribute(conv_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemMax) != cudaSuccess ||
-          cudaFuncSetAttribute(conv_chain_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemMax) != cudaSuccess ||
-          cudaFuncSetAttribute(conv_chain_kernel<false, true, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemMax) != cudaSuccess ||
-          cudaFuncSetAttribute(conv_chain_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemMax) != cudaSuccess ||
-          cudaFuncSetAttribute(conv_chain_kernel<false, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemMax) != cudaSuccess ||
-          cudaFuncSetAttribute(conv_chain_kernel<false, false, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemMax) != cudaSuccess ||
-          cudaFuncSetAttribute(conv_chain_kernel<false, false, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemMax) != cudaSuccess ||
-          cudaFuncSetAttribute(conv_chain_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemMax) != cudaSuccess ||
+      auto optin = [](auto kern) { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemMax) == cudaSuccess; };
+      const bool ok_attr =
+          optin(conv_chain_kernel<false, false, false, true, true, true>) && optin(conv_chain_kernel<false, false, false, true, true, false>) &&
+          optin(conv_chain_kernel<false, false, false, true, false, true>) && optin(conv_chain_kernel<false, false, false, true, false, false>) &&
+          optin(conv_chain_kernel<false, false, false, false, true, true>) && optin(conv_chain_kernel<false, false, false, false, true, false>) &&
+          optin(conv_chain_kernel<false, false, false, false, false, true>) && optin(conv_chain_kernel<false, false, false, false, false, false>) &&
+          optin(conv_chain_kernel<false, true>) && optin(conv_chain_kernel<false, true, false, true, false, true>) &&
+          optin(conv_chain_kernel<false, true, false, true, false, false>) &&
+          optin(conv_chain_kernel<false, false, true>) && optin(conv_chain_kernel<true, false, true>);
+      if (!ok_attr ||
           cudaFuncSetAttribute(conv_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemMax) != cudaSuccess) {
         cudaGetLastError();
         return 0;
@@ -725,28 +727,35 @@ static int plan_chain(Engine* e, const DevGraph& dg, const ChainDecl& ch, const 
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = g_pdl ? 2 : 1;
-    if (pk->p.ps_u8) {
-      bool c = false;
-      for (int l = 0; l < pk->p.n_layers; ++l) c = c || pk->p.L[l].ctr_n > 0;
-      return c ? cudaLaunchKernelEx(&cfg, conv_chain_kernel<false, true>, pk->maps, pk->p)
-               : cudaLaunchKernelEx(&cfg, conv_chain_kernel<false, true, false, true, false>, pk->maps, pk->p);
-    }
-    if (pk->p.dbg != nullptr || pk->p.dbg_flags != 0)     // timeline stamps / timing experiments: the instrumented instantiations
-      return pk->p.pw.enabled ? cudaLaunchKernelEx(&cfg, conv_chain_kernel<true, false, true>, pk->maps, pk->p)
-                              : cudaLaunchKernelEx(&cfg, conv_chain_kernel<false, false, true>, pk->maps, pk->p);
-    if (pk->p.pw.enabled) return cudaLaunchKernelEx(&cfg, conv_chain_kernel<true>, pk->maps, pk->p);
-    // the block chains get the instantiation without the code they do not need (measured: 33.2 vs 34.7 us per RFDB chain
-    // without the tail features): `tail` = any layer with a global residual / gate operand or the pixel-shuffle store,
-    // `ctr` = any layer with a centre block
+    // Instantiation by feature set (the single-thread roles pay for every instruction-cache line: each of these cuts
+    // measured 3-6 % off a chain): `tail` = any layer with a global residual / gate operand or the pixel-shuffle store,
+    // `ctr` = any layer with a centre block, `dyn` = more bands than clusters in flight (dynamic band scheduling)
     bool tail = false, ctr = false;
     for (int l = 0; l < pk->p.n_layers; ++l) {
       tail = tail || pk->p.L[l].res != nullptr || pk->p.L[l].mode0 != 0;
       ctr = ctr || pk->p.L[l].ctr_n > 0;
     }
-    if (tail && ctr) return cudaLaunchKernelEx(&cfg, conv_chain_kernel<false>, pk->maps, pk->p);
-    if (tail) return cudaLaunchKernelEx(&cfg, conv_chain_kernel<false, false, false, true, false>, pk->maps, pk->p);
-    if (ctr) return cudaLaunchKernelEx(&cfg, conv_chain_kernel<false, false, false, false>, pk->maps, pk->p);
-    return cudaLaunchKernelEx(&cfg, conv_chain_kernel<false, false, false, false, false>, pk->maps, pk->p);
+    const bool dyn = pk->p.n_items * strips > grid;
+    if (pk->p.ps_u8) {
+      if (ctr) return cudaLaunchKernelEx(&cfg, conv_chain_kernel<false, true>, pk->maps, pk->p);
+      return dyn ? cudaLaunchKernelEx(&cfg, conv_chain_kernel<false, true, false, true, false, true>, pk->maps, pk->p)
+                 : cudaLaunchKernelEx(&cfg, conv_chain_kernel<false, true, false, true, false, false>, pk->maps, pk->p);
+    }
+    if (pk->p.dbg != nullptr || pk->p.dbg_flags != 0)     // timeline stamps / timing experiments: the instrumented instantiations
+      return pk->p.pw.enabled ? cudaLaunchKernelEx(&cfg, conv_chain_kernel<true, false, true>, pk->maps, pk->p)
+                              : cudaLaunchKernelEx(&cfg, conv_chain_kernel<false, false, true>, pk->maps, pk->p);
+    if (pk->p.pw.enabled) return cudaLaunchKernelEx(&cfg, conv_chain_kernel<true>, pk->maps, pk->p);
+    const int v = (tail ? 4 : 0) + (ctr ? 2 : 0) + (dyn ? 1 : 0);
+    switch (v) {
+      case 7: return cudaLaunchKernelEx(&cfg, conv_chain_kernel<false, false, false, true, true, true>, pk->maps, pk->p);
+      case 6: return cudaLaunchKernelEx(&cfg, conv_chain_kernel<false, false, false, true, true, false>, pk->maps, pk->p);
+      case 5: return cudaLaunchKernelEx(&cfg, conv_chain_kernel<false, false, false, true, false, true>, pk->maps, pk->p);
+      case 4: return cudaLaunchKernelEx(&cfg, conv_chain_kernel<false, false, false, true, false, false>, pk->maps, pk->p);
+      case 3: return cudaLaunchKernelEx(&cfg, conv_chain_kernel<false, false, false, false, true, true>, pk->maps, pk->p);
+      case 2: return cudaLaunchKernelEx(&cfg, conv_chain_kernel<false, false, false, false, true, false>, pk->maps, pk->p);
+      case 1: return cudaLaunchKernelEx(&cfg, conv_chain_kernel<false, false, false, false, false, true>, pk->maps, pk->p);
+      default: return cudaLaunchKernelEx(&cfg, conv_chain_kernel<false, false, false, false, false, false>, pk->maps, pk->p);
+    }
   }});
   if (name_out) *name_out = name;
   return ESR_OK;
