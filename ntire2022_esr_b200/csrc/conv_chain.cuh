@@ -367,8 +367,8 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
     // ================================ TMA producer ================================
     if (elect_one()) {
       // the identity block (constant: does not depend on the previous kernel) - only chains with a block residual have it
-      mbar_arrive_expect_tx(&ident_bar, (uint32_t)p.ident_bytes);
-      if (p.ident_bytes > 0) bulk_load_1d(smem + p.ident_off, p.ident, (uint32_t)p.ident_bytes, &ident_bar);
+      mbar_arrive_expect_tx(&ident_bar, kCtr ? (uint32_t)p.ident_bytes : 0u);
+      if (kCtr && p.ident_bytes > 0) bulk_load_1d(smem + p.ident_off, p.ident, (uint32_t)p.ident_bytes, &ident_bar);
       griddep_wait();
       uint32_t g = 0, ctr_cnt = 0, ring_cnt = 0, items = 0;
       for (int item = (int)cid; item < n_items; ++items, item = next_item(items)) {
@@ -579,7 +579,7 @@ conv_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
         if (l != cur_l) {
           const ChLayer& Lr = p.L[l];
           np = Lr.np; ks = no_mma ? 0 : Lr.ksteps; ctr_n = kCtr ? Lr.ctr_n : 0; acc_col = Lr.acc_col; part_bytes = Lr.part_bytes;
-          res_ident = Lr.res_smem != 0;
+          res_ident = kCtr && Lr.res_smem != 0;   // (the identity tap only occurs in RFDB stages: same instantiations as the centre block)
           cur_l = l;
         }
         const uint32_t pb16 = (uint32_t)part_bytes >> 4;

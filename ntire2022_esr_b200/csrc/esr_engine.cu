@@ -733,7 +733,7 @@ static int plan_chain(Engine* e, const DevGraph& dg, const ChainDecl& ch, const 
     bool tail = false, ctr = false;
     for (int l = 0; l < pk->p.n_layers; ++l) {
       tail = tail || pk->p.L[l].res != nullptr || pk->p.L[l].mode0 != 0;
-      ctr = ctr || pk->p.L[l].ctr_n > 0;
+      ctr = ctr || pk->p.L[l].ctr_n > 0 || pk->p.L[l].res_smem != 0;   // (the identity tap lives in the same instantiations)
     }
     const bool dyn = pk->p.n_items * strips > grid;
     if (pk->p.ps_u8) {
