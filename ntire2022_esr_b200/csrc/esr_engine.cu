@@ -65,7 +65,7 @@ struct Engine {
   DevGraph graphs[2];  // 0: CUDA-core graph (fp32 mode, and fp16 when tc is off), 1: tcgen05 graph
   std::string err;
   // options
-  int opt_tc = 1, opt_shift_mode = 0, opt_use_graph = 1, opt_rows_per_item = 0, opt_timeline = 0, opt_dbg_flags = 0, opt_acc_slots = 4, opt_pdl = 0;
+  int opt_tc = 1, opt_shift_mode = 0, opt_use_graph = 1, opt_rows_per_item = 0, opt_timeline = 0, opt_dbg_flags = 0, opt_acc_slots = 4, opt_pdl = 0, opt_esa_front_old = 0;
   int opt_chain = 1, opt_chain_store_all = 0, opt_chain_mask = -1;   // mask: bit k enables the k-th chain of the graph (debug)
   int opt_chain_pw = 0;   // 1: the pointwise layer behind a chain (RFDB c5, IMDB conv1x1) runs as the chain's last stage.  Off by
                           // default: measured 385.6 vs 375.2 us per RFDN forward at batch 1 - the 144-column epilogue of c5 is
@@ -978,7 +978,11 @@ static int build_plan(Engine* e, Plan& pl) {
         p.B = B; p.H = H; p.W = W;
         esa_dims(H, W, p.H2, p.W2, p.H3, p.W3);
         const int nblk = B * ((p.H3 + 3) / 4) * ((p.W3 + 3) / 4);
+        const int f4 = op.f > 0 ? (op.f + 3) / 4 : 4;    // 4-channel groups of the ESA width
+        const int variant = e->opt_esa_front_old ? 0 : f4;
         pl.launches.push_back(Launch{"esa_conv2_pool:" + op.name, [=](cudaStream_t s) {
+          if (variant == 3) return launch_k(k_esa_conv2_pool4<3>, dim3(nblk), dim3(192), 0, s, p);
+          if (variant == 4) return launch_k(k_esa_conv2_pool4<4>, dim3(nblk), dim3(256), 0, s, p);
           return launch_k(k_esa_conv2_pool<__half>, dim3(nblk), dim3(128), 0, s, p);
         }});
         break;
@@ -1543,6 +1547,7 @@ int esr_set_option(esr_handle* h, const char* key, int value) {
   else if (k == "tc_timeline") h->opt_timeline = value ? 1 : 0;
   else if (k == "tc_dbg_flags") h->opt_dbg_flags = value;
   else if (k == "tc_acc_slots") h->opt_acc_slots = value == 4 ? 4 : 2;
+  else if (k == "esa_front_old") h->opt_esa_front_old = value ? 1 : 0;
   else if (k == "use_pdl") h->opt_pdl = value < 0 || value > 2 ? 0 : value;
   else if (k == "chain_enable") h->opt_chain = value == 2 ? 2 : (value ? 1 : 0);
   else if (k == "chain_store_all") h->opt_chain_store_all = value ? 1 : 0;

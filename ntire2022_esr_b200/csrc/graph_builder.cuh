@@ -482,6 +482,7 @@ struct GraphBuilder {
       const Mat m = conv_mat(p + "conv2", f, f, 3);
       OpDecl op;
       op.kind = OP_ESA_FRONT;
+      op.f = f;
       op.name = p + "conv2+max_pool";
       op.tab = dense_table(m, 16, 16, pos_id(), pos_id());
       op.in = eb.esa; op.in_coff = 0; op.out = eb.s3a;

@@ -894,6 +894,107 @@ __global__ void __launch_bounds__(128) k_esa_conv2_pool(const EsaFrontParams p) 
   }
 }
 
+// The same with the register tile cut to the channels that exist: F4 = number of 4-channel groups of the ESA width
+// (3 for f = 10 / 12: RFDN, RFDN40, the pruned RFDN; 4 for f = 16).  thread = 4 conv2 pixels x 4 output channels, 64 * F4
+// threads: f = 12 does 9 * 12 * 12 instead of 9 * 16 * 16 multiply-adds per pixel and runs 6 warps instead of 4 (the
+// kernel is FMA-issue bound at one warp per scheduler).  Padded input channels are zero and padded weights are zero, so
+// skipping them changes no bit of the result; padded output channels are written as the zeros they would come out as.
+template <int F4>
+__global__ void __launch_bounds__(64 * F4) k_esa_conv2_pool4(const EsaFrontParams p) {
+  __shared__ __align__(16) float wsm[9 * 256];
+  __shared__ __align__(16) float tile[16][16][16];   // conv2 outputs [y][x][c]
+  constexpr int NT = 64 * F4;
+  {
+    const float4* src = reinterpret_cast<const float4*>(p.w);
+    float4* dst = reinterpret_cast<float4*>(wsm);
+    for (int j = threadIdx.x; j < 9 * 64; j += NT) dst[j] = __ldg(src + j);
+  }
+  pdl_wait();
+  __syncthreads();
+  const int tx3 = (p.W3 + 3) >> 2, ty3 = (p.H3 + 3) >> 2;
+  const int bx = blockIdx.x % tx3, by = (blockIdx.x / tx3) % ty3, b = blockIdx.x / (tx3 * ty3);
+  const int cy0 = by * 12, cx0 = bx * 12;   // conv2 origin of this tile (pooled origin * 3)
+  {
+    const int g4 = threadIdx.x % F4, quad = (threadIdx.x / F4) & 3, ty = threadIdx.x / (4 * F4);
+    const int cy = cy0 + ty, cx = cx0 + quad * 4;
+    float acc[4][4];
+    {
+      const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias) + g4);
+#pragma unroll
+      for (int px = 0; px < 4; ++px) { acc[px][0] = bv.x; acc[px][1] = bv.y; acc[px][2] = bv.z; acc[px][3] = bv.w; }
+    }
+    const __half* in = reinterpret_cast<const __half*>(p.in);
+    if (cy < p.H2) {
+#pragma unroll 1
+      for (int ky = 0; ky < 3; ++ky) {
+        const __half* row = in + ((long long)b * p.H + 2 * cy + ky) * p.W * p.in_stride + p.in_coff;
+        uint4 raw[9][2];
+#pragma unroll
+        for (int ip = 0; ip < 9; ++ip) {
+          const int ix = 2 * cx + ip;
+          if (ix < p.W) {
+            const uint4* src = reinterpret_cast<const uint4*>(row + (long long)ix * p.in_stride);
+            raw[ip][0] = src[0];
+            if (F4 > 2) raw[ip][1] = src[1];
+          } else {
+            raw[ip][0] = make_uint4(0, 0, 0, 0);
+            raw[ip][1] = make_uint4(0, 0, 0, 0);
+          }
+        }
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const float* wt = wsm + (ky * 3 + kx) * 256 + g4 * 4;
+#pragma unroll
+          for (int c4 = 0; c4 < F4; ++c4) {          // input channels 4 c4 .. 4 c4 + 3
+            float xv[4][4];
+#pragma unroll
+            for (int px = 0; px < 4; ++px) {
+              const __half2* h2 = reinterpret_cast<const __half2*>(&raw[2 * px + kx][c4 >> 1]) + 2 * (c4 & 1);
+              const float2 f0 = __half22float2(h2[0]), f1 = __half22float2(h2[1]);
+              xv[px][0] = f0.x; xv[px][1] = f0.y; xv[px][2] = f1.x; xv[px][3] = f1.y;
+            }
+#pragma unroll
+            for (int ci = 0; ci < 4; ++ci) {
+              const float4 w0 = *reinterpret_cast<const float4*>(wt + (c4 * 4 + ci) * 16);
+#pragma unroll
+              for (int px = 0; px < 4; ++px) {
+                acc[px][0] = fmaf(xv[px][ci], w0.x, acc[px][0]);
+                acc[px][1] = fmaf(xv[px][ci], w0.y, acc[px][1]);
+                acc[px][2] = fmaf(xv[px][ci], w0.z, acc[px][2]);
+                acc[px][3] = fmaf(xv[px][ci], w0.w, acc[px][3]);
+              }
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int px = 0; px < 4; ++px) {
+      // positions outside the conv2 map never win a max
+      const bool ok = cy < p.H2 && cx + px < p.W2;
+      *reinterpret_cast<float4*>(&tile[ty][quad * 4 + px][g4 * 4]) =
+          ok ? make_float4(acc[px][0], acc[px][1], acc[px][2], acc[px][3]) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    }
+  }
+  __syncthreads();
+  // 4x4 pooled outputs x 16 channels = 256 values
+  for (int o = threadIdx.x; o < 256; o += NT) {
+    const int c = o & 15, pxl = (o >> 4) & 3, pyl = o >> 6;
+    const int py = by * 4 + pyl, pxg = bx * 4 + pxl;
+    if (py < p.H3 && pxg < p.W3) {
+      float m = 0.f;                            // channels beyond the ESA width: what bias 0 + zero weights give
+      if (c < 4 * F4) {
+        m = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 7; ++i)
+#pragma unroll
+          for (int j = 0; j < 7; ++j) m = fmaxf(m, tile[3 * pyl + i][3 * pxl + j][c]);
+      }
+      p.out[(((long long)b * p.H3 + py) * p.W3 + pxg) * 16 + c] = m;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Fused ESA low-resolution chain (fp16 path) on the pooled map: [conv_max + ReLU, conv3 + ReLU] (RFDN;
 // none for RLFN) followed by the last 3x3 composed with conv4 (f -> nf, no activation) - one launch,
