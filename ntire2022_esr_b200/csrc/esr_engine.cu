@@ -1007,9 +1007,14 @@ static int build_plan(Engine* e, Plan& pl) {
         if (!e->attr_esa) {
           CUDA_TRY(e, cudaFuncSetAttribute(k_esa_chain<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
           CUDA_TRY(e, cudaFuncSetAttribute(k_esa_chain<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          CUDA_TRY(e, cudaFuncSetAttribute(k_esa_chain<6, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          CUDA_TRY(e, cudaFuncSetAttribute(k_esa_chain<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
           e->attr_esa = true;
         }
+        const bool f3 = !e->opt_esa_front_old && op.f > 0 && op.f <= 12;   // ESA width 10 / 12: three 4-channel groups
         pl.launches.push_back(Launch{"esa_chain:" + op.name, [=](cudaStream_t s) {
+          if (f3) return small ? launch_k(k_esa_chain<4, 3>, dim3(nblk), dim3(256), smem, s, p)
+                               : launch_k(k_esa_chain<6, 3>, dim3(nblk), dim3(256), smem, s, p);
           if (small) return launch_k(k_esa_chain<4>, dim3(nblk), dim3(256), smem, s, p);
           return launch_k(k_esa_chain<6>, dim3(nblk), dim3(256), smem, s, p);
         }});

@@ -494,6 +494,7 @@ struct GraphBuilder {
     std::fill(c4nb.b.begin(), c4nb.b.end(), 0.0);   // b4 travels with cf'
     OpDecl ch;
     ch.kind = OP_ESA_CHAIN;
+    ch.f = f;
     ch.in = eb.s3a; ch.out = m3buf;
     ch.macs_res = BK_S3;
     std::string last_name = "conv3";
