@@ -1031,8 +1031,10 @@ static int build_plan(Engine* e, Plan& pl) {
         p.B = B; p.H = H; p.W = W; p.cg8 = op.cgroups;
         const long long total = (long long)B * H * W * op.cgroups;
         const int nblk = (int)std::min<long long>((total + 255) / 256, (long long)e->num_sms * 8);
+        const bool small_idx = !e->opt_esa_front_old && total + (long long)nblk * 256 < (1ll << 31);
         pl.launches.push_back(Launch{"esa_apply2:" + op.name, [=](cudaStream_t s) {
-          return launch_k(k_esa_apply2<__half>, dim3(nblk), dim3(256), 0, s, p);
+          if (!small_idx) return launch_k(k_esa_apply2<__half>, dim3(nblk), dim3(256), 0, s, p);
+          return launch_k(k_esa_apply2<__half, unsigned>, dim3(nblk), dim3(256), 0, s, p);
         }});
         break;
       }

@@ -742,16 +742,19 @@ struct EsaApply2Params {
   void* out; int out_stride, out_coff;
   int B, H, W, cg8;   // cg8: 8-channel groups per pixel
 };
-template <typename T>
+// I = index type: unsigned when the work-item count fits 32 bits (the 64-bit divisions of the index decomposition cost
+// more instructions than the rest of a work item)
+template <typename T, typename I = long long>
 __global__ void __launch_bounds__(256, 4) k_esa_apply2(const EsaApply2Params p) {
   pdl_wait();
-  const long long total = (long long)p.B * p.H * p.W * p.cg8;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(idx % p.cg8);
-    const long long pix = idx / p.cg8;
-    const int x = (int)(pix % p.W);
-    const int y = (int)((pix / p.W) % p.H);
-    const int b = (int)(pix / ((long long)p.W * p.H));
+  const I total = (I)((long long)p.B * p.H * p.W * p.cg8);
+  for (I idx = (I)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (I)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % (I)p.cg8);
+    const I pixi = idx / (I)p.cg8;
+    const long long pix = (long long)pixi;
+    const int x = (int)(pixi % (I)p.W);
+    const int y = (int)((pixi / (I)p.W) % (I)p.H);
+    const int b = (int)(pixi / ((I)p.W * (I)p.H));
     const float sy = fmaxf(((float)y + 0.5f) * ((float)p.H3 / (float)p.H) - 0.5f, 0.f);
     const float sx = fmaxf(((float)x + 0.5f) * ((float)p.W3 / (float)p.W) - 0.5f, 0.f);
     const int y0 = min((int)sy, p.H3 - 1), x0 = min((int)sx, p.W3 - 1);
