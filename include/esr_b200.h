@@ -114,8 +114,12 @@ int esr_profile_launches(esr_handle* h, const void* in_nchw, void* out_nchw, int
                          void* workspace, size_t workspace_bytes, int reps, float* ms_out, int n, void* stream);
 
 /* Runtime knobs (tuning / A-B measurements): "tc_enable" (fp16: tcgen05 convolutions on/off),
- * "use_graph", "use_pdl" (programmatic dependent launch between the kernels of a forward),
- * "tc_rows_per_item", "tc_acc_slots", "tc_timeline", "tc_dbg_flags". */
+ * "chain_enable" (0 per-layer kernels only, 1 fused 3x3 chains where the bands of one image fit the device, 2 always),
+ * "chain_pw" (c5 / conv1x1 as the chain's last stage: measured slower, off), "chain_store_all", "chain_mask",
+ * "use_graph", "use_pdl" (programmatic dependent launch: 1 every kernel, 2 only the small ESA kernels; measured slower),
+ * "esa_front_old" (the ESA kernels before their specialisation on the ESA width), "tc_rows_per_item", "tc_acc_slots",
+ * "tc_timeline", "tc_dbg_flags" (the last two select the instrumented kernel instantiations).  Changing an option drops
+ * the cached launch plans. */
 int esr_set_option(esr_handle* h, const char* key, int value);
 
 /* Debug aid: with option "tc_timeline" = 1 every tcgen05 launch records clock64 stamps of block 0
